@@ -1,0 +1,167 @@
+/*
+ * yolopp.h — C ABI of the B200-native YOLO detection post-processing path.
+ *
+ * Drop-in boundary for ONE hot path of zhanggefan/mmdet-yolov4 (an MMDetection 2.12 fork):
+ *
+ *   YOLOCSPHead.get_bboxes / _get_bboxes_single   mmdet/models/dense_heads/yolocsp_head.py:225-382
+ *   YOLOV3Head.get_bboxes / _get_bboxes           mmdet/models/dense_heads/yolo_head.py:171-393
+ *   YOLOV4BBoxCoder.decode                        mmdet/core/bbox/coder/yolov4_bbox_coder.py:39-67
+ *   YOLOBBoxCoder.decode                          mmdet/core/bbox/coder/yolo_bbox_coder.py:60-89
+ *   AnchorGenerator.grid_anchors (YOLO)           mmdet/core/anchor/anchor_generator.py:207-270,639-665
+ *   multiclass_nms                                mmdet/core/post_processing/bbox_nms.py:7-93
+ *   mmcv.ops.nms.batched_nms / nms / nms_cpu      third party, mmcv-full 1.3.2..1.4.0 (call site bbox_nms.py:2,84)
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer marked "device" is a CUDA device pointer on the
+ *     current device, every pointer marked "host" is ordinary host memory.
+ *   - the library never allocates, frees or retains device memory: the caller owns inputs, outputs
+ *     and the workspace (size from yolopp_workspace_bytes).
+ *   - every call is asynchronous on the cudaStream_t it is given (passed as void*), performs no host
+ *     synchronisation, and is re-entrant (no global state).
+ *   - return value: 0 = ok, YOLOPP_E_* otherwise. CUDA launch errors are returned as
+ *     YOLOPP_E_CUDA + cudaError_t. Data-dependent failures (candidate-buffer overflow) cannot be
+ *     known without a sync; they are written to the `status` word of the output block, which the
+ *     caller reads together with the counts.
+ *   - arithmetic is IEEE fp32 with one rounding per reference operation and NO fused multiply-add
+ *     contraction; exp() is the canonical polynomial defined in DESIGN.md §"Canonical arithmetic"
+ *     (the same on CPU and GPU, <= 1.02 ulp), so results are bit-reproducible.
+ *   - ties are broken canonically (score desc, then flat candidate index asc) — DESIGN.md §"Ties".
+ */
+#ifndef YOLOPP_H_
+#define YOLOPP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YOLOPP_ABI_VERSION 1
+
+#define YOLOPP_MAX_LEVELS 8
+#define YOLOPP_MAX_ANCHORS 8      /* base anchors per level (mmdet asserts the same count on every level) */
+#define YOLOPP_MAX_CLASSES 4096   /* 12-bit class field in the sort key */
+#define YOLOPP_MAX_ROWS (1 << 20) /* 20-bit row field in the sort key: rows entering multiclass_nms per image */
+
+/* status / error codes */
+#define YOLOPP_OK 0
+#define YOLOPP_E_INVALID 1        /* bad argument / unsupported configuration */
+#define YOLOPP_E_WORKSPACE 2      /* workspace too small */
+#define YOLOPP_E_OVERFLOW 3       /* (status word) a candidate bin overflowed its capacity */
+#define YOLOPP_E_NO_DEVICE 4      /* no CUDA device / not an sm_100 device */
+#define YOLOPP_E_CUDA 1000        /* + cudaError_t */
+
+/* decode conventions */
+#define YOLOPP_MODE_CSP 0 /* YOLOCSPHead + YOLOV4BBoxCoder: sigmoid on every attr, xy=(2s-1)*stride+c, wh=(2s)^2*a,
+                             ONE objectness top-k per image over all levels, score = cls*conf, then score > thr */
+#define YOLOPP_MODE_V3 1  /* YOLOV3Head + YOLOBBoxCoder: xy=(s-0.5)*stride+c, wh=exp(t)*a, objectness top-k PER LEVEL,
+                             conf >= conf_thr row filter, cls > thr tested BEFORE score = cls*conf */
+
+/*
+ * Everything the reference reads from the head instance, the test_cfg and img_metas.
+ *   head instance : yolocsp_head.py:112-114,151,162,170-178 ; yolo_head.py:52-59
+ *   test_cfg      : yolocsp_head.py:345-348,374-376 ; yolo_head.py:281,365,378-384
+ */
+typedef struct yolopp_params {
+    int32_t abi_version;   /* = YOLOPP_ABI_VERSION */
+    int32_t mode;          /* YOLOPP_MODE_* */
+    int32_t batch;         /* B: images in this call */
+    int32_t num_levels;    /* L, in HEAD ORDER (CSP: strides 8,16,32; V3: 32,16,8) */
+    int32_t num_anchors;   /* A base anchors per level */
+    int32_t num_classes;   /* C (ignored when class_agnostic: one class whose score is the objectness) */
+    int32_t class_agnostic;/* YOLOCSPHead(class_agnostic=True): 5 attrs/anchor (yolocsp_head.py:175-178,360) */
+    int32_t height[YOLOPP_MAX_LEVELS];   /* feature-map H per level */
+    int32_t width[YOLOPP_MAX_LEVELS];    /* feature-map W per level */
+    int32_t stride_w[YOLOPP_MAX_LEVELS]; /* anchor-generator stride (x) — anchor_generator.py:256 */
+    int32_t stride_h[YOLOPP_MAX_LEVELS]; /* anchor-generator stride (y) — anchor_generator.py:257 */
+    int32_t coder_stride[YOLOPP_MAX_LEVELS]; /* featmap_strides[l], the `stride` passed to bbox_coder.decode */
+    /* fp32 base anchors exactly as YOLOAnchorGenerator.gen_single_level_base_anchors builds them
+       (x1,y1,x2,y2 computed in double, rounded once to fp32 — anchor_generator.py:655-662). */
+    float base_anchors[YOLOPP_MAX_LEVELS][YOLOPP_MAX_ANCHORS][4];
+    /* test_cfg */
+    int32_t nms_pre;       /* <=0: no top-k */
+    float score_thr;       /* candidates need score > score_thr (strict, fp32) — bbox_nms.py:54 */
+    float conf_thr;        /* V3 only: rows need conf >= conf_thr when conf_thr > 0 — yolo_head.py:365-376 */
+    float iou_thr;         /* nms_cfg['iou_threshold']: suppress when iou > iou_thr (strict) */
+    int32_t nms_offset;    /* nms_cfg.get('offset', 0): 0 or 1 (mmcv nms) */
+    int32_t split_thr;     /* nms_cfg.get('split_thr', 10000) (mmcv batched_nms) */
+    int32_t nms_class_agnostic; /* nms_cfg.get('class_agnostic', False): no class offsets, one NMS problem */
+    int32_t nms_max_num;   /* nms_cfg.get('max_num', -1) */
+    int32_t max_per_img;   /* cfg.max_per_img (<=0: keep all) */
+    int32_t rescale;       /* divide boxes by scale_factor[b][0..3] before NMS */
+    /* capacity knobs (0 = worst case) */
+    int32_t out_capacity;  /* rows of the per-image output block; 0 -> max_per_img (must be > 0 then) */
+    int32_t reserved[7];
+} yolopp_params;
+
+/* Per-detection outputs. All arrays are device memory, [batch][out_capacity] row-major, caller-owned.
+   Rows >= count[b] are left untouched. */
+typedef struct yolopp_outputs {
+    float* dets;        /* [B][cap][5]  x1,y1,x2,y2,score  (bbox_nms.py:86-93) */
+    int64_t* labels;    /* [B][cap]     class id (int64 like the reference) */
+    int32_t* anchors;   /* [B][cap]     parity tap: concatenated anchor index (level-major, (y*W+x)*A+a); may be NULL */
+    int32_t* rows;      /* [B][cap]     parity tap: row index entering multiclass_nms (top-k rank order); may be NULL */
+    int32_t* count;     /* [B]          number of detections */
+    int32_t* num_candidates; /* [B]     candidates that entered batched_nms (bbox_nms.py:66); may be NULL */
+    int32_t* status;    /* [1]          0 or YOLOPP_E_OVERFLOW, data dependent; written every call */
+} yolopp_outputs;
+
+/* ABI version of the loaded library. */
+int yolopp_abi_version(void);
+
+/* Human-readable name of a return code (static storage). */
+const char* yolopp_strerror(int code);
+
+/* Validates `p` and returns the workspace size in bytes needed by yolopp_get_bboxes (0 on invalid params). */
+size_t yolopp_workspace_bytes(const yolopp_params* p);
+
+/*
+ * The whole path (replaces YOLOCSPHead.get_bboxes yolocsp_head.py:225-310 and
+ * YOLOV3Head.get_bboxes yolo_head.py:171-207, with_nms=True).
+ *   level_ptrs   host array[L] of DEVICE pointers; level l is the raw head output (B, A*(5+C), H_l, W_l),
+ *                contiguous NCHW fp32, channel = a*(5+C)+k   (yolocsp_head.py:264-265)
+ *   scale_factors DEVICE pointer [B][4] fp32 (w,h,w,h) or NULL when !rescale (yolocsp_head.py:365-366)
+ *   workspace    DEVICE pointer, >= yolopp_workspace_bytes(p) bytes, 256-byte aligned
+ */
+int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
+                      const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * bbox_coder.decode as a standalone elementwise op (YOLOV4BBoxCoder.decode yolov4_bbox_coder.py:39-67 when
+ * mode == YOLOPP_MODE_CSP, YOLOBBoxCoder.decode yolo_bbox_coder.py:60-89 when mode == YOLOPP_MODE_V3).
+ * bboxes, pred, out: DEVICE [n][4] fp32. `stride` is the scalar stride.
+ */
+int yolopp_coder_decode(int mode, const float* bboxes, const float* pred, float stride, int64_t n, float* out,
+                        void* stream);
+
+/*
+ * mmcv.ops.nms.batched_nms on device (also backs multiclass_nms and nms).
+ *   boxes  DEVICE [n][4], scores DEVICE [n], idxs DEVICE [n] int64 (NULL = class agnostic / plain nms)
+ *   keep   DEVICE [n] int64: indices into the inputs, in the reference's output order
+ *   dets   DEVICE [n][5]
+ *   num_keep DEVICE [1] int32
+ * `max_num` <= 0 keeps all. workspace from yolopp_nms_workspace_bytes(n).
+ */
+size_t yolopp_nms_workspace_bytes(int64_t n);
+int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, float iou_thr,
+                       int nms_offset, int split_thr, int class_agnostic, int max_num, float* dets, int64_t* keep,
+                       int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Bit-reproducible synthetic head tensors (bench / tests): element i of a level tensor gets
+ * mean[k] + std[k] * z(seed, i) where k is its attribute index and z is a fixed-point Irwin-Hall(4)
+ * variate from a counter-based hash — identical bits from the numpy restatement in oracle/synth.py.
+ *   out DEVICE (B, A*(5+C), H, W); attr_mean/attr_std HOST [num_attrib]
+ */
+int yolopp_synth_level(float* out, int32_t batch, int32_t num_anchors, int32_t num_attrib, int32_t hw,
+                       const float* attr_mean, const float* attr_std, uint64_t seed, void* stream);
+
+/* Canonical sigmoid / exp applied elementwise (tests: bit-parity of the transcendental with the oracle). */
+int yolopp_sigmoid(const float* in, float* out, int64_t n, void* stream);
+int yolopp_exp(const float* in, float* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLOPP_H_ */
