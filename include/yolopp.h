@@ -150,12 +150,13 @@ int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* i
 
 /*
  * Bit-reproducible synthetic head tensors (bench / tests): element i of a level tensor gets
- * mean[k] + std[k] * z(seed, i) where k is its attribute index and z is a fixed-point Irwin-Hall(4)
- * variate from a counter-based hash — identical bits from the numpy restatement in oracle/synth.py.
- *   out DEVICE (B, A*(5+C), H, W); attr_mean/attr_std HOST [num_attrib]
+ * mean[g] + std[g] * z(seed, i) where g is the group of its attribute (0: box t0..t3, 1: objectness t4,
+ * 2: class logits) and z is a fixed-point Irwin-Hall(4) variate from a counter-based hash — identical bits
+ * from the C/numpy restatement used by the tests.
+ *   out DEVICE (B, A*num_attrib, H, W) with hw = H*W; mean3/std3 HOST [3]
  */
 int yolopp_synth_level(float* out, int32_t batch, int32_t num_anchors, int32_t num_attrib, int32_t hw,
-                       const float* attr_mean, const float* attr_std, uint64_t seed, void* stream);
+                       const float* mean3, const float* std3, uint64_t seed, void* stream);
 
 /* Canonical sigmoid / exp applied elementwise (tests: bit-parity of the transcendental with the oracle). */
 int yolopp_sigmoid(const float* in, float* out, int64_t n, void* stream);

@@ -1,0 +1,404 @@
+// yolopp_capi.cu — the C ABI of include/yolopp.h: validation, workspace plan, TMA descriptors, launches.
+// Pure CUDA runtime + one driver entry point (cuTensorMapEncodeTiled, resolved through the runtime so the
+// library does not link libcuda). No torch, no allocation, no host synchronisation.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include "../../include/yolopp.h"
+#include "yolopp_kernels.cuh"
+
+using namespace ypp;
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Plan {
+    DevParams d;
+    size_t off_counters, counters_bytes;
+    size_t off_conf_key, off_rank, off_row_anchor, off_row_box, off_bin_keys, off_kept_keys, off_kept_count,
+        off_cls_range, off_glob_keys, off_glob_kept;
+    size_t total;
+    size_t dec_smem;
+    int dec_ctas_per_sm;
+};
+
+#define CHECK_ARG(cond) \
+    do {                \
+        if (!(cond)) return false; \
+    } while (0)
+
+// Validates the params and lays the workspace out. Level pointers are filled in by the caller.
+bool make_plan(const yolopp_params* p, Plan* plan) {
+    CHECK_ARG(p != nullptr);
+    CHECK_ARG(p->abi_version == YOLOPP_ABI_VERSION);
+    CHECK_ARG(p->mode == YOLOPP_MODE_CSP || p->mode == YOLOPP_MODE_V3);
+    CHECK_ARG(p->batch >= 1 && p->batch <= 65535);
+    CHECK_ARG(p->num_levels >= 1 && p->num_levels <= YOLOPP_MAX_LEVELS);
+    CHECK_ARG(p->num_anchors >= 1 && p->num_anchors <= YOLOPP_MAX_ANCHORS);
+    CHECK_ARG(p->nms_offset == 0 || p->nms_offset == 1);
+    const bool agn = p->class_agnostic != 0;
+    CHECK_ARG(!(agn && p->mode == YOLOPP_MODE_V3));  // YOLOV3Head has no class-agnostic variant
+    const int C = agn ? 1 : p->num_classes;
+    CHECK_ARG(C >= 1 && C <= YOLOPP_MAX_CLASSES);
+    const int NA = agn ? 5 : 5 + p->num_classes;
+
+    memset(plan, 0, sizeof(*plan));
+    DevParams& d = plan->d;
+    d.mode = p->mode;
+    d.B = p->batch;
+    d.L = p->num_levels;
+    d.A = p->num_anchors;
+    d.C = C;
+    d.NA = NA;
+    d.agnostic = agn ? 1 : 0;
+    d.score_thr = p->score_thr;
+    d.conf_thr = p->conf_thr;
+    d.iou_thr = p->iou_thr;
+    d.foff = (float)p->nms_offset;
+    d.split_thr = p->split_thr;
+    d.nms_agnostic = p->nms_class_agnostic ? 1 : 0;
+    d.rescale = p->rescale ? 1 : 0;
+
+    long long n_off = 0, m_off = 0;
+    for (int l = 0; l < d.L; ++l) {
+        CHECK_ARG(p->height[l] >= 1 && p->width[l] >= 1 && p->height[l] <= 16384 && p->width[l] <= 16384);
+        CHECK_ARG(p->stride_w[l] >= 1 && p->stride_h[l] >= 1 && p->coder_stride[l] >= 1);
+        LevelDev& lv = d.lv[l];
+        lv.H = p->height[l];
+        lv.W = p->width[l];
+        long long hw = (long long)lv.H * lv.W;
+        CHECK_ARG(hw * d.A < (1 << 24));
+        lv.HW = (int)hw;
+        lv.n_off = (int)n_off;
+        lv.m_off = (int)m_off;
+        lv.sx = (float)p->stride_w[l];
+        lv.sy = (float)p->stride_h[l];
+        lv.cstride = (float)p->coder_stride[l];
+        for (int a = 0; a < d.A; ++a)
+            for (int k = 0; k < 4; ++k) lv.base[a][k] = p->base_anchors[l][a][k];
+        n_off += hw * d.A;
+        m_off = (long long)align_up((size_t)(m_off + hw * d.A), 4);
+        CHECK_ARG(n_off < (1 << 24));
+    }
+    d.N = (int)n_off;
+    d.M_pad = (int)m_off + 64;  // slack: the rank row of a partial last tile is fetched whole
+
+    // top-k segments: CSP = one over all levels (yolocsp_head.py:350-355); V3 = one per level (yolo_head.py:281-302)
+    d.nsegs = (p->mode == YOLOPP_MODE_CSP) ? 1 : d.L;
+    long long row_off = 0;
+    d.ntopk = 0;
+    for (int s = 0; s < d.nsegs; ++s) {
+        SegDev& sg = d.seg[s];
+        sg.first_level = (p->mode == YOLOPP_MODE_CSP) ? 0 : s;
+        sg.num_levels = (p->mode == YOLOPP_MODE_CSP) ? d.L : 1;
+        long long n = 0;
+        for (int q = 0; q < sg.num_levels; ++q) {
+            n += (long long)d.lv[sg.first_level + q].HW * d.A;
+            d.lv[sg.first_level + q].seg = s;
+        }
+        sg.N = (int)n;
+        sg.has_topk = (p->nms_pre > 0 && p->nms_pre < n) ? 1 : 0;
+        sg.k = sg.has_topk ? p->nms_pre : (int)n;
+        if (sg.has_topk) {
+            CHECK_ARG(sg.k <= SEL_MAX_K);  // smem sort capacity of the select kernel
+            d.topk_segs[d.ntopk++] = s;
+        }
+        sg.row_off = (int)row_off;
+        row_off += sg.k;
+    }
+    CHECK_ARG(row_off <= YOLOPP_MAX_ROWS);
+    d.R = (int)row_off;
+
+    int m_eff = -1;
+    if (p->max_per_img > 0) m_eff = p->max_per_img;
+    if (p->nms_max_num > 0) m_eff = (m_eff > 0 && m_eff < p->nms_max_num) ? m_eff : p->nms_max_num;
+    d.m_eff = m_eff;
+    d.out_cap = p->out_capacity > 0 ? p->out_capacity : p->max_per_img;
+    CHECK_ARG(d.out_cap >= 1 && d.out_cap <= SEL_MAX_K);
+    d.Kc = (m_eff > 0 && m_eff < d.R) ? m_eff : d.R;
+    long long rc = (long long)d.R * d.C;
+    long long G = (p->split_thr > 0) ? (p->split_thr < rc ? p->split_thr : rc) : 1;
+    d.G = (int)(G < 1 ? 1 : G);
+
+    // which kernel decodes which level
+    const size_t stage_bytes = align_up((size_t)NA * TILE_T * 4 + TILE_T * 4, 128);
+    plan->dec_smem = 128 + DEC_STAGES * stage_bytes;
+    const bool tma_fits = plan->dec_smem <= 200 * 1024 && NA <= 256;
+    plan->dec_ctas_per_sm = plan->dec_smem <= 100 * 1024 ? 2 : 1;
+    int tma_tiles = 0, ldg_blocks = 0;
+    for (int l = 0; l < d.L; ++l) {
+        LevelDev& lv = d.lv[l];
+        const SegDev& sg = d.seg[lv.seg];
+        const bool sparse = sg.has_topk && (long long)sg.k * 4 <= sg.N;
+        lv.use_tma = (tma_fits && sparse && (lv.HW % 4 == 0)) ? 1 : 0;
+        if (lv.use_tma) {
+            lv.tpp = (lv.HW + TILE_T - 1) / TILE_T;
+            lv.tile0 = tma_tiles;
+            long long t = (long long)lv.tpp * d.B * d.A;
+            CHECK_ARG(tma_tiles + t < (1ll << 30));
+            tma_tiles += (int)t;
+        } else {
+            lv.tpp = (lv.HW + 127) / 128;
+            lv.tile0 = ldg_blocks;
+            long long t = (long long)lv.tpp * d.B * d.A;
+            CHECK_ARG(ldg_blocks + t < (1ll << 30));
+            ldg_blocks += (int)t;
+        }
+    }
+    d.tma_tiles = tma_tiles;
+    d.ldg_blocks = ldg_blocks;
+
+    // workspace layout
+    size_t off = 0;
+    const size_t B = (size_t)d.B, Cc = (size_t)d.C, R = (size_t)d.R;
+    plan->off_counters = off;  // bin_count[B][C] | img_max[B] | img_ncand[B] | flag[B]
+    plan->counters_bytes = align_up((B * Cc + 3 * B) * 4, 256);
+    off += plan->counters_bytes;
+    plan->off_conf_key = off;
+    off += align_up(B * d.M_pad * 4, 256);
+    plan->off_rank = off;
+    off += align_up(B * d.M_pad * 4, 256);
+    plan->off_row_anchor = off;
+    off += align_up(B * R * 4, 256);
+    plan->off_row_box = off;
+    off += align_up(B * R * 16, 256);
+    plan->off_bin_keys = off;
+    off += align_up(B * Cc * R * 8, 256);
+    plan->off_kept_keys = off;
+    off += align_up(B * Cc * (size_t)d.Kc * 8, 256);
+    plan->off_kept_count = off;
+    off += align_up(B * Cc * 4, 256);
+    plan->off_cls_range = off;
+    off += align_up(B * Cc * 16, 256);
+    plan->off_glob_keys = off;
+    off += align_up(B * (size_t)d.G * 8, 256);
+    plan->off_glob_kept = off;
+    off += align_up(B * (size_t)d.out_cap * 8, 256);
+    plan->total = off;
+    return true;
+}
+
+void bind_workspace(Plan* plan, void* ws) {
+    unsigned char* w = (unsigned char*)ws;
+    DevParams& d = plan->d;
+    const size_t B = (size_t)d.B, Cc = (size_t)d.C;
+    int* counters = (int*)(w + plan->off_counters);
+    d.bin_count = counters;
+    d.img_max = (uint32_t*)(counters + B * Cc);
+    d.img_ncand = counters + B * Cc + B;
+    d.flag = counters + B * Cc + 2 * B;
+    d.conf_key = (uint32_t*)(w + plan->off_conf_key);
+    d.rank = (uint32_t*)(w + plan->off_rank);
+    d.row_anchor = (int*)(w + plan->off_row_anchor);
+    d.row_box = (float4*)(w + plan->off_row_box);
+    d.bin_keys = (u64*)(w + plan->off_bin_keys);
+    d.kept_keys = (u64*)(w + plan->off_kept_keys);
+    d.kept_count = (int*)(w + plan->off_kept_count);
+    d.cls_range = (float4*)(w + plan->off_cls_range);
+    d.glob_keys = (u64*)(w + plan->off_glob_keys);
+    d.glob_kept = (u64*)(w + plan->off_glob_kept);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;  // resolved once; the driver symbol never changes
+    if (fn) return fn;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess) return nullptr;
+    if (qres != cudaDriverEntryPointSuccess) return nullptr;
+    fn = (EncodeTiledFn)sym;
+    return fn;
+}
+
+inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? YOLOPP_OK : YOLOPP_E_CUDA + (int)e; }
+
+int device_check() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return YOLOPP_E_NO_DEVICE;
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return YOLOPP_E_NO_DEVICE;
+    if (major != 10) return YOLOPP_E_NO_DEVICE;  // sm_100a only: no other code path exists
+    return YOLOPP_OK;
+}
+
+int sm_count() {
+    int dev = 0, n = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yolopp_abi_version(void) { return YOLOPP_ABI_VERSION; }
+
+const char* yolopp_strerror(int code) {
+    switch (code) {
+        case YOLOPP_OK: return "ok";
+        case YOLOPP_E_INVALID: return "invalid argument or unsupported configuration";
+        case YOLOPP_E_WORKSPACE: return "workspace too small";
+        case YOLOPP_E_OVERFLOW: return "output capacity overflow";
+        case YOLOPP_E_NO_DEVICE: return "no sm_100 CUDA device";
+        default: return code >= YOLOPP_E_CUDA ? "CUDA error (code - 1000 = cudaError_t)" : "unknown error";
+    }
+}
+
+size_t yolopp_workspace_bytes(const yolopp_params* p) {
+    Plan plan;
+    if (!make_plan(p, &plan)) return 0;
+    return plan.total;
+}
+
+int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
+                      const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream_) {
+    Plan plan;
+    if (!make_plan(p, &plan)) return YOLOPP_E_INVALID;
+    if (!level_ptrs || !out || !out->dets || !out->labels || !out->count || !out->status) return YOLOPP_E_INVALID;
+    if (p->rescale && !scale_factors) return YOLOPP_E_INVALID;
+    if (!workspace || workspace_bytes < plan.total) return YOLOPP_E_WORKSPACE;
+    if (((uintptr_t)workspace & 255) != 0) return YOLOPP_E_INVALID;
+    int rc = device_check();
+    if (rc != YOLOPP_OK) return rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DevParams& d = plan.d;
+    for (int l = 0; l < d.L; ++l) {
+        if (!level_ptrs[l]) return YOLOPP_E_INVALID;
+        d.lv[l].ptr = level_ptrs[l];
+        if (d.lv[l].use_tma && ((uintptr_t)level_ptrs[l] & 15) != 0) return YOLOPP_E_INVALID;
+    }
+    bind_workspace(&plan, workspace);
+    d.scale = scale_factors;
+    d.o_dets = out->dets;
+    d.o_labels = (long long*)out->labels;
+    d.o_anchors = out->anchors;
+    d.o_rows = out->rows;
+    d.o_count = out->count;
+    d.o_ncand = out->num_candidates;
+    d.o_status = out->status;
+
+    cudaError_t e;
+    e = cudaMemsetAsync((unsigned char*)workspace + plan.off_counters, 0, plan.counters_bytes, stream);
+    if (e != cudaSuccess) return cuda_rc(e);
+    e = cudaMemsetAsync(out->status, 0, sizeof(int32_t), stream);
+    if (e != cudaSuccess) return cuda_rc(e);
+
+    if (d.ntopk > 0) {
+        select_kernel<<<dim3(d.ntopk, d.B), SEL_THREADS, 0, stream>>>(d);
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    }
+    if (d.tma_tiles > 0) {
+        EncodeTiledFn enc = get_encode_fn();
+        if (!enc) return YOLOPP_E_NO_DEVICE;
+        TmapPack maps;
+        memset(&maps, 0, sizeof(maps));
+        for (int l = 0; l < d.L; ++l) {
+            if (!d.lv[l].use_tma) continue;
+            cuuint64_t gdim[2] = {(cuuint64_t)d.lv[l].HW, (cuuint64_t)d.B * d.A * d.NA};
+            cuuint64_t gstr[1] = {(cuuint64_t)d.lv[l].HW * 4};
+            cuuint32_t box[2] = {(cuuint32_t)TILE_T, (cuuint32_t)d.NA};
+            cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)d.lv[l].ptr, gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return YOLOPP_E_CUDA + 999;
+        }
+        int grid = sm_count() * plan.dec_ctas_per_sm;
+        if (grid > d.tma_tiles) grid = d.tma_tiles;
+        if (d.mode == YOLOPP_MODE_CSP) {
+            e = cudaFuncSetAttribute(decode_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.dec_smem);
+            if (e != cudaSuccess) return cuda_rc(e);
+            decode_tma_kernel<0><<<grid, DEC_THREADS, plan.dec_smem, stream>>>(d, maps);
+        } else {
+            e = cudaFuncSetAttribute(decode_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.dec_smem);
+            if (e != cudaSuccess) return cuda_rc(e);
+            decode_tma_kernel<1><<<grid, DEC_THREADS, plan.dec_smem, stream>>>(d, maps);
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    }
+    if (d.ldg_blocks > 0) {
+        if (d.mode == YOLOPP_MODE_CSP)
+            decode_ldg_kernel<0><<<d.ldg_blocks, 128, 0, stream>>>(d);
+        else
+            decode_ldg_kernel<1><<<d.ldg_blocks, 128, 0, stream>>>(d);
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    }
+    nms_class_kernel<<<dim3(d.C, d.B), NMS_THREADS, 0, stream>>>(d);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    final_kernel<<<d.B, SEL_THREADS, 0, stream>>>(d);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    nms_global_kernel<<<d.B, NMS_THREADS, 0, stream>>>(d);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    return YOLOPP_OK;
+}
+
+int yolopp_coder_decode(int mode, const float* bboxes, const float* pred, float stride, int64_t n, float* out,
+                        void* stream) {
+    if (mode != YOLOPP_MODE_CSP && mode != YOLOPP_MODE_V3) return YOLOPP_E_INVALID;
+    if (n < 0 || (n > 0 && (!bboxes || !pred || !out))) return YOLOPP_E_INVALID;
+    if (n == 0) return YOLOPP_OK;
+    if ((((uintptr_t)bboxes | (uintptr_t)pred | (uintptr_t)out) & 15) != 0) return YOLOPP_E_INVALID;
+    int rc = device_check();
+    if (rc != YOLOPP_OK) return rc;
+    long long blocks = (n + 255) / 256;
+    int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    coder_decode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mode, (const float4*)bboxes, (const float4*)pred,
+                                                                      stride, n, (float4*)out);
+    return cuda_rc(cudaGetLastError());
+}
+
+static int unary(const float* in, float* out, int64_t n, int op, void* stream) {
+    if (n < 0 || (n > 0 && (!in || !out))) return YOLOPP_E_INVALID;
+    if (n == 0) return YOLOPP_OK;
+    int rc = device_check();
+    if (rc != YOLOPP_OK) return rc;
+    long long blocks = (n + 255) / 256;
+    int cap = sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    unary_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, op);
+    return cuda_rc(cudaGetLastError());
+}
+int yolopp_sigmoid(const float* in, float* out, int64_t n, void* stream) { return unary(in, out, n, 0, stream); }
+int yolopp_exp(const float* in, float* out, int64_t n, void* stream) { return unary(in, out, n, 1, stream); }
+
+int yolopp_synth_level(float* out, int32_t batch, int32_t num_anchors, int32_t num_attrib, int32_t hw,
+                       const float* mean3, const float* std3, uint64_t seed, void* stream) {
+    if (!out || !mean3 || !std3 || batch < 1 || num_anchors < 1 || num_attrib < 5 || hw < 1) return YOLOPP_E_INVALID;
+    int rc = device_check();
+    if (rc != YOLOPP_OK) return rc;
+    Synth3 st;
+    for (int i = 0; i < 3; ++i) {
+        st.mean[i] = mean3[i];
+        st.std[i] = std3[i];
+    }
+    long long n = (long long)batch * num_anchors * num_attrib * hw;
+    long long blocks = (n + 255) / 256;
+    int cap = sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    synth_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, n, num_attrib, hw, st, (u64)seed);
+    return cuda_rc(cudaGetLastError());
+}
+
+// batched_nms standalone: implemented in yolopp_nms_capi.cuh (same kernels, generic inputs)
+size_t yolopp_nms_workspace_bytes(int64_t n) {
+    (void)n;
+    return 0;
+}
+int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, float iou_thr,
+                       int nms_offset, int split_thr, int class_agnostic, int max_num, float* dets, int64_t* keep,
+                       int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
+    (void)boxes; (void)scores; (void)idxs; (void)n; (void)iou_thr; (void)nms_offset; (void)split_thr;
+    (void)class_agnostic; (void)max_num; (void)dets; (void)keep; (void)num_keep; (void)workspace;
+    (void)workspace_bytes; (void)stream;
+    return YOLOPP_E_INVALID;  // TODO(round 1, later milestone)
+}
+
+}  // extern "C"

@@ -1,0 +1,293 @@
+// yolopp_device.cuh — device-side primitives shared by the yolopp kernels (sm_100a).
+//
+//  * canonical fp32 arithmetic: every reference operation is ONE IEEE rounding (__fadd_rn/__fmul_rn/... so
+//    that nvcc can never contract a*b+c into an FMA), exp() is the canonical polynomial of DESIGN.md
+//    §"Canonical arithmetic" (explicit __fmaf_rn; the same sequence as the CPU checker, so bit-reproducible).
+//  * order-preserving float<->uint keys, the 64-bit candidate key, the exact IoU predicate of mmcv nms_cpu.
+//  * block-level radix select / gather / bitonic sort over 64-bit unique keys.
+//  * mbarrier / TMA (cp.async.bulk[.tensor]) wrappers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ypp {
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------------------------------------
+// canonical arithmetic
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// exp(x), <= 1.02 ulp, monotone; identical operation sequence on CPU (fmaf) and GPU (__fmaf_rn).
+__device__ __forceinline__ float c_expf(float x) {
+    if (!(x == x)) return x;
+    float xc = x < -104.0f ? -104.0f : x;
+    xc = xc > 89.0f ? 89.0f : xc;
+    float t = __fmaf_rn(xc, 1.44269502f, 12582912.0f);
+    float j = __fsub_rn(t, 12582912.0f);
+    float r = __fmaf_rn(j, -0.693145752f, xc);
+    r = __fmaf_rn(j, -1.42860677e-06f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    float r2 = __fmul_rn(r, r);
+    float e = __fmaf_rn(p, r2, r);
+    e = __fadd_rn(e, 1.0f);
+    int ji = __float2int_rz(j);
+    int j1 = ji / 2;
+    int j2 = ji - j1;
+    float s1 = __uint_as_float((uint32_t)(j1 + 127) << 23);
+    float s2 = __uint_as_float((uint32_t)(j2 + 127) << 23);
+    return __fmul_rn(__fmul_rn(e, s1), s2);
+}
+
+// torch.sigmoid: 1 / (1 + exp(-x))
+__device__ __forceinline__ float c_sigmoid(float x) {
+    float e = c_expf(-x);
+    return __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+}
+
+// ------------------------------------------------------------------------------------------------
+// keys
+// ------------------------------------------------------------------------------------------------
+// order-preserving map float -> uint32 (a < b  <=>  ord(a) < ord(b))
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t o) {
+    uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+    return __uint_as_float(u);
+}
+
+// candidate key: ascending key order == (score desc, row asc, class asc) == (score desc, flat index asc)
+constexpr int KEY_CLASS_BITS = 12;
+constexpr int KEY_ROW_BITS = 20;
+__device__ __forceinline__ u64 make_key(float score, uint32_t row, uint32_t cls) {
+    return ((u64)(~f2ord(score)) << 32) | ((u64)row << KEY_CLASS_BITS) | (u64)cls;
+}
+__device__ __forceinline__ float key_score(u64 k) { return ord2f(~(uint32_t)(k >> 32)); }
+__device__ __forceinline__ uint32_t key_row(u64 k) { return ((uint32_t)k >> KEY_CLASS_BITS) & ((1u << KEY_ROW_BITS) - 1); }
+__device__ __forceinline__ uint32_t key_cls(u64 k) { return (uint32_t)k & ((1u << KEY_CLASS_BITS) - 1); }
+
+// ------------------------------------------------------------------------------------------------
+// IoU predicate of mmcv nms_cpu:  inter / (area_i + area_j - inter) > thr   (IEEE fp32, division form)
+// ------------------------------------------------------------------------------------------------
+struct Box {
+    float x1, y1, x2, y2, area;
+};
+
+__device__ __forceinline__ float box_area(float x1, float y1, float x2, float y2, float foff) {
+    return fmul(fadd(fsub(x2, x1), foff), fadd(fsub(y2, y1), foff));
+}
+
+// `a` is the earlier (kept) box i, `b` the later box j, exactly as in the reference's inner loop.
+__device__ __forceinline__ bool iou_gt(const Box& a, const Box& b, float thr, float foff) {
+    float xx1 = a.x1 > b.x1 ? a.x1 : b.x1;
+    float yy1 = a.y1 > b.y1 ? a.y1 : b.y1;
+    float xx2 = a.x2 < b.x2 ? a.x2 : b.x2;
+    float yy2 = a.y2 < b.y2 ? a.y2 : b.y2;
+    float w = fadd(fsub(xx2, xx1), foff);
+    w = w > 0.f ? w : 0.f;
+    float h = fadd(fsub(yy2, yy1), foff);
+    h = h > 0.f ? h : 0.f;
+    float inter = fmul(w, h);
+    float uni = fsub(fadd(a.area, b.area), inter);
+    // exact shortcuts around the IEEE division (the division result is monotone in inter/uni, and the
+    // guard band of 1e-6 relative is ~8 ulp wide, far more than the one rounding of thr*uni):
+    if (uni > 0.f && thr >= 0.f) {
+        float t = fmul(thr, uni);
+        if (inter < fmul(t, 0.999999f)) return false;
+        if (inter > fmul(t, 1.000001f) && t > 1e-30f) return true;
+    }
+    return fdiv(inter, uni) > thr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// block-level primitives over unique 64-bit keys
+// ------------------------------------------------------------------------------------------------
+// Shared scratch used by radix_select / gather (one per block).
+struct SelectSmem {
+    int hist[256];
+    int digit;
+    int need;
+    int done;
+    int count;
+};
+
+// Finds T such that exactly `m` eligible keys are <= T. A key is eligible when fetch(i, key) is true and
+// (!has_lo || key > lo). Requires: eligible keys unique, m >= 1, m <= #eligible. All threads of the block
+// must call this (blockDim.x multiple of 32).
+template <class Fetch>
+__device__ u64 radix_select(Fetch fetch, int n_slots, bool has_lo, u64 lo, int m, SelectSmem& S) {
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
+    u64 prefix = 0, pmask = 0;
+    int need = m;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int i = tid; i < 256; i += nth) S.hist[i] = 0;
+        __syncthreads();
+        for (int base = 0; base < n_slots; base += nth) {
+            int i = base + tid;
+            u64 key = 0;
+            bool v = (i < n_slots) && fetch(i, key);
+            v = v && (!has_lo || key > lo) && ((key & pmask) == prefix);
+            unsigned d = v ? (unsigned)((key >> shift) & 0xFFull) : 256u;
+            unsigned peers = __match_any_sync(0xffffffffu, d);
+            if (v && lane == (__ffs(peers) - 1)) atomicAdd(&S.hist[d], __popc(peers));
+        }
+        __syncthreads();
+        if (tid < 32) {
+            int local[8], s = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                local[q] = S.hist[tid * 8 + q];
+                s += local[q];
+            }
+            int incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v2 = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += v2;
+            }
+            int excl = incl - s;
+            if (excl < need && need <= incl) {
+                int cum = excl;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (cum + local[q] >= need) {
+                        S.digit = tid * 8 + q;
+                        S.need = need - cum;
+                        S.done = (local[q] == need - cum);
+                        break;
+                    }
+                    cum += local[q];
+                }
+            }
+        }
+        __syncthreads();
+        const int d = S.digit;
+        need = S.need;
+        const int done = S.done;
+        prefix |= (u64)d << shift;
+        pmask |= 0xFFull << shift;
+        __syncthreads();
+        if (done) return prefix | ((shift > 0) ? ((1ull << shift) - 1ull) : 0ull);
+    }
+    return prefix;
+}
+
+// Appends every eligible key <= T to out[0..cap) (unordered); returns the count (same in all threads).
+template <class Fetch>
+__device__ int gather_le(Fetch fetch, int n_slots, bool has_lo, u64 lo, u64 T, u64* out, int cap, SelectSmem& S) {
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
+    if (tid == 0) S.count = 0;
+    __syncthreads();
+    for (int base = 0; base < n_slots; base += nth) {
+        int i = base + tid;
+        u64 key = 0;
+        bool v = (i < n_slots) && fetch(i, key);
+        v = v && (!has_lo || key > lo) && key <= T;
+        unsigned bal = __ballot_sync(0xffffffffu, v);
+        int slot0 = 0;
+        if (lane == 0 && bal) slot0 = atomicAdd(&S.count, __popc(bal));
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (v) {
+            int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
+            if (slot < cap) out[slot] = key;
+        }
+    }
+    __syncthreads();
+    int c = S.count;
+    __syncthreads();
+    return c < cap ? c : cap;
+}
+
+// In-place ascending bitonic sort of s[0..p2), p2 a power of two. All threads of the block call it.
+__device__ __forceinline__ void bitonic_sort(u64* s, int p2) {
+    const int tid = threadIdx.x, nth = blockDim.x;
+    for (int size = 2; size <= p2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = tid; i < (p2 >> 1); i += nth) {
+                int pos = 2 * i - (i & (stride - 1));
+                int j = pos + stride;
+                bool up = ((pos & size) == 0);
+                u64 a = s[pos], b = s[j];
+                if ((a > b) == up) {
+                    s[pos] = b;
+                    s[j] = a;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mbarrier + TMA
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 2-D tiled TMA load: box (c0 = inner coordinate, c1 = row) -> smem, completes on `bar`.
+__device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// 1-D bulk copy global -> smem (16-byte aligned, size multiple of 16), completes on `bar`.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
+}
+
+}  // namespace ypp

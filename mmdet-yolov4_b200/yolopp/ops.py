@@ -1,0 +1,153 @@
+"""torch custom ops over the C ABI (include/yolopp.h). CUDA dispatch key ONLY — calling them with CPU tensors
+raises NotImplementedError from the dispatcher; there is no fallback implementation.
+
+    torch.ops.yolopp.get_bboxes(pred_maps, scale_factors, params_blob)
+        -> (dets[B,cap,5] f32, labels[B,cap] i64, anchors[B,cap] i32, rows[B,cap] i32, count[B] i32,
+            num_candidates[B] i32, status[1] i32)
+    torch.ops.yolopp.coder_decode(bboxes, pred, stride, mode) -> decoded
+    torch.ops.yolopp.sigmoid(x) / torch.ops.yolopp.exp(x)      (canonical transcendentals; tests)
+
+torch here is plumbing: device memory (caching allocator), the current stream, the dispatcher.
+"""
+import ctypes
+
+import torch
+
+from . import _capi
+
+_LIB_DEF = torch.library.Library('yolopp', 'DEF')
+_LIB_DEF.define('get_bboxes(Tensor[] pred_maps, Tensor? scale_factors, Tensor params) -> '
+                '(Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)')
+_LIB_DEF.define('coder_decode(Tensor bboxes, Tensor pred, float stride, int mode) -> Tensor')
+_LIB_DEF.define('sigmoid(Tensor x) -> Tensor')
+_LIB_DEF.define('exp(Tensor x) -> Tensor')
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _params_from_blob(blob):
+    p = _capi.YoloppParams()
+    raw = blob.cpu().numpy().tobytes()
+    if len(raw) != ctypes.sizeof(p):
+        raise ValueError('params blob has the wrong size')
+    ctypes.memmove(ctypes.byref(p), raw, len(raw))
+    return p
+
+
+def params_to_blob(p):
+    """yolopp_params struct -> uint8 CPU tensor (the custom op's schema only carries tensors and scalars)."""
+    return torch.frombuffer(bytearray(bytes(p)), dtype=torch.uint8).clone()
+
+
+def _get_bboxes_cuda(pred_maps, scale_factors, params):
+    lib = _capi.load_library()
+    p = _params_from_blob(params)
+    L = p.num_levels
+    if len(pred_maps) != L:
+        raise AssertionError(f'expected {L} prediction maps, got {len(pred_maps)}')
+    dev = pred_maps[0].device
+    maps = []
+    for l, t in enumerate(pred_maps):
+        if t.dtype != torch.float32:
+            raise TypeError(f'pred_maps[{l}] must be float32 (got {t.dtype}); the reference path is fp32')
+        if tuple(t.shape) != p.level_shape(l):
+            raise AssertionError(f'pred_maps[{l}] has shape {tuple(t.shape)}, expected {p.level_shape(l)}')
+        if t.device != dev:
+            raise AssertionError('all prediction maps must be on the same device')
+        maps.append(t.contiguous())  # NCHW contiguous (channels_last inputs are re-laid out)
+    B, cap = p.batch, p.capacity
+    with torch.cuda.device(dev):
+        ws_bytes = lib.yolopp_workspace_bytes(ctypes.byref(p))
+        if ws_bytes == 0:
+            raise ValueError('yolopp: invalid or unsupported configuration (see include/yolopp.h limits)')
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        dets = torch.empty((B, cap, 5), dtype=torch.float32, device=dev)
+        labels = torch.empty((B, cap), dtype=torch.int64, device=dev)
+        anchors = torch.empty((B, cap), dtype=torch.int32, device=dev)
+        rows = torch.empty((B, cap), dtype=torch.int32, device=dev)
+        count = torch.empty((B, ), dtype=torch.int32, device=dev)
+        ncand = torch.empty((B, ), dtype=torch.int32, device=dev)
+        status = torch.empty((1, ), dtype=torch.int32, device=dev)
+        sf = None
+        if p.rescale:
+            if scale_factors is None:
+                raise ValueError('rescale=True needs scale_factors')
+            sf = scale_factors.to(device=dev, dtype=torch.float32).contiguous()
+            if tuple(sf.shape) != (B, 4):
+                raise AssertionError('scale_factors must be (B, 4)')
+        ptrs = (ctypes.c_void_p * L)(*[m.data_ptr() for m in maps])
+        out = _capi.YoloppOutputs(dets.data_ptr(), labels.data_ptr(), anchors.data_ptr(), rows.data_ptr(),
+                                  count.data_ptr(), ncand.data_ptr(), status.data_ptr())
+        rc = lib.yolopp_get_bboxes(ctypes.byref(p), ptrs, ctypes.c_void_p(sf.data_ptr() if sf is not None else None),
+                                   ctypes.byref(out), ctypes.c_void_p(ws.data_ptr()), ws_bytes, _stream())
+        _capi.check(rc, 'yolopp_get_bboxes')
+        # the workspace / inputs must outlive the asynchronous kernels: tie them to the current stream
+        cur = torch.cuda.current_stream()
+        for t in maps + [ws] + ([sf] if sf is not None else []):
+            t.record_stream(cur)
+    return dets, labels, anchors, rows, count, ncand, status
+
+
+def _coder_decode_cuda(bboxes, pred, stride, mode):
+    lib = _capi.load_library()
+    assert pred.size(0) == bboxes.size(0)
+    assert pred.size(-1) == bboxes.size(-1) == 4
+    if bboxes.dtype != torch.float32 or pred.dtype != torch.float32:
+        raise TypeError('coder_decode needs float32 tensors')
+    b = bboxes.expand_as(pred).contiguous() if bboxes.shape != pred.shape else bboxes.contiguous()
+    q = pred.contiguous()
+    out = torch.empty_like(q)
+    with torch.cuda.device(q.device):
+        rc = lib.yolopp_coder_decode(int(mode), ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(q.data_ptr()),
+                                     ctypes.c_float(float(stride)), q.numel() // 4, ctypes.c_void_p(out.data_ptr()),
+                                     _stream())
+    _capi.check(rc, 'yolopp_coder_decode')
+    return out
+
+
+def _unary(name):
+
+    def f(x):
+        lib = _capi.load_library()
+        if x.dtype != torch.float32:
+            raise TypeError('float32 only')
+        xc = x.contiguous()
+        out = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            rc = getattr(lib, name)(ctypes.c_void_p(xc.data_ptr()), ctypes.c_void_p(out.data_ptr()), xc.numel(),
+                                    _stream())
+        _capi.check(rc, name)
+        return out
+
+    return f
+
+
+_LIB_IMPL = torch.library.Library('yolopp', 'IMPL')
+_LIB_IMPL.impl('get_bboxes', _get_bboxes_cuda, 'CUDA')
+_LIB_IMPL.impl('coder_decode', _coder_decode_cuda, 'CUDA')
+_LIB_IMPL.impl('sigmoid', _unary('yolopp_sigmoid'), 'CUDA')
+_LIB_IMPL.impl('exp', _unary('yolopp_exp'), 'CUDA')
+
+
+# ----------------------------------------------------------------------------------------------------
+# thin python entry points
+# ----------------------------------------------------------------------------------------------------
+def get_bboxes_raw(params, pred_maps, scale_factors=None):
+    """Runs the whole path; returns the fixed-capacity device tensors (no host sync)."""
+    blob = params if isinstance(params, torch.Tensor) else params_to_blob(params)
+    names = ('dets', 'labels', 'anchors', 'rows', 'count', 'num_candidates', 'status')
+    return dict(zip(names, torch.ops.yolopp.get_bboxes(list(pred_maps), scale_factors, blob)))
+
+
+def coder_decode(bboxes, pred, stride, mode):
+    return torch.ops.yolopp.coder_decode(bboxes, pred, float(stride), int(mode))
+
+
+def sigmoid(x):
+    return torch.ops.yolopp.sigmoid(x)
+
+
+def exp(x):
+    return torch.ops.yolopp.exp(x)

@@ -1,0 +1,170 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Everything goes through the C ABI of
+mmdet-yolov4_b200/csrc/libyolopp.so via the registered torch custom ops, and is compared with the CPU oracle
+(oracle/oracle.c) on the same inputs. Bars: indices / labels / counts bit-exact; boxes and scores bit-exact too
+(the oracle and the kernels share the canonical fp32 arithmetic), which is stricter than the 1e-5 relative
+tolerance north_star states for floating point.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from oracle import oracle
+from yolopp import _capi as capi
+
+pytestmark = pytest.mark.gpu
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def run_cuda(case, params=None, levels=None):
+    import yolopp
+    p = params or cases.build_params(case)
+    if levels is None:
+        levels = yolopp.synth.synth_levels(p, case['seed'], case['dist'])
+    sf = cases.scale_factors(case)
+    sf_t = torch.from_numpy(sf).cuda() if sf is not None else None
+    out = yolopp.get_bboxes_raw(p, levels, sf_t)
+    torch.cuda.synchronize()
+    res = {k: v.cpu().numpy() for k, v in out.items()}
+    return p, levels, res
+
+
+def compare(p, res, orc, name):
+    B = p.batch
+    assert int(res['status'][0]) == 0, f'{name}: status {res["status"]}'
+    np.testing.assert_array_equal(res['num_candidates'], orc['num_candidates'], err_msg=f'{name}: num_candidates')
+    np.testing.assert_array_equal(res['count'], orc['count'], err_msg=f'{name}: count')
+    for b in range(B):
+        n = int(orc['count'][b])
+        np.testing.assert_array_equal(res['anchors'][b, :n], orc['anchors'][b], err_msg=f'{name}: anchors img {b}')
+        np.testing.assert_array_equal(res['labels'][b, :n], orc['labels'][b], err_msg=f'{name}: labels img {b}')
+        np.testing.assert_array_equal(res['rows'][b, :n], orc['rows'][b], err_msg=f'{name}: rows img {b}')
+        np.testing.assert_array_equal(_u32(res['dets'][b, :n]), _u32(orc['dets'][b]), err_msg=f'{name}: dets img {b}')
+
+
+def test_transcendentals_bit_exact():
+    """canonical exp / sigmoid: GPU bits == CPU oracle bits on a dense sweep + random bit patterns."""
+    import yolopp
+    rng = np.random.RandomState(0)
+    xs = np.concatenate([
+        np.linspace(-110, 95, 1 << 20).astype(np.float32),
+        np.linspace(-30, 30, 1 << 21).astype(np.float32),
+        rng.randint(0, 2**32, size=1 << 20, dtype=np.uint64).astype(np.uint32).view(np.float32),
+        np.array([0.0, -0.0, np.inf, -np.inf, 88.72283, 88.72284, -87.33654, -103.97, 1e-45, -1e-45], np.float32),
+    ])
+    xs = xs[~np.isnan(xs)]
+    x = torch.from_numpy(xs).cuda()
+    e = yolopp.exp(x).cpu().numpy()
+    s = yolopp.sigmoid(x).cpu().numpy()
+    np.testing.assert_array_equal(_u32(e), _u32(oracle.expf(xs)))
+    np.testing.assert_array_equal(_u32(s), _u32(oracle.sigmoid(xs)))
+
+
+def test_synth_bit_exact():
+    """device generator == host generator (so full-size device runs are reproducible on the host)."""
+    import yolopp
+    case = cases.CASES['csp_odd']
+    p = cases.build_params(case)
+    dev = yolopp.synth.synth_levels(p, case['seed'], case['dist'])
+    host = cases.host_levels(case, p)
+    for d, h in zip(dev, host):
+        np.testing.assert_array_equal(_u32(d.cpu().numpy()), _u32(h))
+
+
+@pytest.mark.parametrize('name', sorted(cases.CASES))
+def test_get_bboxes_matches_oracle(name):
+    case = cases.CASES[name]
+    p, levels, res = run_cuda(case)
+    host = [x.cpu().numpy() for x in levels]
+    orc = oracle.get_bboxes(p, host, cases.scale_factors(case))
+    compare(p, res, orc, name)
+
+
+def test_coder_decode_matches_oracle():
+    import yolopp
+    rng = np.random.RandomState(1)
+    anchors = (rng.rand(5000, 4).astype(np.float32) * 600)
+    anchors[:, 2:] += anchors[:, :2]
+    pred = rng.randn(5000, 4).astype(np.float32)
+    for mode, coder in ((capi.MODE_CSP, yolopp.YOLOV4BBoxCoder()), (capi.MODE_V3, yolopp.YOLOBBoxCoder())):
+        for stride in (8, 16, 32):
+            got = coder.decode(torch.from_numpy(anchors).cuda(), torch.from_numpy(pred).cuda(), stride).cpu().numpy()
+            np.testing.assert_array_equal(_u32(got), _u32(oracle.coder_decode(mode, anchors, pred, stride)))
+
+
+def test_reference_coder_kat():
+    """The reference's own known-answer test for YOLOBBoxCoder.decode (tests/test_utils/test_coder.py:8-23)."""
+    import yolopp
+    coder = yolopp.YOLOBBoxCoder()
+    bboxes = torch.Tensor([[-42., -29., 74., 61.], [-10., -29., 106., 61.], [22., -29., 138., 61.],
+                           [54., -29., 170., 61.]]).cuda()
+    pred_bboxes = torch.Tensor([[0.4709, 0.6152, 0.1690, -0.4056], [0.5399, 0.6653, 0.1162, -0.4162],
+                                [0.4654, 0.6618, 0.1548, -0.4301], [0.4786, 0.6197, 0.1896, -0.4479]]).cuda()
+    expected = torch.Tensor([[-53.6102, -10.3096, 83.7478, 49.6824], [-15.8700, -8.3901, 114.4236, 50.9693],
+                             [11.1822, -8.0924, 146.6034, 50.4476], [41.2068, -8.9232, 181.4236, 48.5840]])
+    assert expected.allclose(coder.decode(bboxes, pred_bboxes, 32).cpu())
+
+
+def test_head_api_list_of_tuples():
+    """get_bboxes through the reference-shaped head API returns list[(n,5),(n,)] equal to the raw op."""
+    import yolopp
+    case = cases.CASES['csp608_sparse']
+    p = cases.build_params(case)
+    levels = yolopp.synth.synth_levels(p, case['seed'], case['dist'])
+    head = yolopp.YOLOCSPHead(num_classes=80, in_channels=[256, 512, 1024], test_cfg=cases.ref_cfg(case))
+    metas = [dict(scale_factor=1.0) for _ in range(p.batch)]
+    out = head.get_bboxes(levels, metas)
+    orc = oracle.get_bboxes(p, [x.cpu().numpy() for x in levels])
+    assert len(out) == p.batch
+    for b, (dets, labels) in enumerate(out):
+        assert dets.dtype == torch.float32 and labels.dtype == torch.int64 and dets.is_cuda
+        np.testing.assert_array_equal(_u32(dets.cpu().numpy()), _u32(orc['dets'][b]))
+        np.testing.assert_array_equal(labels.cpu().numpy(), orc['labels'][b])
+
+
+def test_cpu_tensors_are_rejected():
+    """No CPU fallback: the custom op only has a CUDA kernel."""
+    import yolopp
+    case = cases.CASES['csp_tiny']
+    p = cases.build_params(case)
+    host = [torch.from_numpy(x) for x in cases.host_levels(case, p)]
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        yolopp.get_bboxes_raw(p, host)
+
+
+def test_full_size_batch64_properties():
+    """BASELINE config 2 at full size (608^2, batch 64): size-independent properties — every image of the
+    batch equals the same image processed alone (images are independent), counts within bounds, scores
+    sorted, and a prefix of the batch matches the oracle."""
+    import yolopp
+    case = dict(cases.CASES['csp608_sparse'], batch=64)
+    p, levels, res = run_cuda(case)
+    assert int(res['status'][0]) == 0
+    assert (res['count'] <= 300).all() and (res['count'] > 0).all()
+    for b in range(64):
+        n = res['count'][b]
+        s = res['dets'][b, :n, 4]
+        assert (np.diff(s) <= 0).all()
+    # image b alone == image b inside the batch
+    for b in (0, 17, 63):
+        p1 = cases.build_params(case, batch=1)
+        lv1 = [x[b:b + 1].contiguous() for x in levels]
+        out1 = yolopp.get_bboxes_raw(p1, lv1)
+        n = int(out1['count'][0])
+        assert n == res['count'][b]
+        np.testing.assert_array_equal(_u32(out1['dets'][0, :n].cpu().numpy()), _u32(res['dets'][b, :n]))
+        np.testing.assert_array_equal(out1['labels'][0, :n].cpu().numpy(), res['labels'][b, :n])
+    # first images against the oracle
+    host = [x[:2].cpu().numpy() for x in levels]
+    p2 = cases.build_params(case, batch=2)
+    orc = oracle.get_bboxes(p2, host)
+    for b in range(2):
+        n = int(orc['count'][b])
+        assert n == res['count'][b]
+        np.testing.assert_array_equal(_u32(res['dets'][b, :n]), _u32(orc['dets'][b]))
+        np.testing.assert_array_equal(res['anchors'][b, :n], orc['anchors'][b])
