@@ -101,7 +101,7 @@ typedef struct yolopp_outputs {
     float* dets;        /* [B][cap][5]  x1,y1,x2,y2,score  (bbox_nms.py:86-93) */
     int64_t* labels;    /* [B][cap]     class id (int64 like the reference) */
     int32_t* anchors;   /* [B][cap]     parity tap: concatenated anchor index (level-major, (y*W+x)*A+a); may be NULL */
-    int32_t* rows;      /* [B][cap]     parity tap: row index entering multiclass_nms (top-k rank order); may be NULL */
+    int32_t* rows;      /* [B][cap]     parity tap: row index in top-k rank order (before the V3 conf_thr row filter); may be NULL */
     int32_t* count;     /* [B]          number of detections */
     int32_t* num_candidates; /* [B]     candidates that entered batched_nms (bbox_nms.py:66); may be NULL */
     int32_t* status;    /* [1]          0 or YOLOPP_E_OVERFLOW, data dependent; written every call */
@@ -126,6 +126,35 @@ size_t yolopp_workspace_bytes(const yolopp_params* p);
  */
 int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
                       const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Same as yolopp_get_bboxes, and records `events[i]` (cudaEvent_t created by the caller with timing enabled)
+ * on `stream` at the stage boundaries, so a benchmark can time each kernel on the launching stream without a
+ * profiler:  0 select | 1 decode (TMA levels) | 2 decode (other levels) | 3 per-class NMS | 4 final merge |
+ * 5 global NMS | 6 end.  num_events must be >= YOLOPP_NUM_STAGE_EVENTS.
+ */
+#define YOLOPP_NUM_STAGE_EVENTS 7
+int yolopp_get_bboxes_profiled(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
+                               const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream,
+                               void* const* events, int num_events);
+
+/* How a configuration is executed (for DESIGN.md / bench.py roofline arithmetic). */
+typedef struct yolopp_plan_info {
+    int32_t anchors_per_image;   /* N */
+    int32_t rows_per_image;      /* R: rows entering multiclass_nms */
+    int32_t num_attrib;          /* 5 + C (5 when class agnostic) */
+    int32_t tma_level_mask;      /* bit l set: level l is streamed by the TMA decode kernel */
+    int32_t tma_tiles;           /* tiles of the TMA decode kernel */
+    int32_t ldg_blocks;          /* blocks of the generic decode kernel */
+    int32_t decode_smem_bytes;   /* dynamic shared memory of the TMA decode kernel */
+    int32_t decode_ctas_per_sm;
+    int32_t kernel_launches;     /* kernels launched per yolopp_get_bboxes call */
+    int32_t reserved0;
+    int64_t tma_bytes_per_image; /* algorithmic bytes read per image by the TMA decode kernel: 4*A*(5+C)*sum(HW) */
+    int64_t ldg_bytes_per_image; /* ... by the generic decode kernel */
+    int64_t workspace_bytes;
+} yolopp_plan_info;
+int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info);
 
 /*
  * bbox_coder.decode as a standalone elementwise op (YOLOV4BBoxCoder.decode yolov4_bbox_coder.py:39-67 when

@@ -257,8 +257,9 @@ size_t yolopp_workspace_bytes(const yolopp_params* p) {
     return plan.total;
 }
 
-int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
-                      const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream_) {
+static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
+                          const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream_,
+                          void* const* events, int num_events) {
     Plan plan;
     if (!make_plan(p, &plan)) return YOLOPP_E_INVALID;
     if (!level_ptrs || !out || !out->dets || !out->labels || !out->count || !out->status) return YOLOPP_E_INVALID;
@@ -285,15 +286,25 @@ int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, co
     d.o_status = out->status;
 
     cudaError_t e;
+    int ev_i = 0;
+#define YPP_MARK()                                                                          \
+    do {                                                                                    \
+        if (events && ev_i < num_events) {                                                  \
+            e = cudaEventRecord((cudaEvent_t)events[ev_i++], stream);                       \
+            if (e != cudaSuccess) return cuda_rc(e);                                        \
+        }                                                                                   \
+    } while (0)
     e = cudaMemsetAsync((unsigned char*)workspace + plan.off_counters, 0, plan.counters_bytes, stream);
     if (e != cudaSuccess) return cuda_rc(e);
     e = cudaMemsetAsync(out->status, 0, sizeof(int32_t), stream);
     if (e != cudaSuccess) return cuda_rc(e);
 
+    YPP_MARK();  // 0: start of select
     if (d.ntopk > 0) {
         select_kernel<<<dim3(d.ntopk, d.B), SEL_THREADS, 0, stream>>>(d);
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
     }
+    YPP_MARK();  // 1: start of decode (TMA)
     if (d.tma_tiles > 0) {
         EncodeTiledFn enc = get_encode_fn();
         if (!enc) return YOLOPP_E_NO_DEVICE;
@@ -323,6 +334,7 @@ int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, co
         }
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
     }
+    YPP_MARK();  // 2: start of decode (LDG)
     if (d.ldg_blocks > 0) {
         if (d.mode == YOLOPP_MODE_CSP)
             decode_ldg_kernel<0><<<d.ldg_blocks, 128, 0, stream>>>(d);
@@ -330,12 +342,59 @@ int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, co
             decode_ldg_kernel<1><<<d.ldg_blocks, 128, 0, stream>>>(d);
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
     }
+    YPP_MARK();  // 3: start of per-class NMS
     nms_class_kernel<<<dim3(d.C, d.B), NMS_THREADS, 0, stream>>>(d);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    YPP_MARK();  // 4: start of final merge
     final_kernel<<<d.B, SEL_THREADS, 0, stream>>>(d);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    YPP_MARK();  // 5: start of global NMS
     nms_global_kernel<<<d.B, NMS_THREADS, 0, stream>>>(d);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    YPP_MARK();  // 6: end
+#undef YPP_MARK
+    return YOLOPP_OK;
+}
+
+int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
+                      const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream) {
+    return run_get_bboxes(p, level_ptrs, scale_factors, out, workspace, workspace_bytes, stream, nullptr, 0);
+}
+
+int yolopp_get_bboxes_profiled(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
+                               const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream,
+                               void* const* events, int num_events) {
+    if (!events || num_events < YOLOPP_NUM_STAGE_EVENTS) return YOLOPP_E_INVALID;
+    return run_get_bboxes(p, level_ptrs, scale_factors, out, workspace, workspace_bytes, stream, events, num_events);
+}
+
+int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info) {
+    Plan plan;
+    if (!info || !make_plan(p, &plan)) return YOLOPP_E_INVALID;
+    memset(info, 0, sizeof(*info));
+    const DevParams& d = plan.d;
+    info->anchors_per_image = d.N;
+    info->rows_per_image = d.R;
+    info->num_attrib = d.NA;
+    info->tma_tiles = d.tma_tiles;
+    info->ldg_blocks = d.ldg_blocks;
+    info->decode_smem_bytes = (int32_t)plan.dec_smem;
+    info->decode_ctas_per_sm = plan.dec_ctas_per_sm;
+    info->workspace_bytes = (int64_t)plan.total;
+    for (int l = 0; l < d.L; ++l) {
+        int64_t bytes = (int64_t)4 * d.A * d.NA * d.lv[l].HW;
+        if (d.lv[l].use_tma) {
+            info->tma_level_mask |= 1 << l;
+            info->tma_bytes_per_image += bytes;
+        } else {
+            info->ldg_bytes_per_image += bytes;
+        }
+    }
+    int launches = 3;  // nms_class, final, nms_global
+    if (d.ntopk > 0) ++launches;
+    if (d.tma_tiles > 0) ++launches;
+    if (d.ldg_blocks > 0) ++launches;
+    info->kernel_launches = launches;
     return YOLOPP_OK;
 }
 

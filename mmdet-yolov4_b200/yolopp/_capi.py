@@ -88,6 +88,29 @@ class YoloppOutputs(ctypes.Structure):
     ]
 
 
+class YoloppPlanInfo(ctypes.Structure):
+    """struct yolopp_plan_info (include/yolopp.h)."""
+    _fields_ = [
+        ('anchors_per_image', c_int32),
+        ('rows_per_image', c_int32),
+        ('num_attrib', c_int32),
+        ('tma_level_mask', c_int32),
+        ('tma_tiles', c_int32),
+        ('ldg_blocks', c_int32),
+        ('decode_smem_bytes', c_int32),
+        ('decode_ctas_per_sm', c_int32),
+        ('kernel_launches', c_int32),
+        ('reserved0', c_int32),
+        ('tma_bytes_per_image', c_int64),
+        ('ldg_bytes_per_image', c_int64),
+        ('workspace_bytes', c_int64),
+    ]
+
+
+NUM_STAGE_EVENTS = 7
+STAGE_NAMES = ('select', 'decode_tma', 'decode_ldg', 'nms_class', 'final', 'nms_global')
+
+
 def _pair(v):
     return (int(v[0]), int(v[1])) if isinstance(v, (tuple, list, np.ndarray)) else (int(v), int(v))
 
@@ -179,6 +202,11 @@ def load_library(path=None):
     lib.yolopp_workspace_bytes.argtypes = [pp]
     lib.yolopp_get_bboxes.restype = ctypes.c_int
     lib.yolopp_get_bboxes.argtypes = [pp, ctypes.POINTER(c_void_p), c_void_p, po, c_void_p, c_size_t, c_void_p]
+    lib.yolopp_get_bboxes_profiled.restype = ctypes.c_int
+    lib.yolopp_get_bboxes_profiled.argtypes = [pp, ctypes.POINTER(c_void_p), c_void_p, po, c_void_p, c_size_t,
+                                               c_void_p, ctypes.POINTER(c_void_p), ctypes.c_int]
+    lib.yolopp_describe.restype = ctypes.c_int
+    lib.yolopp_describe.argtypes = [pp, ctypes.POINTER(YoloppPlanInfo)]
     lib.yolopp_coder_decode.restype = ctypes.c_int
     lib.yolopp_coder_decode.argtypes = [ctypes.c_int, c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p]
     lib.yolopp_nms_workspace_bytes.restype = c_size_t
@@ -202,8 +230,15 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = ('yolopp_abi_version', 'yolopp_strerror', 'yolopp_workspace_bytes', 'yolopp_get_bboxes',
+                    'yolopp_get_bboxes_profiled', 'yolopp_describe',
                     'yolopp_coder_decode', 'yolopp_nms_workspace_bytes', 'yolopp_batched_nms', 'yolopp_synth_level',
                     'yolopp_sigmoid', 'yolopp_exp')
+
+
+def describe(params):
+    info = YoloppPlanInfo()
+    check(load_library().yolopp_describe(ctypes.byref(params), ctypes.byref(info)), 'yolopp_describe')
+    return info
 
 
 def check(code, what='yolopp'):

@@ -152,7 +152,7 @@ def _scale_factors(img_metas, batch):
     return torch.from_numpy(sf)
 
 
-def _get_bboxes_impl(mode, head, pred_maps, img_metas, cfg, rescale, with_nms):
+def _run_raw(mode, head, pred_maps, img_metas, cfg, rescale, with_nms):
     cfg = head.test_cfg if cfg is None else cfg
     num_levels = len(pred_maps)
     assert num_levels == head.num_levels
@@ -178,7 +178,12 @@ def _get_bboxes_impl(mode, head, pred_maps, img_metas, cfg, rescale, with_nms):
     sf = _scale_factors(img_metas, batch) if rescale else None
     if sf is not None:
         sf = sf.to(pred_maps[0].device, non_blocking=True)
-    out = ops.get_bboxes_raw(params, pred_maps, sf)
+    return params, ops.get_bboxes_raw(params, pred_maps, sf)
+
+
+def _get_bboxes_impl(mode, head, pred_maps, img_metas, cfg, rescale, with_nms):
+    params, out = _run_raw(mode, head, pred_maps, img_metas, cfg, rescale, with_nms)
+    batch = params.batch
     # one small device->host read: counts + status (the reference syncs dozens of times per image)
     host = torch.cat([out['count'], out['num_candidates'], out['status']]).cpu()
     count, ncand, status = host[:batch], host[batch:2 * batch], int(host[-1])
@@ -193,6 +198,29 @@ def _get_bboxes_impl(mode, head, pred_maps, img_metas, cfg, rescale, with_nms):
         else:
             result.append((out['dets'][b, :n], out['labels'][b, :n]))
     return result
+
+
+def _get_results_host(mode, head, pred_maps, img_metas, cfg, rescale):
+    """get_bboxes + bbox2result's device->host step fused: ONE D2H of the fixed-capacity block into pinned
+    memory, then numpy views. Returns list[(ndarray(n,5) f32, ndarray(n,) i64)]."""
+    params, out = _run_raw(mode, head, pred_maps, img_metas, cfg, rescale, True)
+    B, cap = params.batch, params.capacity
+    key = (B, cap, out['dets'].device)
+    buf = getattr(head, '_yolopp_host', None)
+    if buf is None or buf[0] != key:
+        buf = (key, torch.empty((B, cap, 5), dtype=torch.float32).pin_memory(),
+               torch.empty((B, cap), dtype=torch.int64).pin_memory(),
+               torch.empty((2 * B + 1, ), dtype=torch.int32).pin_memory())
+        head._yolopp_host = buf
+    _, h_dets, h_labels, h_meta = buf
+    h_dets.copy_(out['dets'], non_blocking=True)
+    h_labels.copy_(out['labels'], non_blocking=True)
+    h_meta.copy_(torch.cat([out['count'], out['num_candidates'], out['status']]), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    if int(h_meta[-1]) != 0:
+        raise RuntimeError(f'yolopp_get_bboxes: {_capi.load_library().yolopp_strerror(int(h_meta[-1])).decode()}')
+    d, l, cnt = h_dets.numpy(), h_labels.numpy(), h_meta.numpy()[:B]
+    return [(d[b, :cnt[b]], l[b, :cnt[b]]) for b in range(B)]
 
 
 class _HeadBase:
@@ -223,6 +251,11 @@ class _HeadBase:
     def get_bboxes(self, pred_maps, img_metas, cfg=None, rescale=False, with_nms=True):
         """list[(Tensor(n,5), Tensor(n,))] — same contract as the reference's get_bboxes."""
         return _get_bboxes_impl(self._mode, self, pred_maps, img_metas, cfg, rescale, with_nms)
+
+    def get_results_host(self, pred_maps, img_metas, cfg=None, rescale=False):
+        """Host-side results (numpy) with a single device->host copy per batch — what `simple_test` needs
+        before `bbox2result` (mmdet/models/detectors/single_stage.py:102-111)."""
+        return _get_results_host(self._mode, self, pred_maps, img_metas, cfg, rescale)
 
 
 class YOLOCSPHead(_HeadBase):

@@ -151,3 +151,64 @@ def sigmoid(x):
 
 def exp(x):
     return torch.ops.yolopp.exp(x)
+
+
+class Session:
+    """Pre-allocated workspace + output block for one configuration (serving loops / the benchmark):
+    `run()` is a single C-ABI call, no allocation, no host sync. `run(profile=True)` additionally records the
+    per-stage CUDA events (yolopp_get_bboxes_profiled); `stage_ms()` reads them after a synchronize."""
+
+    def __init__(self, params, device='cuda'):
+        self.lib = _capi.load_library()
+        self.p = params
+        self.dev = torch.device(device)
+        B, cap = params.batch, params.capacity
+        with torch.cuda.device(self.dev):
+            self.ws_bytes = self.lib.yolopp_workspace_bytes(ctypes.byref(params))
+            if self.ws_bytes == 0:
+                raise ValueError('yolopp: invalid or unsupported configuration')
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.dev)
+            self.out = dict(
+                dets=torch.zeros((B, cap, 5), dtype=torch.float32, device=self.dev),
+                labels=torch.zeros((B, cap), dtype=torch.int64, device=self.dev),
+                anchors=torch.zeros((B, cap), dtype=torch.int32, device=self.dev),
+                rows=torch.zeros((B, cap), dtype=torch.int32, device=self.dev),
+                count=torch.zeros((B, ), dtype=torch.int32, device=self.dev),
+                num_candidates=torch.zeros((B, ), dtype=torch.int32, device=self.dev),
+                status=torch.zeros((1, ), dtype=torch.int32, device=self.dev))
+        o = self.out
+        self._outs = _capi.YoloppOutputs(o['dets'].data_ptr(), o['labels'].data_ptr(), o['anchors'].data_ptr(),
+                                         o['rows'].data_ptr(), o['count'].data_ptr(), o['num_candidates'].data_ptr(),
+                                         o['status'].data_ptr())
+        self._events = None
+        self.info = _capi.describe(params)
+
+    def _make_events(self):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(_capi.NUM_STAGE_EVENTS)]
+        for e in evs:
+            e.record()  # forces creation of the underlying cudaEvent_t
+        torch.cuda.synchronize(self.dev)
+        return evs
+
+    def run(self, pred_maps, scale_factors=None, profile=False):
+        p = self.p
+        ptrs = (ctypes.c_void_p * p.num_levels)(*[m.data_ptr() for m in pred_maps])
+        sf = ctypes.c_void_p(scale_factors.data_ptr() if scale_factors is not None else None)
+        with torch.cuda.device(self.dev):
+            if profile:
+                if self._events is None:
+                    self._events = self._make_events()
+                evp = (ctypes.c_void_p * len(self._events))(*[e.cuda_event for e in self._events])
+                rc = self.lib.yolopp_get_bboxes_profiled(ctypes.byref(p), ptrs, sf, ctypes.byref(self._outs),
+                                                         ctypes.c_void_p(self.ws.data_ptr()), self.ws_bytes, _stream(),
+                                                         evp, len(self._events))
+            else:
+                rc = self.lib.yolopp_get_bboxes(ctypes.byref(p), ptrs, sf, ctypes.byref(self._outs),
+                                                ctypes.c_void_p(self.ws.data_ptr()), self.ws_bytes, _stream())
+        _capi.check(rc, 'yolopp_get_bboxes')
+        return self.out
+
+    def stage_ms(self):
+        """dict stage -> milliseconds of the last profiled run (call after torch.cuda.synchronize())."""
+        ev = self._events
+        return {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(_capi.STAGE_NAMES)}

@@ -487,6 +487,9 @@ static int64_t get_bboxes_single(const yolopp_params* p, const float* const* lev
     float* ms = (float*)malloc(sizeof(float) * (size_t)(R > 0 ? R : 1) * (size_t)(C + 1));
     const float* factors = NULL;
     int64_t R2 = R;
+    /* parity tap: row index in top-k rank order BEFORE the V3 conf_thr filter */
+    int64_t* rowid = (int64_t*)malloc(sizeof(int64_t) * (size_t)(R > 0 ? R : 1));
+    for (int64_t r = 0; r < R; ++r) rowid[r] = r;
     if (p->mode == YOLOPP_MODE_CSP) {
         for (int64_t r = 0; r < R; ++r) {
             for (int c = 0; c < C; ++c)
@@ -503,6 +506,7 @@ static int64_t get_bboxes_single(const yolopp_params* p, const float* const* lev
                     memmove(box + 4 * w, box + 4 * r, sizeof(float) * 4);
                     memmove(cls + w * C, cls + r * C, sizeof(float) * (size_t)C);
                     src[w] = src[r];
+                    rowid[w] = rowid[r];
                     ++w;
                 }
             R2 = w;
@@ -526,7 +530,7 @@ static int64_t get_bboxes_single(const yolopp_params* p, const float* const* lev
     for (int64_t q = 0; q < nk; ++q) {
         memcpy(out_dets + 5 * q, d + 5 * q, sizeof(float) * 5);
         out_labels[q] = lab[q];
-        if (out_row) out_row[q] = (int32_t)(flat[q] / C);
+        if (out_row) out_row[q] = (int32_t)rowid[flat[q] / C];
         if (out_anchor) out_anchor[q] = (int32_t)src[flat[q] / C];
     }
     if (out_ncand) *out_ncand = (int32_t)ncand;
@@ -535,6 +539,7 @@ static int64_t get_bboxes_single(const yolopp_params* p, const float* const* lev
     free(box);
     free(src);
     free(ms);
+    free(rowid);
     free(d);
     free(lab);
     free(flat);
