@@ -130,10 +130,10 @@ int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, co
 /*
  * Same as yolopp_get_bboxes, and records `events[i]` (cudaEvent_t created by the caller with timing enabled)
  * on `stream` at the stage boundaries, so a benchmark can time each kernel on the launching stream without a
- * profiler:  0 select | 1 decode (TMA levels) | 2 decode (other levels) | 3 per-class NMS | 4 final merge |
- * 5 global NMS | 6 end.  num_events must be >= YOLOPP_NUM_STAGE_EVENTS.
+ * profiler:  0 select | 1 decode (TMA levels) | 2 decode (other levels) | 3 per-image NMS + output | 4 end.
+ * num_events must be >= YOLOPP_NUM_STAGE_EVENTS.
  */
-#define YOLOPP_NUM_STAGE_EVENTS 7
+#define YOLOPP_NUM_STAGE_EVENTS 5
 int yolopp_get_bboxes_profiled(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
                                const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream,
                                void* const* events, int num_events);

@@ -17,10 +17,9 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct Plan {
     DevParams d;
     size_t off_counters, counters_bytes;
-    size_t off_conf_key, off_rank, off_row_anchor, off_row_box, off_bin_keys, off_kept_keys, off_kept_count,
-        off_cls_range, off_glob_keys, off_glob_kept;
+    size_t off_ckey, off_rank, off_row_anchor, off_row_box, off_mat;
     size_t total;
-    size_t dec_smem;
+    size_t dec_smem, sel_smem, nms_smem;
     int dec_ctas_per_sm;
 };
 
@@ -99,6 +98,8 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
             d.lv[sg.first_level + q].seg = s;
         }
         sg.N = (int)n;
+        sg.m_begin = d.lv[sg.first_level].m_off;
+        sg.m_end = d.lv[sg.first_level + sg.num_levels - 1].m_off + d.lv[sg.first_level + sg.num_levels - 1].HW * d.A;
         sg.has_topk = (p->nms_pre > 0 && p->nms_pre < n) ? 1 : 0;
         sg.k = sg.has_topk ? p->nms_pre : (int)n;
         if (sg.has_topk) {
@@ -116,11 +117,19 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     if (p->nms_max_num > 0) m_eff = (m_eff > 0 && m_eff < p->nms_max_num) ? m_eff : p->nms_max_num;
     d.m_eff = m_eff;
     d.out_cap = p->out_capacity > 0 ? p->out_capacity : p->max_per_img;
-    CHECK_ARG(d.out_cap >= 1 && d.out_cap <= SEL_MAX_K);
-    d.Kc = (m_eff > 0 && m_eff < d.R) ? m_eff : d.R;
-    long long rc = (long long)d.R * d.C;
-    long long G = (p->split_thr > 0) ? (p->split_thr < rc ? p->split_thr : rc) : 1;
-    d.G = (int)(G < 1 ? 1 : G);
+    CHECK_ARG(d.out_cap >= 1 && d.out_cap <= NMS_MAX_KEEP);
+    CHECK_ARG(m_eff <= NMS_MAX_KEEP);
+    // boxes the NMS pass may keep: max_num when given, else one more than fits (to flag the overflow)
+    d.keep_cap = m_eff > 0 ? m_eff : d.out_cap + 1;
+    CHECK_ARG((long long)d.R * d.C < (1ll << 31));
+    int max_k = 0;
+    for (int s = 0; s < d.nsegs; ++s)
+        if (d.seg[s].has_topk && d.seg[s].k > max_k) max_k = d.seg[s].k;
+    int kcap = 2048;
+    while (kcap < 2 * max_k) kcap <<= 1;
+    d.sel_kcap = kcap;
+    plan->sel_smem = (size_t)kcap * 8;
+    plan->nms_smem = (size_t)NMS_KCAP * 8 + (size_t)d.keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)d.keep_cap * 24;
 
     // which kernel decodes which level
     const size_t stage_bytes = align_up((size_t)NA * TILE_T * 4 + TILE_T * 4, 128);
@@ -153,29 +162,19 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     // workspace layout
     size_t off = 0;
     const size_t B = (size_t)d.B, Cc = (size_t)d.C, R = (size_t)d.R;
-    plan->off_counters = off;  // bin_count[B][C] | img_max[B] | img_ncand[B] | flag[B]
-    plan->counters_bytes = align_up((B * Cc + 3 * B) * 4, 256);
+    plan->off_counters = off;  // img_max[B]
+    plan->counters_bytes = align_up(B * 4, 256);
     off += plan->counters_bytes;
-    plan->off_conf_key = off;
-    off += align_up(B * d.M_pad * 4, 256);
+    plan->off_ckey = off;
+    off += align_up(B * d.M_pad * 8, 256);
     plan->off_rank = off;
     off += align_up(B * d.M_pad * 4, 256);
     plan->off_row_anchor = off;
     off += align_up(B * R * 4, 256);
     plan->off_row_box = off;
     off += align_up(B * R * 16, 256);
-    plan->off_bin_keys = off;
-    off += align_up(B * Cc * R * 8, 256);
-    plan->off_kept_keys = off;
-    off += align_up(B * Cc * (size_t)d.Kc * 8, 256);
-    plan->off_kept_count = off;
-    off += align_up(B * Cc * 4, 256);
-    plan->off_cls_range = off;
-    off += align_up(B * Cc * 16, 256);
-    plan->off_glob_keys = off;
-    off += align_up(B * (size_t)d.G * 8, 256);
-    plan->off_glob_kept = off;
-    off += align_up(B * (size_t)d.out_cap * 8, 256);
+    plan->off_mat = off;
+    off += align_up(B * R * Cc * 4, 256);
     plan->total = off;
     return true;
 }
@@ -183,22 +182,12 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
 void bind_workspace(Plan* plan, void* ws) {
     unsigned char* w = (unsigned char*)ws;
     DevParams& d = plan->d;
-    const size_t B = (size_t)d.B, Cc = (size_t)d.C;
-    int* counters = (int*)(w + plan->off_counters);
-    d.bin_count = counters;
-    d.img_max = (uint32_t*)(counters + B * Cc);
-    d.img_ncand = counters + B * Cc + B;
-    d.flag = counters + B * Cc + 2 * B;
-    d.conf_key = (uint32_t*)(w + plan->off_conf_key);
+    d.img_max = (uint32_t*)(w + plan->off_counters);
+    d.ckey = (u64*)(w + plan->off_ckey);
     d.rank = (uint32_t*)(w + plan->off_rank);
     d.row_anchor = (int*)(w + plan->off_row_anchor);
     d.row_box = (float4*)(w + plan->off_row_box);
-    d.bin_keys = (u64*)(w + plan->off_bin_keys);
-    d.kept_keys = (u64*)(w + plan->off_kept_keys);
-    d.kept_count = (int*)(w + plan->off_kept_count);
-    d.cls_range = (float4*)(w + plan->off_cls_range);
-    d.glob_keys = (u64*)(w + plan->off_glob_keys);
-    d.glob_kept = (u64*)(w + plan->off_glob_kept);
+    d.mat = (uint32_t*)(w + plan->off_mat);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -301,7 +290,9 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
 
     YPP_MARK();  // 0: start of select
     if (d.ntopk > 0) {
-        select_kernel<<<dim3(d.ntopk, d.B), SEL_THREADS, 0, stream>>>(d);
+        e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.sel_smem);
+        if (e != cudaSuccess) return cuda_rc(e);
+        select_kernel<<<dim3(d.ntopk, d.B), SEL_THREADS, plan.sel_smem, stream>>>(d);
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
     }
     YPP_MARK();  // 1: start of decode (TMA)
@@ -342,16 +333,12 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
             decode_ldg_kernel<1><<<d.ldg_blocks, 128, 0, stream>>>(d);
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
     }
-    YPP_MARK();  // 3: start of per-class NMS
-    nms_class_kernel<<<dim3(d.C, d.B), NMS_THREADS, 0, stream>>>(d);
+    YPP_MARK();  // 3: start of the per-image NMS
+    e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.nms_smem);
+    if (e != cudaSuccess) return cuda_rc(e);
+    nms_image_kernel<<<d.B, NMS_THREADS, plan.nms_smem, stream>>>(d);
     if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
-    YPP_MARK();  // 4: start of final merge
-    final_kernel<<<d.B, SEL_THREADS, 0, stream>>>(d);
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
-    YPP_MARK();  // 5: start of global NMS
-    nms_global_kernel<<<d.B, NMS_THREADS, 0, stream>>>(d);
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
-    YPP_MARK();  // 6: end
+    YPP_MARK();  // 4: end
 #undef YPP_MARK
     return YOLOPP_OK;
 }
@@ -390,7 +377,7 @@ int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info) {
             info->ldg_bytes_per_image += bytes;
         }
     }
-    int launches = 3;  // nms_class, final, nms_global
+    int launches = 1;  // nms_image
     if (d.ntopk > 0) ++launches;
     if (d.tma_tiles > 0) ++launches;
     if (d.ldg_blocks > 0) ++launches;

@@ -67,15 +67,12 @@ __device__ __forceinline__ float ord2f(uint32_t o) {
     return __uint_as_float(u);
 }
 
-// candidate key: ascending key order == (score desc, row asc, class asc) == (score desc, flat index asc)
-constexpr int KEY_CLASS_BITS = 12;
-constexpr int KEY_ROW_BITS = 20;
-__device__ __forceinline__ u64 make_key(float score, uint32_t row, uint32_t cls) {
-    return ((u64)(~f2ord(score)) << 32) | ((u64)row << KEY_CLASS_BITS) | (u64)cls;
-}
+// candidate key: (~ord(score) << 32) | flat candidate index (row * C + class, the reference's own flat index,
+// bbox_nms.py:47-49): ascending key order == (score desc, flat index asc).
+__device__ __forceinline__ u64 make_key(float score, uint32_t flat) { return ((u64)(~f2ord(score)) << 32) | (u64)flat; }
 __device__ __forceinline__ float key_score(u64 k) { return ord2f(~(uint32_t)(k >> 32)); }
-__device__ __forceinline__ uint32_t key_row(u64 k) { return ((uint32_t)k >> KEY_CLASS_BITS) & ((1u << KEY_ROW_BITS) - 1); }
-__device__ __forceinline__ uint32_t key_cls(u64 k) { return (uint32_t)k & ((1u << KEY_CLASS_BITS) - 1); }
+__device__ __forceinline__ uint32_t key_flat(u64 k) { return (uint32_t)k; }
+constexpr uint32_t SCORE_NONE = 0xFFFFFFFFu;  // score-matrix entry of a (row, class) pair that is not a candidate
 
 // ------------------------------------------------------------------------------------------------
 // IoU predicate of mmcv nms_cpu:  inter / (area_i + area_j - inter) > thr   (IEEE fp32, division form)
@@ -234,6 +231,151 @@ __device__ __forceinline__ int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
     return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// adaptive two-pass selection of the smallest keys (fast path of every top-k on the path)
+// ------------------------------------------------------------------------------------------------
+constexpr int TS_BINS = 2048;
+struct TopSelSmem {
+    int hist[TS_BINS];
+    int wsum[32];
+    int kb, above, bsize, count;
+    u64 red[2][32];
+    SelectSmem rs;  // fallback radix select
+};
+
+// block-wide min / max of 64-bit values (all threads call; result broadcast)
+__device__ __forceinline__ void block_minmax(u64 vmin, u64 vmax, u64& omin, u64& omax, TopSelSmem& S) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 a = __shfl_xor_sync(0xffffffffu, vmin, o), b = __shfl_xor_sync(0xffffffffu, vmax, o);
+        vmin = a < vmin ? a : vmin;
+        vmax = b > vmax ? b : vmax;
+    }
+    if (lane == 0) {
+        S.red[0][warp] = vmin;
+        S.red[1][warp] = vmax;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        u64 a = lane < nw ? S.red[0][lane] : ~0ull, b = lane < nw ? S.red[1][lane] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            u64 a2 = __shfl_xor_sync(0xffffffffu, a, o), b2 = __shfl_xor_sync(0xffffffffu, b, o);
+            a = a2 < a ? a2 : a;
+            b = b2 > b ? b2 : b;
+        }
+        if (lane == 0) {
+            S.red[0][0] = a;
+            S.red[1][0] = b;
+        }
+    }
+    __syncthreads();
+    omin = S.red[0][0];
+    omax = S.red[1][0];
+    __syncthreads();
+}
+
+// Gathers into out[0..cnt) — SORTED ascending — a prefix of the ascending order of the eligible keys
+// (eligible: fetch(i,key) && lo_incl <= key <= hi_incl) that holds at least min(m, #eligible) keys; cnt <= cap.
+// Fast path: one histogram pass over the 11 bits below the common prefix of [lo_incl, hi_incl], one gather
+// pass, one smem sort. Falls back to the exact 8-bit radix select when the pivot bucket does not fit.
+// Requires unique keys, cap a power of two >= m, blockDim.x in {256, 512, 1024}; all threads call.
+template <class Fetch>
+__device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 hi_incl, int m, u64* out, int cap,
+                                    TopSelSmem& S) {
+    const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
+    const u64 x = lo_incl ^ hi_incl;
+    int shift = 0;
+    if (x) {
+        int hb = 63 - __clzll((long long)x);
+        shift = hb > 10 ? hb - 10 : 0;
+    }
+    const u64 base = lo_incl >> shift;
+    for (int i = tid; i < TS_BINS; i += nth) S.hist[i] = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_slots; b0 += nth) {
+        int i = b0 + tid;
+        u64 key = 0;
+        if (i < n_slots && fetch(i, key) && key >= lo_incl && key <= hi_incl) atomicAdd(&S.hist[(int)((key >> shift) - base)], 1);
+    }
+    __syncthreads();
+    // locate the pivot bucket: per-thread partial sums -> warp scan -> block scan
+    const int per = TS_BINS / nth;  // 2, 4 or 8
+    int loc[8], s = 0;
+    for (int q = 0; q < per; ++q) {
+        loc[q] = S.hist[tid * per + q];
+        s += loc[q];
+    }
+    int incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) S.wsum[warp] = incl;
+    if (tid == 0) {
+        S.kb = -1;
+    }
+    __syncthreads();
+    int woff = 0, total = 0;
+    for (int w = 0; w < nw; ++w) {
+        int v = S.wsum[w];
+        if (w < warp) woff += v;
+        total += v;
+    }
+    if (m > total) m = total;
+    if (total == 0) return 0;
+    const int excl = woff + incl - s;
+    if (excl < m && m <= excl + s) {
+        int cum = excl;
+        for (int q = 0; q < per; ++q) {
+            if (cum + loc[q] >= m) {
+                S.kb = tid * per + q;
+                S.above = cum;
+                S.bsize = loc[q];
+                break;
+            }
+            cum += loc[q];
+        }
+    }
+    __syncthreads();
+    const int kb = S.kb, above = S.above, bsize = S.bsize;
+    __syncthreads();
+    int cnt;
+    if (above + bsize <= cap) {
+        if (tid == 0) S.count = 0;
+        __syncthreads();
+        for (int b0 = 0; b0 < n_slots; b0 += nth) {
+            int i = b0 + tid;
+            u64 key = 0;
+            bool v = (i < n_slots) && fetch(i, key) && key >= lo_incl && key <= hi_incl;
+            v = v && ((int)((key >> shift) - base) <= kb);
+            unsigned bal = __ballot_sync(0xffffffffu, v);
+            int slot0 = 0;
+            if (lane == 0 && bal) slot0 = atomicAdd(&S.count, __popc(bal));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+            if (v) {
+                int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
+                if (slot < cap) out[slot] = key;
+            }
+        }
+        __syncthreads();
+        cnt = S.count < cap ? S.count : cap;
+        __syncthreads();
+    } else {
+        const bool has_lo = lo_incl > 0;
+        auto f2 = [&](int i, u64& key) -> bool { return fetch(i, key) && key <= hi_incl; };
+        u64 T = radix_select(f2, n_slots, has_lo, lo_incl - 1, m, S.rs);
+        cnt = gather_le(f2, n_slots, has_lo, lo_incl - 1, T, out, cap, S.rs);
+    }
+    const int p2 = next_pow2(cnt);
+    for (int i = cnt + tid; i < p2; i += nth) out[i] = ~0ull;
+    __syncthreads();
+    bitonic_sort(out, p2);
+    return cnt;
 }
 
 // ------------------------------------------------------------------------------------------------

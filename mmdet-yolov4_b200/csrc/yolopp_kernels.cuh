@@ -1,12 +1,12 @@
 // yolopp_kernels.cuh — the kernels of the post-processing path (sm_100a). Included by yolopp_capi.cu.
 //
-//   K0 select_kernel      objectness top-k per (image, segment): radix select + smem sort -> rank map
-//   K1 decode_tma_kernel  TMA-streamed fused decode + score + threshold + per-class binning (aligned levels)
+//   K0 select_kernel      objectness top-k per (image, segment): adaptive 2-pass select + smem sort -> rank map
+//   K1 decode_tma_kernel  TMA-streamed fused decode + score + threshold -> dense (row, class) score matrix
 //      decode_ldg_kernel  same semantics with plain coalesced loads (HW % 4 != 0 levels, dense admission)
-//   K3 nms_class_kernel   per (image, class): sort, class-offset boxes, greedy NMS with a kept list
-//   K4 final_kernel       per image: regime decision, top max_per_img over all classes, gather outputs
-//   K5 nms_global_kernel  per image, only when the reference's single-problem regime (n < split_thr) is not
-//                         separable by class: one global greedy pass
+//   K2 nms_image_kernel   per image: candidates visited in global (score desc, flat index asc) order, fetched in
+//                         sorted chunks by the adaptive select; greedy NMS against a kept list with the
+//                         reference's regime rule (n < split_thr: one problem over class-offset boxes;
+//                         else: classes independent); stops at max_per_img kept and writes the outputs.
 #pragma once
 #include "yolopp_device.cuh"
 
@@ -17,16 +17,17 @@ constexpr int MAXA = 8;
 constexpr uint32_t RANK_INVALID = 0xFFFFFFFFu;
 
 constexpr int TILE_T = 60;       // positions per TMA tile: 240-byte rows (16-B multiple), row pitch = 4*odd banks
-constexpr int DEC_STAGES = 4;    // TMA pipeline depth
-constexpr int DEC_CWARPS = 4;    // consumer warps per CTA (+1 producer warp)
+constexpr int DEC_STAGES = 4;    // TMA pipeline depth == consumer warps: every consumer warp owns one stage
+constexpr int DEC_CWARPS = 4;    // consumer warps per CTA (+1 producer warp), one whole tile per warp
 constexpr int DEC_THREADS = 32 * (1 + DEC_CWARPS);
 
 constexpr int SEL_THREADS = 1024;
-constexpr int SEL_MAX_K = 4096;  // smem sort capacity of K0 / K4
+constexpr int SEL_MAX_K = 4096;  // largest nms_pre the select kernel sorts in shared memory
 
-constexpr int NMS_THREADS = 256;
-constexpr int NMS_CH = 1024;     // candidates sorted / staged per chunk
-constexpr int NMS_KS = 512;      // kept boxes held in shared memory (the rest are re-read from global)
+constexpr int NMS_THREADS = 1024;
+constexpr int NMS_KCAP = 2048;   // sorted-chunk buffer (keys)
+constexpr int NMS_CH = 1024;     // candidates staged (boxes) per chunk
+constexpr int NMS_MAX_KEEP = 4096;
 
 struct LevelDev {
     const float* ptr;
@@ -48,6 +49,7 @@ struct SegDev {
     int k;        // rows kept (k == N when no top-k runs)
     int row_off;  // first row of the segment
     int has_topk;
+    int m_begin, m_end;  // plane-major index range of the segment
 };
 
 struct DevParams {
@@ -56,26 +58,18 @@ struct DevParams {
     int topk_segs[MAXL];
     int N, M_pad, R;
     float score_thr, conf_thr, iou_thr, foff;
-    int split_thr, nms_agnostic, m_eff, Kc, out_cap, rescale;
-    int G;  // capacity of glob_keys per image
+    int split_thr, nms_agnostic, m_eff, keep_cap, out_cap, rescale;
+    int sel_kcap;  // key buffer (power of two) of the select kernel
     int tma_tiles, ldg_blocks;
     LevelDev lv[MAXL];
     SegDev seg[MAXL];
     // workspace
-    uint32_t* conf_key;  // [B][M_pad]
-    uint32_t* rank;      // [B][M_pad]
+    u64* ckey;           // [B][M_pad]  (~ord(conf) << 32 | n), ~0 in the alignment padding
+    uint32_t* rank;      // [B][M_pad]  row of each anchor (plane-major), RANK_INVALID when not admitted
     int* row_anchor;     // [B][R]
     float4* row_box;     // [B][R]
-    u64* bin_keys;       // [B][C][R]
-    int* bin_count;      // [B][C]
+    uint32_t* mat;       // [B][R][C]   score bits of candidate (row, class), SCORE_NONE otherwise
     uint32_t* img_max;   // [B]  f2ord(max coordinate over candidate boxes)
-    int* img_ncand;      // [B]
-    u64* kept_keys;      // [B][C][Kc]
-    int* kept_count;     // [B][C]
-    float4* cls_range;   // [B][C]  (min x1', min y1', max x2', max y2') of the class-offset boxes
-    int* flag;           // [B]  1: image needs the global pass
-    u64* glob_keys;      // [B][G]
-    u64* glob_kept;      // [B][out_cap]
     const float* scale;  // [B][4] or null
     // outputs
     float* o_dets;
@@ -90,17 +84,20 @@ struct DevParams {
 // ------------------------------------------------------------------------------------------------
 // K0: objectness top-k
 // ------------------------------------------------------------------------------------------------
-// One CTA per (top-k segment, image). Keys are (~ord(conf) << 32 | n): ascending = (conf desc, anchor asc).
+// One CTA per (top-k segment, image). Keys are (~ord(conf) << 32 | n): ascending = (conf desc, anchor asc) —
+// the canonical order of conf_pred.topk(nms_pre) (yolocsp_head.py:350-355 / yolo_head.py:281-302).
 __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_constant__ DevParams P) {
-    __shared__ SelectSmem S;
-    __shared__ u64 sel[SEL_MAX_K];
+    extern __shared__ __align__(16) unsigned char sel_smem[];
+    __shared__ TopSelSmem S;
+    u64* sel = reinterpret_cast<u64*>(sel_smem);
     const int b = blockIdx.y;
     const SegDev& sg = P.seg[P.topk_segs[blockIdx.x]];
     const int tid = threadIdx.x;
-    uint32_t* ckey = P.conf_key + (size_t)b * P.M_pad;
+    u64* ckey = P.ckey + (size_t)b * P.M_pad;
     uint32_t* rank = P.rank + (size_t)b * P.M_pad;
 
-    // pass 0: objectness of every anchor of the segment -> 32-bit key, rank map cleared
+    // pass 0: objectness of every anchor of the segment -> composite key; rank map cleared; key range
+    u64 kmin = ~0ull, kmax = 0ull;
     for (int li = 0; li < sg.num_levels; ++li) {
         const LevelDev& lv = P.lv[sg.first_level + li];
         for (int a = 0; a < P.A; ++a) {
@@ -108,56 +105,41 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
             for (int hw = tid; hw < lv.HW; hw += SEL_THREADS) {
                 float conf = c_sigmoid(__ldg(plane + hw));
                 int m = lv.m_off + a * lv.HW + hw;
-                ckey[m] = ~f2ord(conf);
+                u64 key = ((u64)(~f2ord(conf)) << 32) | (u64)(uint32_t)(lv.n_off + hw * P.A + a);
+                ckey[m] = key;
                 rank[m] = RANK_INVALID;
+                kmin = key < kmin ? key : kmin;
+                kmax = key > kmax ? key : kmax;
             }
         }
+        // alignment padding between levels never matches a key
+        const int pad0 = lv.m_off + P.A * lv.HW, pad1 = (pad0 + 3) & ~3;
+        if (tid < pad1 - pad0) ckey[pad0 + tid] = ~0ull;
     }
-    __syncthreads();
+    u64 gmin, gmax;
+    block_minmax(kmin, kmax, gmin, gmax, S);  // also orders the global writes above (block barrier)
 
-    // slots are enumerated plane-major inside the segment; every level of a segment is contiguous in m
-    // except for the alignment padding, so enumerate per level.
-    const int first = sg.first_level, nl = sg.num_levels, A = P.A;
-    const LevelDev* lvp = P.lv;
+    const u64* kp = ckey + sg.m_begin;
     auto fetch = [=](int i, u64& key) -> bool {
-        // i in [0, seg.N): locate level
-        int l = first;
-        int rem = i;
-        for (int q = 0; q < nl; ++q) {
-            int cnt = lvp[first + q].HW * A;
-            if (rem < cnt) {
-                l = first + q;
-                break;
-            }
-            rem -= cnt;
-        }
-        const LevelDev& lv = lvp[l];
-        int a = rem / lv.HW, hw = rem - a * lv.HW;
-        uint32_t n = (uint32_t)(lv.n_off + hw * A + a);
-        key = ((u64)ckey[lv.m_off + rem] << 32) | (u64)n;
-        return true;
+        key = kp[i];
+        return key != ~0ull;
     };
-    const int k = sg.k;
-    u64 T = radix_select(fetch, sg.N, false, 0ull, k, S);
-    int cnt = gather_le(fetch, sg.N, false, 0ull, T, sel, SEL_MAX_K, S);
-    const int p2 = next_pow2(cnt);
-    for (int i = cnt + tid; i < p2; i += SEL_THREADS) sel[i] = ~0ull;
-    __syncthreads();
-    bitonic_sort(sel, p2);
-    for (int i = tid; i < cnt; i += SEL_THREADS) {
-        uint32_t n = (uint32_t)sel[i];
-        // n -> (level, hw, a) -> m
+    const int cnt = select_sorted_prefix(fetch, sg.m_end - sg.m_begin, gmin, gmax, sg.k, sel, P.sel_kcap, S);
+    const int k = cnt < sg.k ? cnt : sg.k;
+    const int first = sg.first_level, nl = sg.num_levels, A = P.A;
+    for (int i = tid; i < k; i += SEL_THREADS) {
+        const int n = (int)(uint32_t)sel[i];
         int l = first;
         for (int q = nl - 1; q >= 0; --q)
-            if ((int)n >= lvp[first + q].n_off) {
+            if (n >= P.lv[first + q].n_off) {
                 l = first + q;
                 break;
             }
-        const LevelDev& lv = lvp[l];
-        int loc = (int)n - lv.n_off;
-        int hw = loc / A, a = loc - hw * A;
+        const LevelDev& lv = P.lv[l];
+        const int loc = n - lv.n_off;
+        const int hw = loc / A, a = loc - hw * A;
         rank[lv.m_off + a * lv.HW + hw] = (uint32_t)(sg.row_off + i);
-        P.row_anchor[(size_t)b * P.R + sg.row_off + i] = (int)n;
+        P.row_anchor[(size_t)b * P.R + sg.row_off + i] = n;
     }
 }
 
@@ -219,7 +201,9 @@ struct TmapPack {
 };
 
 // Persistent, warp-specialised: warp 0 streams (NA x TILE_T) tiles of the raw head tensor into a 4-stage smem
-// ring with TMA; 4 consumer warps walk the admitted anchors of each tile (lanes over classes).
+// ring with TMA (+ the tile's rank-map row with a 1-D bulk copy); each of the 4 consumer warps owns one stage
+// and processes whole tiles: admitted anchors one after the other, lanes over classes, scores written with
+// coalesced stores into the (row, class) matrix. No atomics with a return value anywhere.
 template <int MODE>
 __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_constant__ DevParams P,
                                                                   const __grid_constant__ TmapPack maps) {
@@ -236,7 +220,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
     if (threadIdx.x == 0) {
         for (int s = 0; s < DEC_STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], DEC_CWARPS);
+            mbar_init(&empty[s], 1);
         }
         fence_mbar_init();
     }
@@ -270,10 +254,9 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
         }
         return;
     }
-    // ---------------- consumers ----------------
+    // ---------------- consumers: warp cw takes iterations it == cw (mod DEC_CWARPS), stage == cw ----------------
     const int cw = warp - 1;
-    int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+    for (int it = cw, t = blockIdx.x + cw * gridDim.x; t < total; it += DEC_CWARPS, t += DEC_CWARPS * gridDim.x) {
         const int s = it % DEC_STAGES;
         const uint32_t ph = (uint32_t)(it / DEC_STAGES) & 1u;
         int l = 0;
@@ -291,20 +274,16 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
         const float* tile = reinterpret_cast<const float*>(stages + (size_t)s * stage_bytes);
         const uint32_t* rk = reinterpret_cast<const uint32_t*>(stages + (size_t)s * stage_bytes + tile_bytes);
 
-        // admitted positions of the tile as a 64-bit mask (identical in every consumer warp)
+        // admitted positions of the tile as a 64-bit mask
         uint32_t r_lo = RANK_INVALID, r_hi = RANK_INVALID;
         {
-            int p0 = lane, p1 = lane + 32;
-            if (hw0 + p0 < lv.HW)
-                r_lo = sg.has_topk ? rk[p0]
-                                   : (uint32_t)(sg.row_off + (lv.n_off - P.lv[sg.first_level].n_off) + (hw0 + p0) * P.A + a);
-            if (p1 < TILE_T && hw0 + p1 < lv.HW)
-                r_hi = sg.has_topk ? rk[p1]
-                                   : (uint32_t)(sg.row_off + (lv.n_off - P.lv[sg.first_level].n_off) + (hw0 + p1) * P.A + a);
+            const int p0 = lane, p1 = lane + 32;
+            const int rbase = sg.row_off + (lv.n_off - P.lv[sg.first_level].n_off) + a;
+            if (hw0 + p0 < lv.HW) r_lo = sg.has_topk ? rk[p0] : (uint32_t)(rbase + (hw0 + p0) * P.A);
+            if (p1 < TILE_T && hw0 + p1 < lv.HW) r_hi = sg.has_topk ? rk[p1] : (uint32_t)(rbase + (hw0 + p1) * P.A);
         }
         uint32_t m_lo = __ballot_sync(0xffffffffu, r_lo != RANK_INVALID);
         uint32_t m_hi = __ballot_sync(0xffffffffu, r_hi != RANK_INVALID);
-        int idx = 0;
         while (m_lo | m_hi) {
             int pos;
             if (m_lo) {
@@ -314,8 +293,8 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
                 pos = 32 + __ffs(m_hi) - 1;
                 m_hi &= m_hi - 1;
             }
-            if ((idx++ % DEC_CWARPS) != cw) continue;
             const uint32_t r = __shfl_sync(0xffffffffu, pos < 32 ? r_lo : r_hi, pos & 31);
+            uint32_t* mrow = P.mat + ((size_t)b * P.R + r) * P.C;
 
             // attributes 0..4: one lane each
             float act = 0.f;
@@ -326,8 +305,10 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
             const float a0 = __shfl_sync(0xffffffffu, act, 0), a1 = __shfl_sync(0xffffffffu, act, 1);
             const float a2 = __shfl_sync(0xffffffffu, act, 2), a3 = __shfl_sync(0xffffffffu, act, 3);
             const float conf = __shfl_sync(0xffffffffu, act, 4);
-            if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) continue;  // yolo_head.py:365-376
-
+            if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) {  // yolo_head.py:365-376: row dropped
+                for (int c = lane; c < P.C; c += 32) mrow[c] = SCORE_NONE;
+                continue;
+            }
             const int hw = hw0 + pos;
             const int y = hw / lv.W, x = hw - y * lv.W;
             float4 bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
@@ -336,42 +317,32 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
                 P.row_box[(size_t)b * P.R + r] = bx;
                 if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + r] = lv.n_off + hw * P.A + a;
             }
-
-            int npass = 0;
+            bool any = false;
             if (P.agnostic) {
                 // cls_pred = conf_pred[:, None]  (yolocsp_head.py:360): one class, score = objectness
-                bool pass = (lane == 0) && (conf > P.score_thr);
-                if (pass) {
-                    int slot = atomicAdd(&P.bin_count[b], 1);
-                    if (slot < P.R) P.bin_keys[(size_t)b * P.R + slot] = make_key(conf, r, 0);
-                }
-                npass = __popc(__ballot_sync(0xffffffffu, pass));
+                const bool pass = conf > P.score_thr;
+                if (lane == 0) mrow[0] = pass ? __float_as_uint(conf) : SCORE_NONE;
+                any = pass;
             } else {
                 for (int c0 = 0; c0 < P.C; c0 += 32) {
                     const int c = c0 + lane;
                     bool pass = false;
-                    float score = 0.f;
                     if (c < P.C) {
-                        float sgm = c_sigmoid(tile[(5 + c) * TILE_T + pos]);
+                        const float sgm = c_sigmoid(tile[(5 + c) * TILE_T + pos]);
+                        float score;
                         if (MODE == 0) {
-                            score = fmul(sgm, conf);  // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
+                            score = fmul(sgm, conf);     // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
                             pass = score > P.score_thr;  // bbox_nms.py:54
                         } else {
                             pass = sgm > P.score_thr;  // threshold on the class score alone (bbox_nms.py:54) ...
                             score = fmul(sgm, conf);   // ... then scores * score_factors     (bbox_nms.py:57-62)
                         }
+                        mrow[c] = pass ? __float_as_uint(score) : SCORE_NONE;
                     }
-                    if (pass) {
-                        int slot = atomicAdd(&P.bin_count[b * P.C + c], 1);
-                        if (slot < P.R) P.bin_keys[((size_t)b * P.C + c) * P.R + slot] = make_key(score, r, (uint32_t)c);
-                    }
-                    npass += __popc(__ballot_sync(0xffffffffu, pass));
+                    any |= __any_sync(0xffffffffu, pass);
                 }
             }
-            if (npass > 0 && lane == 0) {
-                atomicAdd(&P.img_ncand[b], npass);
-                atomicMax(&P.img_max[b], f2ord(box_max(bx)));
-            }
+            if (any && lane == 0) atomicMax(&P.img_max[b], f2ord(box_max(bx)));  // boxes.max() (mmcv batched_nms)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
@@ -393,197 +364,189 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
     const int ht = loc - plane * lv.tpp;
     const int b = plane / P.A, a = plane - b * P.A;
     const int hw = ht * 128 + threadIdx.x;
-    const int lane = threadIdx.x & 31;
     const SegDev& sg = P.seg[lv.seg];
     const float* slab = lv.ptr + (size_t)plane * P.NA * lv.HW;
 
-    bool adm = hw < lv.HW;
-    uint32_t r = RANK_INVALID;
-    if (adm) {
-        r = row_of(P, lv, b, a, hw);
-        adm = (r != RANK_INVALID);
+    if (hw >= lv.HW) return;
+    const uint32_t r = row_of(P, lv, b, a, hw);
+    if (r == RANK_INVALID) return;
+    uint32_t* mrow = P.mat + ((size_t)b * P.R + r) * P.C;
+    const float t0 = __ldg(slab + 0 * (size_t)lv.HW + hw), t1 = __ldg(slab + 1 * (size_t)lv.HW + hw);
+    const float t2 = __ldg(slab + 2 * (size_t)lv.HW + hw), t3 = __ldg(slab + 3 * (size_t)lv.HW + hw);
+    const float conf = c_sigmoid(__ldg(slab + 4 * (size_t)lv.HW + hw));
+    if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) {
+        for (int c = 0; c < P.C; ++c) mrow[c] = SCORE_NONE;
+        return;
     }
-    float conf = 0.f;
-    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (adm) {
-        float t0 = __ldg(slab + 0 * (size_t)lv.HW + hw), t1 = __ldg(slab + 1 * (size_t)lv.HW + hw);
-        float t2 = __ldg(slab + 2 * (size_t)lv.HW + hw), t3 = __ldg(slab + 3 * (size_t)lv.HW + hw);
-        conf = c_sigmoid(__ldg(slab + 4 * (size_t)lv.HW + hw));
-        if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) adm = false;
-        if (adm) {
-            float a0 = c_sigmoid(t0), a1 = c_sigmoid(t1);
-            float a2 = (MODE == 0) ? c_sigmoid(t2) : c_expf(t2);
-            float a3 = (MODE == 0) ? c_sigmoid(t3) : c_expf(t3);
-            const int y = hw / lv.W, x = hw - y * lv.W;
-            bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
-            if (P.rescale) bx = rescale_box(bx, P.scale + 4 * b);
-            P.row_box[(size_t)b * P.R + r] = bx;
-            if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + r] = lv.n_off + hw * P.A + a;
-        }
-    }
-    int npass = 0;
+    const float a0 = c_sigmoid(t0), a1 = c_sigmoid(t1);
+    const float a2 = (MODE == 0) ? c_sigmoid(t2) : c_expf(t2);
+    const float a3 = (MODE == 0) ? c_sigmoid(t3) : c_expf(t3);
+    const int y = hw / lv.W, x = hw - y * lv.W;
+    float4 bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
+    if (P.rescale) bx = rescale_box(bx, P.scale + 4 * b);
+    P.row_box[(size_t)b * P.R + r] = bx;
+    if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + r] = lv.n_off + hw * P.A + a;
+    bool any = false;
     if (P.agnostic) {
-        bool pass = adm && (conf > P.score_thr);
-        unsigned bal = __ballot_sync(0xffffffffu, pass);
-        if (bal) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&P.bin_count[b], __popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) {
-                int slot = base + __popc(bal & ((1u << lane) - 1u));
-                if (slot < P.R) P.bin_keys[(size_t)b * P.R + slot] = make_key(conf, r, 0);
-                npass = 1;
-            }
-        }
+        any = conf > P.score_thr;
+        mrow[0] = any ? __float_as_uint(conf) : SCORE_NONE;
     } else {
         const float* cls = slab + 5 * (size_t)lv.HW + hw;
-#pragma unroll 4
+#pragma unroll 8
         for (int c = 0; c < P.C; ++c) {
-            bool pass = false;
-            float score = 0.f;
-            if (adm) {
-                float sgm = c_sigmoid(__ldg(cls + (size_t)c * lv.HW));
-                if (MODE == 0) {
-                    score = fmul(sgm, conf);
-                    pass = score > P.score_thr;
-                } else {
-                    pass = sgm > P.score_thr;
-                    score = fmul(sgm, conf);
-                }
+            const float sgm = c_sigmoid(__ldg(cls + (size_t)c * lv.HW));
+            float score;
+            bool pass;
+            if (MODE == 0) {
+                score = fmul(sgm, conf);
+                pass = score > P.score_thr;
+            } else {
+                pass = sgm > P.score_thr;
+                score = fmul(sgm, conf);
             }
-            unsigned bal = __ballot_sync(0xffffffffu, pass);
-            if (bal) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&P.bin_count[b * P.C + c], __popc(bal));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (pass) {
-                    int slot = base + __popc(bal & ((1u << lane) - 1u));
-                    if (slot < P.R) P.bin_keys[((size_t)b * P.C + c) * P.R + slot] = make_key(score, r, (uint32_t)c);
-                    ++npass;
-                }
-            }
+            mrow[c] = pass ? __float_as_uint(score) : SCORE_NONE;
+            any |= pass;
         }
     }
-    // per-image candidate count and max coordinate: warp-reduce, one atomic per warp
-    uint32_t mx = npass > 0 ? f2ord(box_max(bx)) : 0u;
-    int tot = npass;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        uint32_t om = __shfl_xor_sync(0xffffffffu, mx, o);
-        mx = om > mx ? om : mx;
-    }
-    if (lane == 0 && tot > 0) {
-        atomicAdd(&P.img_ncand[b], tot);
-        atomicMax(&P.img_max[b], mx);
-    }
+    if (any) atomicMax(&P.img_max[b], f2ord(box_max(bx)));
 }
 
 // ------------------------------------------------------------------------------------------------
-// greedy NMS over a stream of keys (shared by K3 and K5)
+// K2: per-image NMS over the merged, score-ordered candidate stream
 // ------------------------------------------------------------------------------------------------
-struct NmsSmem {
-    u64 keys[NMS_CH];
-    float cx1[NMS_CH], cy1[NMS_CH], cx2[NMS_CH], cy2[NMS_CH], car[NMS_CH];
-    float kx1[NMS_KS], ky1[NMS_KS], kx2[NMS_KS], ky2[NMS_KS], kar[NMS_KS];
-    SelectSmem sel;
-    unsigned sup;
-    int nk;
-};
+// Suppression rule of mmcv batched_nms, both regimes:
+//   n < split_thr : ONE greedy pass over all candidates; boxes carry the class offset idx * (max + 1) unless
+//                   nms class_agnostic, so classes normally cannot touch — but the test is purely geometric,
+//                   exactly like the reference (cross-class suppression possible when offset ranges overlap).
+//   n >= split_thr: classes are processed independently (a kept box only suppresses boxes of its own class),
+//                   still on the offset boxes.
+// In both regimes the result order is (score desc, flat index asc) and only the first max_num are returned,
+// so candidates are visited in that global order and the pass stops once `cap` boxes are kept.
+__global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_constant__ DevParams P) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    __shared__ TopSelSmem S;
+    __shared__ unsigned s_sup;
+    __shared__ int s_nk, s_cnt;
+    const int cap = P.keep_cap;
+    u64* keys = reinterpret_cast<u64*>(nms_smem);                 // [NMS_KCAP]
+    u64* kkey = keys + NMS_KCAP;                                   // [cap]
+    float* cx1 = reinterpret_cast<float*>(kkey + cap);             // [NMS_CH] x 5
+    float* cy1 = cx1 + NMS_CH;
+    float* cx2 = cy1 + NMS_CH;
+    float* cy2 = cx2 + NMS_CH;
+    float* car = cy2 + NMS_CH;
+    int* ccl = reinterpret_cast<int*>(car + NMS_CH);               // [NMS_CH]
+    float* kx1 = reinterpret_cast<float*>(ccl + NMS_CH);           // [cap] x 5
+    float* ky1 = kx1 + cap;
+    float* kx2 = ky1 + cap;
+    float* ky2 = kx2 + cap;
+    float* kar = ky2 + cap;
+    int* kcl = reinterpret_cast<int*>(kar + cap);                  // [cap]
 
-// class-offset box of a key:  boxes + idxs.to(boxes) * (max_coordinate + 1)   (mmcv batched_nms)
-__device__ __forceinline__ Box offset_box(const float4* row_box, u64 key, bool use_off, float mp1, float foff) {
-    float4 bx = row_box[key_row(key)];
-    Box o;
-    if (use_off) {
-        float off = fmul((float)key_cls(key), mp1);
-        o.x1 = fadd(bx.x, off);
-        o.y1 = fadd(bx.y, off);
-        o.x2 = fadd(bx.z, off);
-        o.y2 = fadd(bx.w, off);
-    } else {
-        o.x1 = bx.x;
-        o.y1 = bx.y;
-        o.x2 = bx.z;
-        o.y2 = bx.w;
-    }
-    o.area = box_area(o.x1, o.y1, o.x2, o.y2, foff);
-    return o;
-}
-
-// Greedy NMS (mmcv nms_cpu semantics) over the n unique keys gkeys[0..n), visited in ascending key order
-// (= score desc, flat index asc). Stops after `cap` kept. Kept keys are written, in order, to kept_out.
-// Returns the number kept (same value in every thread). blockDim.x == NMS_THREADS.
-__device__ int nms_stream(const u64* __restrict__ gkeys, int n, const float4* __restrict__ row_box, bool use_off,
-                          float mp1, float foff, float thr, int cap, u64* __restrict__ kept_out, NmsSmem& S) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NW = NMS_THREADS / 32;
-    if (tid == 0) {
-        S.nk = 0;
-        S.sup = 0u;
-    }
-    __syncthreads();
-    int processed = 0;
-    u64 prev = 0ull;
-    bool first = true;
-    auto fetch = [=](int i, u64& key) -> bool {
-        key = gkeys[i];
-        return true;
-    };
-    while (processed < n && S.nk < cap) {
-        const int m = min(NMS_CH, n - processed);
-        if (n <= NMS_CH) {
-            for (int i = tid; i < n; i += NMS_THREADS) S.keys[i] = gkeys[i];
-            __syncthreads();
-        } else {
-            u64 T = radix_select(fetch, n, !first, prev, m, S.sel);
-            gather_le(fetch, n, !first, prev, T, S.keys, NMS_CH, S.sel);
+    const int C = P.C;
+    const int slots = P.R * C;
+    const uint32_t* mat = P.mat + (size_t)b * slots;
+    const float4* row_box = P.row_box + (size_t)b * P.R;
+
+    // pass 0: count the candidates and find the key range
+    u64 kmin = ~0ull, kmax = 0ull;
+    int cntl = 0;
+    for (int i = tid; i < slots; i += NMS_THREADS) {
+        const uint32_t sb = mat[i];
+        if (sb != SCORE_NONE) {
+            const u64 key = make_key(__uint_as_float(sb), (uint32_t)i);
+            kmin = key < kmin ? key : kmin;
+            kmax = key > kmax ? key : kmax;
+            ++cntl;
         }
-        const int p2 = next_pow2(m);
-        for (int i = m + tid; i < p2; i += NMS_THREADS) S.keys[i] = ~0ull;
-        __syncthreads();
-        bitonic_sort(S.keys, p2);
+    }
+    if (tid == 0) {
+        s_cnt = 0;
+        s_nk = 0;
+        s_sup = 0u;
+    }
+    u64 gmin, gmax;
+    block_minmax(kmin, kmax, gmin, gmax, S);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cntl += __shfl_xor_sync(0xffffffffu, cntl, o);
+    if (lane == 0 && cntl) atomicAdd(&s_cnt, cntl);
+    __syncthreads();
+    const int ntot = s_cnt;
+    if (tid == 0 && P.o_ncand) P.o_ncand[b] = ntot;
+    if (ntot == 0) {
+        if (tid == 0) P.o_count[b] = 0;
+        return;
+    }
+    const bool per_class = !(ntot < P.split_thr);  // regime of mmcv batched_nms
+    const bool use_off = !P.nms_agnostic;
+    const float mp1 = fadd(ord2f(P.img_max[b]), 1.0f);  // max_coordinate + 1
+    const float thr = P.iou_thr, foff = P.foff;
+
+    auto fetch = [=](int i, u64& key) -> bool {
+        const uint32_t sb = mat[i];
+        key = make_key(__uint_as_float(sb), (uint32_t)i);
+        return sb != SCORE_NONE;
+    };
+
+    int processed = 0;
+    u64 lo = gmin;
+    while (processed < ntot && s_nk < cap) {
+        const int want = min(NMS_CH, ntot - processed);
+        int got = select_sorted_prefix(fetch, slots, lo, gmax, want, keys, NMS_KCAP, S);
+        const int m = got < NMS_CH ? got : NMS_CH;  // boxes staged this round (a prefix of the sorted order)
+        if (m == 0) break;
         for (int i = tid; i < m; i += NMS_THREADS) {
-            Box bx = offset_box(row_box, S.keys[i], use_off, mp1, foff);
-            S.cx1[i] = bx.x1;
-            S.cy1[i] = bx.y1;
-            S.cx2[i] = bx.x2;
-            S.cy2[i] = bx.y2;
-            S.car[i] = bx.area;
+            const uint32_t flat = key_flat(keys[i]);
+            const int r = (int)(flat / (uint32_t)C), c = (int)(flat - (uint32_t)r * (uint32_t)C);
+            const float4 bx = row_box[r];
+            float x1 = bx.x, y1 = bx.y, x2 = bx.z, y2 = bx.w;
+            if (use_off) {  // boxes + idxs.to(boxes) * (max_coordinate + 1)
+                const float off = fmul((float)c, mp1);
+                x1 = fadd(x1, off);
+                y1 = fadd(y1, off);
+                x2 = fadd(x2, off);
+                y2 = fadd(y2, off);
+            }
+            cx1[i] = x1;
+            cy1[i] = y1;
+            cx2[i] = x2;
+            cy2[i] = y2;
+            car[i] = box_area(x1, y1, x2, y2, foff);
+            ccl[i] = c;
         }
         __syncthreads();
         for (int s0 = 0; s0 < m; s0 += 32) {
-            const int nk = S.nk;
+            const int nk = s_nk;
             if (nk >= cap) break;
             const int j = s0 + lane;
             const bool valid = j < m;
             Box bj;
-            bj.x1 = valid ? S.cx1[j] : 0.f;
-            bj.y1 = valid ? S.cy1[j] : 0.f;
-            bj.x2 = valid ? S.cx2[j] : 0.f;
-            bj.y2 = valid ? S.cy2[j] : 0.f;
-            bj.area = valid ? S.car[j] : 0.f;
+            bj.x1 = valid ? cx1[j] : 0.f;
+            bj.y1 = valid ? cy1[j] : 0.f;
+            bj.x2 = valid ? cx2[j] : 0.f;
+            bj.y2 = valid ? cy2[j] : 0.f;
+            bj.area = valid ? car[j] : 0.f;
+            const int cj = valid ? ccl[j] : -1;
             // phase A: against the kept list, kept boxes strided over the warps
             bool sup = false;
             for (int k = warp; k < nk; k += NW) {
                 Box bk;
-                if (k < NMS_KS) {
-                    bk.x1 = S.kx1[k];
-                    bk.y1 = S.ky1[k];
-                    bk.x2 = S.kx2[k];
-                    bk.y2 = S.ky2[k];
-                    bk.area = S.kar[k];
-                } else {
-                    bk = offset_box(row_box, kept_out[k], use_off, mp1, foff);
-                }
-                if (valid && !sup && iou_gt(bk, bj, thr, foff)) sup = true;
+                bk.x1 = kx1[k];
+                bk.y1 = ky1[k];
+                bk.x2 = kx2[k];
+                bk.y2 = ky2[k];
+                bk.area = kar[k];
+                const bool same = !per_class || (kcl[k] == cj);
+                if (valid && !sup && same && iou_gt(bk, bj, thr, foff)) sup = true;
             }
-            unsigned bal = __ballot_sync(0xffffffffu, sup);
-            if (lane == 0 && bal) atomicOr(&S.sup, bal);
+            const unsigned bal = __ballot_sync(0xffffffffu, sup);
+            if (lane == 0 && bal) atomicOr(&s_sup, bal);
             __syncthreads();
             // phase B: inside the 32-box group, sequential over i, parallel over j > i (warp 0)
             if (warp == 0) {
-                bool alive = valid && !((S.sup >> lane) & 1u);
+                bool alive = valid && !((s_sup >> lane) & 1u);
                 const int room = cap - nk;
                 int kept_here = 0;
                 for (int i = 0; i < 32; ++i) {
@@ -596,223 +559,54 @@ __device__ int nms_stream(const u64* __restrict__ gkeys, int n, const float4* __
                     bi.x2 = __shfl_sync(0xffffffffu, bj.x2, i);
                     bi.y2 = __shfl_sync(0xffffffffu, bj.y2, i);
                     bi.area = __shfl_sync(0xffffffffu, bj.area, i);
-                    if (lane > i && alive && iou_gt(bi, bj, thr, foff)) alive = false;
+                    const int ci = __shfl_sync(0xffffffffu, cj, i);
+                    const bool same = !per_class || (ci == cj);
+                    if (lane > i && alive && same && iou_gt(bi, bj, thr, foff)) alive = false;
                 }
                 const unsigned km = __ballot_sync(0xffffffffu, alive);
                 const int rnk = __popc(km & ((1u << lane) - 1u));
                 if (alive && rnk < room) {
                     const int kidx = nk + rnk;
-                    if (kidx < NMS_KS) {
-                        S.kx1[kidx] = bj.x1;
-                        S.ky1[kidx] = bj.y1;
-                        S.kx2[kidx] = bj.x2;
-                        S.ky2[kidx] = bj.y2;
-                        S.kar[kidx] = bj.area;
-                    }
-                    kept_out[kidx] = S.keys[j];
+                    kx1[kidx] = bj.x1;
+                    ky1[kidx] = bj.y1;
+                    kx2[kidx] = bj.x2;
+                    ky2[kidx] = bj.y2;
+                    kar[kidx] = bj.area;
+                    kcl[kidx] = cj;
+                    kkey[kidx] = keys[j];
                 }
                 if (lane == 0) {
-                    S.nk = nk + min(__popc(km), room);
-                    S.sup = 0u;
+                    s_nk = nk + min(__popc(km), room);
+                    s_sup = 0u;
                 }
             }
             __syncthreads();
         }
         processed += m;
-        prev = S.keys[m - 1];
-        first = false;
+        lo = keys[m - 1] + 1ull;
         __syncthreads();
     }
-    const int nk = S.nk;
-    __syncthreads();
-    return nk;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3: per (image, class) NMS
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NMS_THREADS) nms_class_kernel(const __grid_constant__ DevParams P) {
-    __shared__ NmsSmem S;
-    __shared__ float red[4][NMS_THREADS / 32];
-    const int c = blockIdx.x, b = blockIdx.y;
-    const int bin = b * P.C + c;
-    int n = P.bin_count[bin];
-    n = n < P.R ? n : P.R;
-    if (n == 0) {
-        if (threadIdx.x == 0) P.kept_count[bin] = 0;
-        return;
-    }
-    const u64* gkeys = P.bin_keys + (size_t)bin * P.R;
-    const float4* row_box = P.row_box + (size_t)b * P.R;
-    const bool use_off = !P.nms_agnostic;
-    const float mp1 = fadd(ord2f(P.img_max[b]), 1.0f);  // max_coordinate + 1
-    const int ntot = P.img_ncand[b];
-
-    // class extent of the offset boxes: only needed to decide whether the reference's single-problem regime
-    // (n < split_thr) separates by class (final_kernel)
-    if (ntot < P.split_thr && use_off) {
-        float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-        for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
-            Box bx = offset_box(row_box, gkeys[i], true, mp1, P.foff);
-            mnx = fminf(mnx, bx.x1);
-            mny = fminf(mny, bx.y1);
-            mxx = fmaxf(mxx, bx.x2);
-            mxy = fmaxf(mxy, bx.y2);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
-            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o));
-            mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
-            mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
-        }
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (lane == 0) {
-            red[0][warp] = mnx;
-            red[1][warp] = mny;
-            red[2][warp] = mxx;
-            red[3][warp] = mxy;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int w = 1; w < NMS_THREADS / 32; ++w) {
-                mnx = fminf(mnx, red[0][w]);
-                mny = fminf(mny, red[1][w]);
-                mxx = fmaxf(mxx, red[2][w]);
-                mxy = fmaxf(mxy, red[3][w]);
-            }
-            P.cls_range[bin] = make_float4(mnx, mny, mxx, mxy);
-        }
-        __syncthreads();
-    }
-    const int nk = nms_stream(gkeys, n, row_box, use_off, mp1, P.foff, P.iou_thr, P.Kc,
-                              P.kept_keys + (size_t)bin * P.Kc, S);
-    if (threadIdx.x == 0) P.kept_count[bin] = nk;
-}
-
-// ------------------------------------------------------------------------------------------------
-// output row
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void emit_det(const DevParams& P, int b, int i, u64 key) {
-    const uint32_t r = key_row(key), c = key_cls(key);
-    const float4 bx = P.row_box[(size_t)b * P.R + r];
-    float* d = P.o_dets + ((size_t)b * P.out_cap + i) * 5;
-    d[0] = bx.x;
-    d[1] = bx.y;
-    d[2] = bx.z;
-    d[3] = bx.w;
-    d[4] = key_score(key);
-    P.o_labels[(size_t)b * P.out_cap + i] = (long long)c;
-    if (P.o_anchors) P.o_anchors[(size_t)b * P.out_cap + i] = P.row_anchor[(size_t)b * P.R + r];
-    if (P.o_rows) P.o_rows[(size_t)b * P.out_cap + i] = (int)r;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4: per image merge of the per-class kept lists (+ regime decision)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SEL_THREADS) final_kernel(const __grid_constant__ DevParams P) {
-    __shared__ SelectSmem S;
-    __shared__ u64 sel[SEL_MAX_K];
-    __shared__ int s_flag, s_total;
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int ntot = P.img_ncand[b];
-    if (tid == 0) {
-        s_flag = 0;
-        s_total = 0;
-        if (P.o_ncand) P.o_ncand[b] = ntot;
-    }
-    __syncthreads();
-    if (ntot == 0) {
-        if (tid == 0) {
-            P.o_count[b] = 0;
-            P.flag[b] = 0;
-        }
-        return;
-    }
-    // regime: below split_thr the reference runs ONE greedy pass over all classes' offset boxes. That equals
-    // the per-class passes iff no two classes' offset extents intersect (otherwise -> global pass, K5).
-    if (ntot < P.split_thr) {
-        if (P.nms_agnostic) {
-            if (tid == 0) s_flag = 1;
-        } else {
-            const int C = P.C;
-            for (int pr = tid; pr < C * C; pr += SEL_THREADS) {
-                int c1 = pr / C, c2 = pr - c1 * C;
-                if (c1 >= c2) continue;
-                if (P.bin_count[b * C + c1] == 0 || P.bin_count[b * C + c2] == 0) continue;
-                float4 r1 = P.cls_range[b * C + c1], r2 = P.cls_range[b * C + c2];
-                // possible positive intersection on both axes (NaNs compare false -> flagged conservatively)
-                // (with nms offset 1 touching boxes still intersect: compare x2 + 1 strictly)
-                const float fo = P.foff;
-                bool sep = (fo == 0.f) ? ((r1.z <= r2.x) || (r2.z <= r1.x) || (r1.w <= r2.y) || (r2.w <= r1.y))
-                                       : ((fadd(r1.z, fo) < r2.x) || (fadd(r2.z, fo) < r1.x) ||
-                                          (fadd(r1.w, fo) < r2.y) || (fadd(r2.w, fo) < r1.y));
-                if (!sep) s_flag = 1;
-            }
-        }
-    }
-    __syncthreads();
-    const int flagged = s_flag;
-    if (tid == 0) P.flag[b] = flagged;
-    if (flagged) return;  // K5 produces this image
-
-    // total kept over classes
-    int part = 0;
-    for (int c = tid; c < P.C; c += SEL_THREADS) part += P.kept_count[b * P.C + c];
-    if (part) atomicAdd(&s_total, part);
-    __syncthreads();
-    const int total = s_total;
-    int want = P.m_eff > 0 ? min(P.m_eff, total) : total;
-    if (want > P.out_cap) {
-        want = P.out_cap;
+    // outputs: dets = (boxes[keep], scores[keep]), labels[keep]  (bbox_nms.py:84-93)
+    int nk = s_nk;
+    if (nk > P.out_cap) {
+        nk = P.out_cap;
         if (tid == 0) atomicMax(P.o_status, 3);  // YOLOPP_E_OVERFLOW
     }
-    const int Kc = P.Kc;
-    const u64* kk = P.kept_keys + (size_t)b * P.C * Kc;
-    const int* kcnt = P.kept_count + b * P.C;
-    auto fetch = [=](int i, u64& key) -> bool {
-        int c = i / Kc, sl = i - c * Kc;
-        if (sl >= kcnt[c]) return false;
-        key = kk[i];
-        return true;
-    };
-    const int slots = P.C * Kc;
-    u64 T = ~0ull;
-    if (want < total) T = radix_select(fetch, slots, false, 0ull, want, S);
-    int cnt = gather_le(fetch, slots, false, 0ull, T, sel, SEL_MAX_K, S);
-    const int p2 = next_pow2(cnt);
-    for (int i = cnt + tid; i < p2; i += SEL_THREADS) sel[i] = ~0ull;
-    __syncthreads();
-    bitonic_sort(sel, p2);
-    for (int i = tid; i < cnt; i += SEL_THREADS) emit_det(P, b, i, sel[i]);
-    if (tid == 0) P.o_count[b] = cnt;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K5: global single-problem NMS for flagged images
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NMS_THREADS) nms_global_kernel(const __grid_constant__ DevParams P) {
-    __shared__ NmsSmem S;
-    const int b = blockIdx.x, tid = threadIdx.x;
-    if (!P.flag[b]) return;
-    // compact the class bins of the image into one array
-    u64* g = P.glob_keys + (size_t)b * P.G;
-    int off = 0;
-    for (int c = 0; c < P.C; ++c) {
-        int cnt = P.bin_count[b * P.C + c];
-        cnt = cnt < P.R ? cnt : P.R;
-        const u64* src = P.bin_keys + ((size_t)b * P.C + c) * P.R;
-        for (int i = tid; i < cnt && off + i < P.G; i += NMS_THREADS) g[off + i] = src[i];
-        off += cnt;
+    for (int i = tid; i < nk; i += NMS_THREADS) {
+        const u64 key = kkey[i];
+        const uint32_t flat = key_flat(key);
+        const int r = (int)(flat / (uint32_t)C), c = (int)(flat - (uint32_t)r * (uint32_t)C);
+        const float4 bx = row_box[r];
+        float* d = P.o_dets + ((size_t)b * P.out_cap + i) * 5;
+        d[0] = bx.x;
+        d[1] = bx.y;
+        d[2] = bx.z;
+        d[3] = bx.w;
+        d[4] = key_score(key);
+        P.o_labels[(size_t)b * P.out_cap + i] = (long long)c;
+        if (P.o_anchors) P.o_anchors[(size_t)b * P.out_cap + i] = P.row_anchor[(size_t)b * P.R + r];
+        if (P.o_rows) P.o_rows[(size_t)b * P.out_cap + i] = r;
     }
-    const int n = off < P.G ? off : P.G;
-    __syncthreads();
-    const float mp1 = fadd(ord2f(P.img_max[b]), 1.0f);
-    int cap = P.m_eff > 0 ? P.m_eff : P.out_cap;
-    if (cap > P.out_cap) cap = P.out_cap;
-    u64* kept = P.glob_kept + (size_t)b * P.out_cap;
-    const int nk = nms_stream(g, n, P.row_box + (size_t)b * P.R, !P.nms_agnostic, mp1, P.foff, P.iou_thr, cap, kept, S);
-    for (int i = tid; i < nk; i += NMS_THREADS) emit_det(P, b, i, kept[i]);
     if (tid == 0) P.o_count[b] = nk;
 }
 

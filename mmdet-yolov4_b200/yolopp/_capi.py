@@ -107,8 +107,8 @@ class YoloppPlanInfo(ctypes.Structure):
     ]
 
 
-NUM_STAGE_EVENTS = 7
-STAGE_NAMES = ('select', 'decode_tma', 'decode_ldg', 'nms_class', 'final', 'nms_global')
+NUM_STAGE_EVENTS = 5
+STAGE_NAMES = ('select', 'decode_tma', 'decode_ldg', 'nms_image')
 
 
 def _pair(v):
