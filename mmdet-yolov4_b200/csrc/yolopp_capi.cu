@@ -128,8 +128,8 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     int kcap = 2048;
     while (kcap < 2 * max_k) kcap <<= 1;
     d.sel_kcap = kcap;
-    plan->sel_smem = (size_t)kcap * 8;
-    plan->nms_smem = (size_t)NMS_KCAP * 8 + (size_t)d.keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)d.keep_cap * 24;
+    plan->sel_smem = (size_t)kcap * 8 * 2;  // sorted keys + scatter scratch
+    plan->nms_smem = (size_t)NMS_KCAP * 8 * 2 + (size_t)d.keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)d.keep_cap * 24;
 
     // which kernel decodes which level
     const size_t stage_bytes = align_up((size_t)NA * TILE_T * 4 + TILE_T * 4, 128);
@@ -162,8 +162,8 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     // workspace layout
     size_t off = 0;
     const size_t B = (size_t)d.B, Cc = (size_t)d.C, R = (size_t)d.R;
-    plan->off_counters = off;  // img_max[B]
-    plan->counters_bytes = align_up(B * 4, 256);
+    plan->off_counters = off;  // img_max[B] | img_best[B] | img_worst[B] | img_cnt[B]
+    plan->counters_bytes = align_up(4 * B * 4, 256);
     off += plan->counters_bytes;
     plan->off_ckey = off;
     off += align_up(B * d.M_pad * 8, 256);
@@ -183,6 +183,9 @@ void bind_workspace(Plan* plan, void* ws) {
     unsigned char* w = (unsigned char*)ws;
     DevParams& d = plan->d;
     d.img_max = (uint32_t*)(w + plan->off_counters);
+    d.img_best = d.img_max + d.B;
+    d.img_worst = d.img_max + 2 * (size_t)d.B;
+    d.img_cnt = (int*)(d.img_max + 3 * (size_t)d.B);
     d.ckey = (u64*)(w + plan->off_ckey);
     d.rank = (uint32_t*)(w + plan->off_rank);
     d.row_anchor = (int*)(w + plan->off_row_anchor);

@@ -278,14 +278,16 @@ __device__ __forceinline__ void block_minmax(u64 vmin, u64 vmax, u64& omin, u64&
     __syncthreads();
 }
 
-// Gathers into out[0..cnt) — SORTED ascending — a prefix of the ascending order of the eligible keys
+// Writes into out[0..cnt) — SORTED ascending — a prefix of the ascending order of the eligible keys
 // (eligible: fetch(i,key) && lo_incl <= key <= hi_incl) that holds at least min(m, #eligible) keys; cnt <= cap.
-// Fast path: one histogram pass over the 11 bits below the common prefix of [lo_incl, hi_incl], one gather
-// pass, one smem sort. Falls back to the exact 8-bit radix select when the pivot bucket does not fit.
-// Requires unique keys, cap a power of two >= m, blockDim.x in {256, 512, 1024}; all threads call.
+// Fast path (bucket sort): one histogram pass over the 11 bits below the common prefix of [lo_incl, hi_incl],
+// an exclusive scan, one scatter pass (keys land grouped by bucket), and a ranking step inside each bucket.
+// Falls back to the exact 8-bit radix select + bitonic sort when the pivot bucket does not fit in `cap`.
+// Requires unique keys, cap a power of two >= m, blockDim.x in {256, 512, 1024}; `tmp` is scratch of `cap`
+// keys; all threads call.
 template <class Fetch>
-__device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 hi_incl, int m, u64* out, int cap,
-                                    TopSelSmem& S) {
+__device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 hi_incl, int m, u64* out, u64* tmp,
+                                    int cap, TopSelSmem& S) {
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
     const u64 x = lo_incl ^ hi_incl;
     int shift = 0;
@@ -296,13 +298,22 @@ __device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 h
     const u64 base = lo_incl >> shift;
     for (int i = tid; i < TS_BINS; i += nth) S.hist[i] = 0;
     __syncthreads();
-    for (int b0 = 0; b0 < n_slots; b0 += nth) {
-        int i = b0 + tid;
-        u64 key = 0;
-        if (i < n_slots && fetch(i, key) && key >= lo_incl && key <= hi_incl) atomicAdd(&S.hist[(int)((key >> shift) - base)], 1);
+    constexpr int U = 8;  // independent loads in flight per thread
+    for (int b0 = 0; b0 < n_slots; b0 += nth * U) {
+        u64 key[U];
+        bool ok[U];
+#pragma unroll
+        for (int q = 0; q < U; ++q) {
+            const int i = b0 + q * nth + tid;
+            key[q] = 0;
+            ok[q] = (i < n_slots) && fetch(i, key[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < U; ++q)
+            if (ok[q] && key[q] >= lo_incl && key[q] <= hi_incl) atomicAdd(&S.hist[(int)((key[q] >> shift) - base)], 1);
     }
     __syncthreads();
-    // locate the pivot bucket: per-thread partial sums -> warp scan -> block scan
+    // exclusive scan of the histogram (in place) + pivot bucket: per-thread partial sums -> warp scan -> block scan
     const int per = TS_BINS / nth;  // 2, 4 or 8
     int loc[8], s = 0;
     for (int q = 0; q < per; ++q) {
@@ -316,9 +327,7 @@ __device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 h
         if (lane >= o) incl += v;
     }
     if (lane == 31) S.wsum[warp] = incl;
-    if (tid == 0) {
-        S.kb = -1;
-    }
+    if (tid == 0) S.kb = -1;
     __syncthreads();
     int woff = 0, total = 0;
     for (int w = 0; w < nw; ++w) {
@@ -329,52 +338,65 @@ __device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 h
     if (m > total) m = total;
     if (total == 0) return 0;
     const int excl = woff + incl - s;
-    if (excl < m && m <= excl + s) {
+    {
         int cum = excl;
         for (int q = 0; q < per; ++q) {
-            if (cum + loc[q] >= m) {
+            S.hist[tid * per + q] = cum;  // exclusive offset of the bucket
+            if (cum < m && m <= cum + loc[q]) {
                 S.kb = tid * per + q;
                 S.above = cum;
                 S.bsize = loc[q];
-                break;
             }
             cum += loc[q];
         }
     }
     __syncthreads();
     const int kb = S.kb, above = S.above, bsize = S.bsize;
-    __syncthreads();
     int cnt;
     if (above + bsize <= cap) {
-        if (tid == 0) S.count = 0;
-        __syncthreads();
-        for (int b0 = 0; b0 < n_slots; b0 += nth) {
-            int i = b0 + tid;
-            u64 key = 0;
-            bool v = (i < n_slots) && fetch(i, key) && key >= lo_incl && key <= hi_incl;
-            v = v && ((int)((key >> shift) - base) <= kb);
-            unsigned bal = __ballot_sync(0xffffffffu, v);
-            int slot0 = 0;
-            if (lane == 0 && bal) slot0 = atomicAdd(&S.count, __popc(bal));
-            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-            if (v) {
-                int slot = slot0 + __popc(bal & ((1u << lane) - 1u));
-                if (slot < cap) out[slot] = key;
+        // scatter: hist[bucket] is the running cursor of the bucket, keys land grouped by bucket in tmp
+        for (int b0 = 0; b0 < n_slots; b0 += nth * U) {
+            u64 key[U];
+            bool ok[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int i = b0 + q * nth + tid;
+                key[q] = 0;
+                ok[q] = (i < n_slots) && fetch(i, key[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                if (ok[q] && key[q] >= lo_incl && key[q] <= hi_incl) {
+                    const int bk = (int)((key[q] >> shift) - base);
+                    if (bk <= kb) {
+                        const int pos = atomicAdd(&S.hist[bk], 1);
+                        tmp[pos] = key[q];
+                    }
+                }
             }
         }
         __syncthreads();
-        cnt = S.count < cap ? S.count : cap;
+        cnt = above + bsize;
+        // rank inside the bucket: after the scatter hist[bk] is the END of bucket bk, hist[bk-1] its start
+        for (int pos = tid; pos < cnt; pos += nth) {
+            const u64 key = tmp[pos];
+            const int bk = (int)((key >> shift) - base);
+            const int st = bk ? S.hist[bk - 1] : 0, en = S.hist[bk];
+            int rnk = st;
+            for (int q = st; q < en; ++q) rnk += (tmp[q] < key) ? 1 : 0;
+            out[rnk] = key;
+        }
         __syncthreads();
     } else {
         const bool has_lo = lo_incl > 0;
         auto f2 = [&](int i, u64& key) -> bool { return fetch(i, key) && key <= hi_incl; };
         u64 T = radix_select(f2, n_slots, has_lo, lo_incl - 1, m, S.rs);
         cnt = gather_le(f2, n_slots, has_lo, lo_incl - 1, T, out, cap, S.rs);
+        const int p2 = next_pow2(cnt);
+        for (int i = cnt + tid; i < p2; i += nth) out[i] = ~0ull;
+        __syncthreads();
+        bitonic_sort(out, p2);
     }
-    const int p2 = next_pow2(cnt);
-    for (int i = cnt + tid; i < p2; i += nth) out[i] = ~0ull;
-    __syncthreads();
-    bitonic_sort(out, p2);
     return cnt;
 }
 
@@ -419,6 +441,21 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const void* tmap, int c0,
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
             smem_u32(dst)),
         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// Same, with an L2 cache policy (createpolicy): the head tensors are read exactly once -> evict_first keeps the
+// small, re-read intermediates (score matrix, rank map, boxes) resident in the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* dst, const void* tmap, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, "
+        "%4}], [%2], %5;" ::"r"(smem_u32(dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
         : "memory");
 }
 // 1-D bulk copy global -> smem (16-byte aligned, size multiple of 16), completes on `bar`.

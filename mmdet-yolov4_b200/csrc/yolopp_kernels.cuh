@@ -17,8 +17,10 @@ constexpr int MAXA = 8;
 constexpr uint32_t RANK_INVALID = 0xFFFFFFFFu;
 
 constexpr int TILE_T = 60;       // positions per TMA tile: 240-byte rows (16-B multiple), row pitch = 4*odd banks
-constexpr int DEC_STAGES = 4;    // TMA pipeline depth == consumer warps: every consumer warp owns one stage
-constexpr int DEC_CWARPS = 4;    // consumer warps per CTA (+1 producer warp), one whole tile per warp
+constexpr int DEC_STAGES = 4;    // TMA pipeline depth
+constexpr int DEC_CWARPS = 8;    // consumer warps per CTA (+1 producer warp), one whole tile per warp
+constexpr int DEC_BATCH = 4;     // admitted anchors whose logits a consumer pulls into registers at once
+constexpr int DEC_ROUNDS = 3;    // class sweeps held in registers (C <= 96); wider heads read the tile in place
 constexpr int DEC_THREADS = 32 * (1 + DEC_CWARPS);
 
 constexpr int SEL_THREADS = 1024;
@@ -27,6 +29,7 @@ constexpr int SEL_MAX_K = 4096;  // largest nms_pre the select kernel sorts in s
 constexpr int NMS_THREADS = 1024;
 constexpr int NMS_KCAP = 2048;   // sorted-chunk buffer (keys)
 constexpr int NMS_CH = 1024;     // candidates staged (boxes) per chunk
+constexpr int NMS_G = 64;        // candidates resolved per round
 constexpr int NMS_MAX_KEEP = 4096;
 
 struct LevelDev {
@@ -69,7 +72,10 @@ struct DevParams {
     int* row_anchor;     // [B][R]
     float4* row_box;     // [B][R]
     uint32_t* mat;       // [B][R][C]   score bits of candidate (row, class), SCORE_NONE otherwise
-    uint32_t* img_max;   // [B]  f2ord(max coordinate over candidate boxes)
+    uint32_t* img_max;   // [B]  f2ord(max coordinate over candidate boxes)            (zeroed per call)
+    uint32_t* img_best;  // [B]  max over candidates of  ord(score)                      (zeroed per call)
+    uint32_t* img_worst; // [B]  max over candidates of ~ord(score)                      (zeroed per call)
+    int* img_cnt;        // [B]  number of candidates                                    (zeroed per call)
     const float* scale;  // [B][4] or null
     // outputs
     float* o_dets;
@@ -96,20 +102,35 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
     u64* ckey = P.ckey + (size_t)b * P.M_pad;
     uint32_t* rank = P.rank + (size_t)b * P.M_pad;
 
-    // pass 0: objectness of every anchor of the segment -> composite key; rank map cleared; key range
+    // pass 0: objectness of every anchor of the segment -> composite key; rank map cleared; key range.
+    // Loads are issued in batches of 8 per thread so that one DRAM round trip covers 8 anchors.
     u64 kmin = ~0ull, kmax = 0ull;
     for (int li = 0; li < sg.num_levels; ++li) {
         const LevelDev& lv = P.lv[sg.first_level + li];
+        const float* lbase = lv.ptr + (size_t)b * P.A * P.NA * lv.HW;
+        constexpr int U = 8;
         for (int a = 0; a < P.A; ++a) {
-            const float* plane = lv.ptr + ((size_t)(b * P.A + a) * P.NA + 4) * lv.HW;
-            for (int hw = tid; hw < lv.HW; hw += SEL_THREADS) {
-                float conf = c_sigmoid(__ldg(plane + hw));
-                int m = lv.m_off + a * lv.HW + hw;
-                u64 key = ((u64)(~f2ord(conf)) << 32) | (u64)(uint32_t)(lv.n_off + hw * P.A + a);
-                ckey[m] = key;
-                rank[m] = RANK_INVALID;
-                kmin = key < kmin ? key : kmin;
-                kmax = key > kmax ? key : kmax;
+            const float* plane = lbase + ((size_t)a * P.NA + 4) * lv.HW;
+            const int m0 = lv.m_off + a * lv.HW;
+            for (int h0 = 0; h0 < lv.HW; h0 += SEL_THREADS * U) {
+                float v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int hw = h0 + u * SEL_THREADS + tid;
+                    v[u] = hw < lv.HW ? __ldg(plane + hw) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int hw = h0 + u * SEL_THREADS + tid;
+                    if (hw < lv.HW) {
+                        const float conf = c_sigmoid(v[u]);
+                        const u64 key = ((u64)(~f2ord(conf)) << 32) | (u64)(uint32_t)(lv.n_off + hw * P.A + a);
+                        ckey[m0 + hw] = key;
+                        rank[m0 + hw] = RANK_INVALID;
+                        kmin = key < kmin ? key : kmin;
+                        kmax = key > kmax ? key : kmax;
+                    }
+                }
             }
         }
         // alignment padding between levels never matches a key
@@ -124,7 +145,8 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
         key = kp[i];
         return key != ~0ull;
     };
-    const int cnt = select_sorted_prefix(fetch, sg.m_end - sg.m_begin, gmin, gmax, sg.k, sel, P.sel_kcap, S);
+    const int cnt = select_sorted_prefix(fetch, sg.m_end - sg.m_begin, gmin, gmax, sg.k, sel, sel + P.sel_kcap,
+                                         P.sel_kcap, S);
     const int k = cnt < sg.k ? cnt : sg.k;
     const int first = sg.first_level, nl = sg.num_levels, A = P.A;
     for (int i = tid; i < k; i += SEL_THREADS) {
@@ -200,10 +222,86 @@ struct TmapPack {
     CUtensorMap m[MAXL];
 };
 
+// One admitted anchor, processed by a whole warp: lanes 0..4 activate the box / objectness logits (`attr_v` is
+// the raw logit of attribute `lane` there), then the lanes sweep the classes: `cls(u)` returns the raw logit of
+// class u*32 + lane (registers, shared-memory tile or a global gather). Writes row r of the score matrix, the
+// decoded box, and the per-image statistics.
+template <int MODE, class ClsLoad>
+__device__ __forceinline__ void process_anchor(const DevParams& P, const LevelDev& lv, const SegDev& sg, int b, int a,
+                                               int hw, uint32_t r, int lane, float attr_v, ClsLoad cls) {
+    uint32_t* mrow = P.mat + ((size_t)b * P.R + r) * P.C;
+    float act = 0.f;
+    if (lane < 5) act = (MODE == 0 || lane < 2 || lane == 4) ? c_sigmoid(attr_v) : c_expf(attr_v);
+    const float a0 = __shfl_sync(0xffffffffu, act, 0), a1 = __shfl_sync(0xffffffffu, act, 1);
+    const float a2 = __shfl_sync(0xffffffffu, act, 2), a3 = __shfl_sync(0xffffffffu, act, 3);
+    const float conf = __shfl_sync(0xffffffffu, act, 4);
+    if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) {  // yolo_head.py:365-376: row dropped
+        for (int c = lane; c < P.C; c += 32) mrow[c] = SCORE_NONE;
+        return;
+    }
+    const int y = hw / lv.W, x = hw - y * lv.W;
+    float4 bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
+    if (P.rescale) bx = rescale_box(bx, P.scale + 4 * b);
+    if (lane == 0) {
+        P.row_box[(size_t)b * P.R + r] = bx;
+        if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + r] = lv.n_off + hw * P.A + a;
+    }
+    uint32_t best = 0u, worst = 0u;  // max of ord(score) / ~ord(score) over this lane's candidates
+    int npass = 0;
+    if (P.agnostic) {
+        // cls_pred = conf_pred[:, None]  (yolocsp_head.py:360): one class, score = objectness
+        const bool pass = conf > P.score_thr;
+        if (lane == 0) {
+            mrow[0] = pass ? __float_as_uint(conf) : SCORE_NONE;
+            if (pass) {
+                best = f2ord(conf);
+                worst = ~best;
+                npass = 1;
+            }
+        }
+    } else {
+        for (int c0 = 0, u = 0; c0 < P.C; c0 += 32, ++u) {
+            const int c = c0 + lane;
+            if (c < P.C) {
+                const float sgm = c_sigmoid(cls(u));
+                float score;
+                bool pass;
+                if (MODE == 0) {
+                    score = fmul(sgm, conf);     // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
+                    pass = score > P.score_thr;  // bbox_nms.py:54
+                } else {
+                    pass = sgm > P.score_thr;  // threshold on the class score alone (bbox_nms.py:54) ...
+                    score = fmul(sgm, conf);   // ... then scores * score_factors     (bbox_nms.py:57-62)
+                }
+                mrow[c] = pass ? __float_as_uint(score) : SCORE_NONE;
+                if (pass) {
+                    const uint32_t o = f2ord(score);
+                    best = o > best ? o : best;
+                    worst = ~o > worst ? ~o : worst;
+                    ++npass;
+                }
+            }
+        }
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, npass > 0);
+    if (any) {
+        best = __reduce_max_sync(0xffffffffu, best);
+        worst = __reduce_max_sync(0xffffffffu, worst);
+        npass = __reduce_add_sync(0xffffffffu, npass);
+        if (lane == 0) {
+            atomicMax(&P.img_max[b], f2ord(box_max(bx)));  // boxes.max()  (mmcv batched_nms)
+            atomicMax(&P.img_best[b], best);
+            atomicMax(&P.img_worst[b], worst);
+            atomicAdd(&P.img_cnt[b], npass);
+        }
+    }
+}
+
 // Persistent, warp-specialised: warp 0 streams (NA x TILE_T) tiles of the raw head tensor into a 4-stage smem
-// ring with TMA (+ the tile's rank-map row with a 1-D bulk copy); each of the 4 consumer warps owns one stage
-// and processes whole tiles: admitted anchors one after the other, lanes over classes, scores written with
-// coalesced stores into the (row, class) matrix. No atomics with a return value anywhere.
+// ring with TMA (L2 evict-first: the tensor is read exactly once) plus the tile's rank-map row with a 1-D bulk
+// copy. 8 consumer warps take whole tiles round-robin: a consumer pulls the logits of the tile's admitted
+// anchors into registers, hands the stage straight back to the producer, and only then does the math
+// (lanes over classes), so a stage is held for a few hundred cycles, not for the whole decode of the tile.
 template <int MODE>
 __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_constant__ DevParams P,
                                                                   const __grid_constant__ TmapPack maps) {
@@ -212,16 +310,14 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
     const uint32_t tile_bytes = (uint32_t)NA * TILE_T * 4u;
     const uint32_t rank_bytes = TILE_T * 4u;
     const uint32_t stage_bytes = (tile_bytes + rank_bytes + 127u) & ~127u;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
-    uint64_t* empty = full + DEC_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [DEC_CWARPS]: tile for consumer warp w has landed
+    uint64_t* empty = full + DEC_CWARPS;                      // [DEC_STAGES]: stage s may be refilled
     unsigned char* stages = smem_raw + 128;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < DEC_STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
-        }
+        for (int w = 0; w < DEC_CWARPS; ++w) mbar_init(&full[w], 1);
+        for (int s = 0; s < DEC_STAGES; ++s) mbar_init(&empty[s], 1);
         fence_mbar_init();
     }
     __syncthreads();
@@ -230,6 +326,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
     if (warp == 0) {
         // ---------------- producer ----------------
         if (lane == 0) {
+            const uint64_t pol = l2_policy_evict_first();
             int it = 0;
             for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
                 const int s = it % DEC_STAGES;
@@ -245,20 +342,21 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
                 const int bb = plane / P.A, a = plane - bb * P.A;
                 unsigned char* dst = stages + (size_t)s * stage_bytes;
                 const bool topk = P.seg[lv.seg].has_topk != 0;
-                mbar_arrive_expect_tx(&full[s], tile_bytes + (topk ? rank_bytes : 0u));
-                tma_load_2d(dst, &maps.m[l], ht * TILE_T, plane * NA, &full[s]);
+                uint64_t* fb = &full[it % DEC_CWARPS];
+                mbar_arrive_expect_tx(fb, tile_bytes + (topk ? rank_bytes : 0u));
+                tma_load_2d_hint(dst, &maps.m[l], ht * TILE_T, plane * NA, fb, pol);
                 if (topk)
                     bulk_load_1d(dst + tile_bytes, P.rank + (size_t)bb * P.M_pad + lv.m_off + a * lv.HW + ht * TILE_T,
-                                 rank_bytes, &full[s]);
+                                 rank_bytes, fb);
             }
         }
         return;
     }
-    // ---------------- consumers: warp cw takes iterations it == cw (mod DEC_CWARPS), stage == cw ----------------
+    // ---------------- consumers: warp cw takes iterations it == cw (mod DEC_CWARPS) ----------------
     const int cw = warp - 1;
+    const bool in_regs = P.C <= 32 * DEC_ROUNDS;
     for (int it = cw, t = blockIdx.x + cw * gridDim.x; t < total; it += DEC_CWARPS, t += DEC_CWARPS * gridDim.x) {
         const int s = it % DEC_STAGES;
-        const uint32_t ph = (uint32_t)(it / DEC_STAGES) & 1u;
         int l = 0;
         for (int q = 0; q < P.L; ++q)
             if (P.lv[q].use_tma && t >= P.lv[q].tile0) l = q;
@@ -270,7 +368,10 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
         const int hw0 = ht * TILE_T;
         const SegDev& sg = P.seg[lv.seg];
 
-        mbar_wait(&full[s], ph);
+        // "full" barriers are per CONSUMER WARP, not per stage: two warps alternate on each stage, and a parity
+        // wait can only tell the current phase from the one before it — a barrier must therefore be waited on
+        // by the same agent in every phase.
+        mbar_wait(&full[cw], (uint32_t)(it / DEC_CWARPS) & 1u);
         const float* tile = reinterpret_cast<const float*>(stages + (size_t)s * stage_bytes);
         const uint32_t* rk = reinterpret_cast<const uint32_t*>(stages + (size_t)s * stage_bytes + tile_bytes);
 
@@ -284,74 +385,79 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
         }
         uint32_t m_lo = __ballot_sync(0xffffffffu, r_lo != RANK_INVALID);
         uint32_t m_hi = __ballot_sync(0xffffffffu, r_hi != RANK_INVALID);
+        bool released = false;
+        if (!(m_lo | m_hi)) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            released = true;
+        }
         while (m_lo | m_hi) {
-            int pos;
-            if (m_lo) {
-                pos = __ffs(m_lo) - 1;
-                m_lo &= m_lo - 1;
-            } else {
-                pos = 32 + __ffs(m_hi) - 1;
-                m_hi &= m_hi - 1;
-            }
-            const uint32_t r = __shfl_sync(0xffffffffu, pos < 32 ? r_lo : r_hi, pos & 31);
-            uint32_t* mrow = P.mat + ((size_t)b * P.R + r) * P.C;
-
-            // attributes 0..4: one lane each
-            float act = 0.f;
-            if (lane < 5) {
-                float v = tile[lane * TILE_T + pos];
-                act = (MODE == 0 || lane < 2 || lane == 4) ? c_sigmoid(v) : c_expf(v);
-            }
-            const float a0 = __shfl_sync(0xffffffffu, act, 0), a1 = __shfl_sync(0xffffffffu, act, 1);
-            const float a2 = __shfl_sync(0xffffffffu, act, 2), a3 = __shfl_sync(0xffffffffu, act, 3);
-            const float conf = __shfl_sync(0xffffffffu, act, 4);
-            if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) {  // yolo_head.py:365-376: row dropped
-                for (int c = lane; c < P.C; c += 32) mrow[c] = SCORE_NONE;
-                continue;
-            }
-            const int hw = hw0 + pos;
-            const int y = hw / lv.W, x = hw - y * lv.W;
-            float4 bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
-            if (P.rescale) bx = rescale_box(bx, P.scale + 4 * b);
-            if (lane == 0) {
-                P.row_box[(size_t)b * P.R + r] = bx;
-                if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + r] = lv.n_off + hw * P.A + a;
-            }
-            bool any = false;
-            if (P.agnostic) {
-                // cls_pred = conf_pred[:, None]  (yolocsp_head.py:360): one class, score = objectness
-                const bool pass = conf > P.score_thr;
-                if (lane == 0) mrow[0] = pass ? __float_as_uint(conf) : SCORE_NONE;
-                any = pass;
-            } else {
-                for (int c0 = 0; c0 < P.C; c0 += 32) {
-                    const int c = c0 + lane;
-                    bool pass = false;
-                    if (c < P.C) {
-                        const float sgm = c_sigmoid(tile[(5 + c) * TILE_T + pos]);
-                        float score;
-                        if (MODE == 0) {
-                            score = fmul(sgm, conf);     // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
-                            pass = score > P.score_thr;  // bbox_nms.py:54
-                        } else {
-                            pass = sgm > P.score_thr;  // threshold on the class score alone (bbox_nms.py:54) ...
-                            score = fmul(sgm, conf);   // ... then scores * score_factors     (bbox_nms.py:57-62)
-                        }
-                        mrow[c] = pass ? __float_as_uint(score) : SCORE_NONE;
+            // pull up to DEC_BATCH admitted anchors out of the tile
+            int pos[DEC_BATCH];
+            uint32_t rr[DEC_BATCH];
+            float av[DEC_BATCH];
+            float tv[DEC_BATCH][DEC_ROUNDS];
+            int nb = 0;
+#pragma unroll
+            for (int q = 0; q < DEC_BATCH; ++q) {
+                pos[q] = -1;
+                rr[q] = RANK_INVALID;
+                av[q] = 0.f;
+#pragma unroll
+                for (int u = 0; u < DEC_ROUNDS; ++u) tv[q][u] = 0.f;
+                if (m_lo | m_hi) {
+                    int ps;
+                    if (m_lo) {
+                        ps = __ffs(m_lo) - 1;
+                        m_lo &= m_lo - 1;
+                    } else {
+                        ps = 32 + __ffs(m_hi) - 1;
+                        m_hi &= m_hi - 1;
                     }
-                    any |= __any_sync(0xffffffffu, pass);
+                    pos[q] = ps;
+                    rr[q] = __shfl_sync(0xffffffffu, ps < 32 ? r_lo : r_hi, ps & 31);
+                    if (lane < 5) av[q] = tile[lane * TILE_T + ps];
+                    if (in_regs && !P.agnostic) {
+#pragma unroll
+                        for (int u = 0; u < DEC_ROUNDS; ++u) {
+                            const int c = u * 32 + lane;
+                            if (c < P.C) tv[q][u] = tile[(5 + c) * TILE_T + ps];
+                        }
+                    }
+                    nb = q + 1;
                 }
             }
-            if (any && lane == 0) atomicMax(&P.img_max[b], f2ord(box_max(bx)));  // boxes.max() (mmcv batched_nms)
+            // last batch and everything is in registers: give the stage back before the math
+            if (in_regs && !(m_lo | m_hi)) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                released = true;
+            }
+#pragma unroll
+            for (int q = 0; q < DEC_BATCH; ++q) {
+                if (q < nb) {
+                    const int ps = pos[q];
+                    if (in_regs) {
+                        process_anchor<MODE>(P, lv, sg, b, a, hw0 + ps, rr[q], lane, av[q],
+                                             [&](int u) -> float { return u == 0 ? tv[q][0] : (u == 1 ? tv[q][1] : tv[q][2]); });
+                    } else {
+                        process_anchor<MODE>(P, lv, sg, b, a, hw0 + ps, rr[q], lane, av[q],
+                                             [&](int u) -> float { return tile[(5 + u * 32 + lane) * TILE_T + ps]; });
+                    }
+                }
+            }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        if (!released) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
     }
 }
 
-// Generic path: one thread per position, coalesced scalar loads, loop over classes. Used for levels whose
-// plane stride is not 16-byte aligned (e.g. 19x19) and for dense admission (no top-k), where every anchor is
-// computed anyway.
+// Generic path for levels the TMA kernel cannot take (plane stride not 16-byte aligned, e.g. 19x19) and for
+// dense admission (no top-k: every anchor is computed anyway).
+//   SPARSE: a warp scans 32 positions, then gathers each admitted anchor's logits (lanes over classes).
+//   dense : one thread per position, coalesced loads, loop over classes.
 template <int MODE>
 __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__ DevParams P) {
     const int t = blockIdx.x;
@@ -364,16 +470,35 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
     const int ht = loc - plane * lv.tpp;
     const int b = plane / P.A, a = plane - b * P.A;
     const int hw = ht * 128 + threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const SegDev& sg = P.seg[lv.seg];
     const float* slab = lv.ptr + (size_t)plane * P.NA * lv.HW;
+    const size_t HW = (size_t)lv.HW;
 
-    if (hw >= lv.HW) return;
-    const uint32_t r = row_of(P, lv, b, a, hw);
+    uint32_t r = RANK_INVALID;
+    if (hw < lv.HW) r = row_of(P, lv, b, a, hw);
+
+    if (sg.has_topk) {
+        // sparse admission: warp-cooperative gather per admitted anchor
+        unsigned adm = __ballot_sync(0xffffffffu, r != RANK_INVALID);
+        const int hw_w = hw - lane;  // first position of this warp
+        while (adm) {
+            const int src = __ffs(adm) - 1;
+            adm &= adm - 1;
+            const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+            const int hwp = hw_w + src;
+            const float av = lane < 5 ? __ldg(slab + (size_t)lane * HW + hwp) : 0.f;
+            process_anchor<MODE>(P, lv, sg, b, a, hwp, rr, lane, av,
+                                 [&](int u) -> float { return __ldg(slab + (size_t)(5 + u * 32 + lane) * HW + hwp); });
+        }
+        return;
+    }
+    // dense admission
     if (r == RANK_INVALID) return;
     uint32_t* mrow = P.mat + ((size_t)b * P.R + r) * P.C;
-    const float t0 = __ldg(slab + 0 * (size_t)lv.HW + hw), t1 = __ldg(slab + 1 * (size_t)lv.HW + hw);
-    const float t2 = __ldg(slab + 2 * (size_t)lv.HW + hw), t3 = __ldg(slab + 3 * (size_t)lv.HW + hw);
-    const float conf = c_sigmoid(__ldg(slab + 4 * (size_t)lv.HW + hw));
+    const float t0 = __ldg(slab + 0 * HW + hw), t1 = __ldg(slab + 1 * HW + hw);
+    const float t2 = __ldg(slab + 2 * HW + hw), t3 = __ldg(slab + 3 * HW + hw);
+    const float conf = c_sigmoid(__ldg(slab + 4 * HW + hw));
     if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) {
         for (int c = 0; c < P.C; ++c) mrow[c] = SCORE_NONE;
         return;
@@ -385,16 +510,22 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
     float4 bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
     if (P.rescale) bx = rescale_box(bx, P.scale + 4 * b);
     P.row_box[(size_t)b * P.R + r] = bx;
-    if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + r] = lv.n_off + hw * P.A + a;
-    bool any = false;
+    P.row_anchor[(size_t)b * P.R + r] = lv.n_off + hw * P.A + a;
+    uint32_t best = 0u, worst = 0u;
+    int npass = 0;
     if (P.agnostic) {
-        any = conf > P.score_thr;
-        mrow[0] = any ? __float_as_uint(conf) : SCORE_NONE;
+        const bool pass = conf > P.score_thr;
+        mrow[0] = pass ? __float_as_uint(conf) : SCORE_NONE;
+        if (pass) {
+            best = f2ord(conf);
+            worst = ~best;
+            npass = 1;
+        }
     } else {
-        const float* cls = slab + 5 * (size_t)lv.HW + hw;
+        const float* cls = slab + 5 * HW + hw;
 #pragma unroll 8
         for (int c = 0; c < P.C; ++c) {
-            const float sgm = c_sigmoid(__ldg(cls + (size_t)c * lv.HW));
+            const float sgm = c_sigmoid(__ldg(cls + (size_t)c * HW));
             float score;
             bool pass;
             if (MODE == 0) {
@@ -405,10 +536,20 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
                 score = fmul(sgm, conf);
             }
             mrow[c] = pass ? __float_as_uint(score) : SCORE_NONE;
-            any |= pass;
+            if (pass) {
+                const uint32_t o = f2ord(score);
+                best = o > best ? o : best;
+                worst = ~o > worst ? ~o : worst;
+                ++npass;
+            }
         }
     }
-    if (any) atomicMax(&P.img_max[b], f2ord(box_max(bx)));
+    if (npass > 0) {
+        atomicMax(&P.img_max[b], f2ord(box_max(bx)));
+        atomicMax(&P.img_best[b], best);
+        atomicMax(&P.img_worst[b], worst);
+        atomicAdd(&P.img_cnt[b], npass);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -425,11 +566,12 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
 __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_constant__ DevParams P) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ TopSelSmem S;
-    __shared__ unsigned s_sup;
-    __shared__ int s_nk, s_cnt;
+    __shared__ u64 s_sup, s_masks[NMS_G];
+    __shared__ int s_nk;
     const int cap = P.keep_cap;
-    u64* keys = reinterpret_cast<u64*>(nms_smem);                 // [NMS_KCAP]
-    u64* kkey = keys + NMS_KCAP;                                   // [cap]
+    u64* keys = reinterpret_cast<u64*>(nms_smem);                 // [NMS_KCAP] sorted chunk
+    u64* ktmp = keys + NMS_KCAP;                                   // [NMS_KCAP] scratch of the select
+    u64* kkey = ktmp + NMS_KCAP;                                   // [cap]
     float* cx1 = reinterpret_cast<float*>(kkey + cap);             // [NMS_CH] x 5
     float* cy1 = cx1 + NMS_CH;
     float* cx2 = cy1 + NMS_CH;
@@ -444,41 +586,25 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
     int* kcl = reinterpret_cast<int*>(kar + cap);                  // [cap]
 
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int NW = NMS_THREADS / 32;
     const int C = P.C;
     const int slots = P.R * C;
     const uint32_t* mat = P.mat + (size_t)b * slots;
     const float4* row_box = P.row_box + (size_t)b * P.R;
 
-    // pass 0: count the candidates and find the key range
-    u64 kmin = ~0ull, kmax = 0ull;
-    int cntl = 0;
-    for (int i = tid; i < slots; i += NMS_THREADS) {
-        const uint32_t sb = mat[i];
-        if (sb != SCORE_NONE) {
-            const u64 key = make_key(__uint_as_float(sb), (uint32_t)i);
-            kmin = key < kmin ? key : kmin;
-            kmax = key > kmax ? key : kmax;
-            ++cntl;
-        }
-    }
+    // candidate count and score range of the image were accumulated by the decode kernels
     if (tid == 0) {
-        s_cnt = 0;
         s_nk = 0;
-        s_sup = 0u;
+        s_sup = 0ull;
     }
-    u64 gmin, gmax;
-    block_minmax(kmin, kmax, gmin, gmax, S);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) cntl += __shfl_xor_sync(0xffffffffu, cntl, o);
-    if (lane == 0 && cntl) atomicAdd(&s_cnt, cntl);
     __syncthreads();
-    const int ntot = s_cnt;
+    const int ntot = P.img_cnt[b];
     if (tid == 0 && P.o_ncand) P.o_ncand[b] = ntot;
     if (ntot == 0) {
         if (tid == 0) P.o_count[b] = 0;
         return;
     }
+    const u64 gmin = (u64)(~P.img_best[b]) << 32;
+    const u64 gmax = ((u64)P.img_worst[b] << 32) | 0xFFFFFFFFull;
     const bool per_class = !(ntot < P.split_thr);  // regime of mmcv batched_nms
     const bool use_off = !P.nms_agnostic;
     const float mp1 = fadd(ord2f(P.img_max[b]), 1.0f);  // max_coordinate + 1
@@ -492,9 +618,13 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
 
     int processed = 0;
     u64 lo = gmin;
+    // the first chunk only needs a little more than `cap` candidates; later chunks (heavy suppression) are full
+    int chunk = cap + (cap >> 2) + 64;
+    chunk = chunk < NMS_CH ? chunk : NMS_CH;
     while (processed < ntot && s_nk < cap) {
-        const int want = min(NMS_CH, ntot - processed);
-        int got = select_sorted_prefix(fetch, slots, lo, gmax, want, keys, NMS_KCAP, S);
+        const int want = min(chunk, ntot - processed);
+        chunk = NMS_CH;
+        const int got = select_sorted_prefix(fetch, slots, lo, gmax, want, keys, ktmp, NMS_KCAP, S);
         const int m = got < NMS_CH ? got : NMS_CH;  // boxes staged this round (a prefix of the sorted order)
         if (m == 0) break;
         for (int i = tid; i < m; i += NMS_THREADS) {
@@ -517,67 +647,105 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
             ccl[i] = c;
         }
         __syncthreads();
-        for (int s0 = 0; s0 < m; s0 += 32) {
+        for (int s0 = 0; s0 < m; s0 += NMS_G) {
             const int nk = s_nk;
             if (nk >= cap) break;
-            const int j = s0 + lane;
-            const bool valid = j < m;
-            Box bj;
-            bj.x1 = valid ? cx1[j] : 0.f;
-            bj.y1 = valid ? cy1[j] : 0.f;
-            bj.x2 = valid ? cx2[j] : 0.f;
-            bj.y2 = valid ? cy2[j] : 0.f;
-            bj.area = valid ? car[j] : 0.f;
-            const int cj = valid ? ccl[j] : -1;
-            // phase A: against the kept list, kept boxes strided over the warps
-            bool sup = false;
-            for (int k = warp; k < nk; k += NW) {
-                Box bk;
-                bk.x1 = kx1[k];
-                bk.y1 = ky1[k];
-                bk.x2 = kx2[k];
-                bk.y2 = ky2[k];
-                bk.area = kar[k];
-                const bool same = !per_class || (kcl[k] == cj);
-                if (valid && !sup && same && iou_gt(bk, bj, thr, foff)) sup = true;
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, sup);
-            if (lane == 0 && bal) atomicOr(&s_sup, bal);
-            __syncthreads();
-            // phase B: inside the 32-box group, sequential over i, parallel over j > i (warp 0)
-            if (warp == 0) {
-                bool alive = valid && !((s_sup >> lane) & 1u);
-                const int room = cap - nk;
-                int kept_here = 0;
-                for (int i = 0; i < 32; ++i) {
-                    const bool ai = __shfl_sync(0xffffffffu, alive, i) != 0;
-                    if (!ai) continue;
-                    if (++kept_here > room) break;  // later boxes cannot enter the first `cap` kept
-                    Box bi;
-                    bi.x1 = __shfl_sync(0xffffffffu, bj.x1, i);
-                    bi.y1 = __shfl_sync(0xffffffffu, bj.y1, i);
-                    bi.x2 = __shfl_sync(0xffffffffu, bj.x2, i);
-                    bi.y2 = __shfl_sync(0xffffffffu, bj.y2, i);
-                    bi.area = __shfl_sync(0xffffffffu, bj.area, i);
-                    const int ci = __shfl_sync(0xffffffffu, cj, i);
-                    const bool same = !per_class || (ci == cj);
-                    if (lane > i && alive && same && iou_gt(bi, bj, thr, foff)) alive = false;
+            // ---- phase A: the group's 64 candidates against the kept list (16 kept-subsets x 64 candidates)
+            {
+                const int j = s0 + (tid & (NMS_G - 1));
+                const bool valid = j < m;
+                Box bj;
+                bj.x1 = valid ? cx1[j] : 0.f;
+                bj.y1 = valid ? cy1[j] : 0.f;
+                bj.x2 = valid ? cx2[j] : 0.f;
+                bj.y2 = valid ? cy2[j] : 0.f;
+                bj.area = valid ? car[j] : 0.f;
+                const int cj = valid ? ccl[j] : -1;
+                bool sup = false;
+                for (int k = tid >> 6; k < nk; k += NMS_THREADS / NMS_G) {
+                    Box bk;
+                    bk.x1 = kx1[k];
+                    bk.y1 = ky1[k];
+                    bk.x2 = kx2[k];
+                    bk.y2 = ky2[k];
+                    bk.area = kar[k];
+                    const bool same = !per_class || (kcl[k] == cj);
+                    if (valid && !sup && same && iou_gt(bk, bj, thr, foff)) sup = true;
                 }
-                const unsigned km = __ballot_sync(0xffffffffu, alive);
-                const int rnk = __popc(km & ((1u << lane) - 1u));
-                if (alive && rnk < room) {
-                    const int kidx = nk + rnk;
-                    kx1[kidx] = bj.x1;
-                    ky1[kidx] = bj.y1;
-                    kx2[kidx] = bj.x2;
-                    ky2[kidx] = bj.y2;
-                    kar[kidx] = bj.area;
-                    kcl[kidx] = cj;
-                    kkey[kidx] = keys[j];
+                const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                if (lane == 0 && bal) atomicOr(&s_sup, (u64)bal << ((warp & 1) * 32));
+            }
+            // ---- phase B1: suppression rows inside the group, row i = bits j > i that box i would suppress
+            for (int i = warp; i < NMS_G; i += NMS_THREADS / 32) {
+                const int gi = s0 + i;
+                u64 row = 0ull;
+                if (gi < m) {
+                    Box bi;
+                    bi.x1 = cx1[gi];
+                    bi.y1 = cy1[gi];
+                    bi.x2 = cx2[gi];
+                    bi.y2 = cy2[gi];
+                    bi.area = car[gi];
+                    const int ci = ccl[gi];
+                    unsigned w2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int jj = h * 32 + lane, gj = s0 + jj;
+                        bool hit = false;
+                        if (jj > i && gj < m) {
+                            Box bj;
+                            bj.x1 = cx1[gj];
+                            bj.y1 = cy1[gj];
+                            bj.x2 = cx2[gj];
+                            bj.y2 = cy2[gj];
+                            bj.area = car[gj];
+                            const bool same = !per_class || (ccl[gj] == ci);
+                            hit = same && iou_gt(bi, bj, thr, foff);
+                        }
+                        w2[h] = __ballot_sync(0xffffffffu, hit);
+                    }
+                    row = ((u64)w2[1] << 32) | (u64)w2[0];
+                }
+                if (lane == 0) s_masks[i] = row;
+            }
+            __syncthreads();
+            // ---- phase B2: greedy scan over the group (warp 0): bit operations only
+            if (warp == 0) {
+                const int gcount = min(NMS_G, m - s0);
+                const u64 validm = gcount >= 64 ? ~0ull : ((1ull << gcount) - 1ull);
+                u64 alive = validm & ~s_sup;
+                const u64 ma = s_masks[lane], mb = s_masks[lane + 32];
+                const int room = cap - nk;
+                u64 keptm = 0ull, rem = alive;
+                int kept_here = 0;
+                while (rem) {
+                    const int i = __ffsll((long long)rem) - 1;
+                    if (++kept_here > room) break;  // later boxes cannot enter the first `cap` kept
+                    keptm |= 1ull << i;
+                    const u64 src = i < 32 ? ma : mb;
+                    const unsigned lo32 = __shfl_sync(0xffffffffu, (unsigned)src, i & 31);
+                    const unsigned hi32 = __shfl_sync(0xffffffffu, (unsigned)(src >> 32), i & 31);
+                    alive &= ~(((u64)hi32 << 32) | (u64)lo32);
+                    rem = (i >= 63) ? 0ull : (alive & ~((2ull << i) - 1ull));
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int jj = h * 32 + lane;
+                    if ((keptm >> jj) & 1ull) {
+                        const int kidx = nk + __popcll(keptm & ((1ull << jj) - 1ull));
+                        const int gj = s0 + jj;
+                        kx1[kidx] = cx1[gj];
+                        ky1[kidx] = cy1[gj];
+                        kx2[kidx] = cx2[gj];
+                        ky2[kidx] = cy2[gj];
+                        kar[kidx] = car[gj];
+                        kcl[kidx] = ccl[gj];
+                        kkey[kidx] = keys[gj];
+                    }
                 }
                 if (lane == 0) {
-                    s_nk = nk + min(__popc(km), room);
-                    s_sup = 0u;
+                    s_nk = nk + __popcll(keptm);
+                    s_sup = 0ull;
                 }
             }
             __syncthreads();
