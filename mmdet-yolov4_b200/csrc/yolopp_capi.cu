@@ -17,7 +17,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct Plan {
     DevParams d;
     size_t off_counters, counters_bytes;
-    size_t off_ckey, off_rank, off_row_anchor, off_row_box, off_mat;
+    size_t off_ckey, off_rank, off_row_anchor, off_row_box, off_row_stat, off_mat;
     size_t total;
     size_t dec_smem, sel_smem, nms_smem;
     int dec_ctas_per_sm;
@@ -75,6 +75,7 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
         lv.sx = (float)p->stride_w[l];
         lv.sy = (float)p->stride_h[l];
         lv.cstride = (float)p->coder_stride[l];
+        lv.inv_w = 1.0f / (float)lv.W;
         for (int a = 0; a < d.A; ++a)
             for (int k = 0; k < 4; ++k) lv.base[a][k] = p->base_anchors[l][a][k];
         n_off += hw * d.A;
@@ -132,10 +133,10 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     plan->nms_smem = (size_t)NMS_KCAP * 8 * 2 + (size_t)d.keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)d.keep_cap * 24;
 
     // which kernel decodes which level
-    const size_t stage_bytes = align_up((size_t)NA * TILE_T * 4 + TILE_T * 4, 128);
-    plan->dec_smem = 128 + DEC_STAGES * stage_bytes;
+    const StageGeom geom = stage_geom(NA);
+    plan->dec_smem = 1024 /*alignment slack*/ + 1024 /*barriers*/ + (size_t)DEC_STAGES * geom.stage_bytes;
     const bool tma_fits = plan->dec_smem <= 200 * 1024 && NA <= 256;
-    plan->dec_ctas_per_sm = plan->dec_smem <= 100 * 1024 ? 2 : 1;
+    plan->dec_ctas_per_sm = plan->dec_smem <= 110 * 1024 ? 2 : 1;
     int tma_tiles = 0, ldg_blocks = 0;
     for (int l = 0; l < d.L; ++l) {
         LevelDev& lv = d.lv[l];
@@ -162,9 +163,8 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     // workspace layout
     size_t off = 0;
     const size_t B = (size_t)d.B, Cc = (size_t)d.C, R = (size_t)d.R;
-    plan->off_counters = off;  // img_max[B] | img_best[B] | img_worst[B] | img_cnt[B]
-    plan->counters_bytes = align_up(4 * B * 4, 256);
-    off += plan->counters_bytes;
+    plan->off_counters = off;
+    plan->counters_bytes = 0;
     plan->off_ckey = off;
     off += align_up(B * d.M_pad * 8, 256);
     plan->off_rank = off;
@@ -172,6 +172,8 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     plan->off_row_anchor = off;
     off += align_up(B * R * 4, 256);
     plan->off_row_box = off;
+    off += align_up(B * R * 16, 256);
+    plan->off_row_stat = off;
     off += align_up(B * R * 16, 256);
     plan->off_mat = off;
     off += align_up(B * R * Cc * 4, 256);
@@ -182,14 +184,11 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
 void bind_workspace(Plan* plan, void* ws) {
     unsigned char* w = (unsigned char*)ws;
     DevParams& d = plan->d;
-    d.img_max = (uint32_t*)(w + plan->off_counters);
-    d.img_best = d.img_max + d.B;
-    d.img_worst = d.img_max + 2 * (size_t)d.B;
-    d.img_cnt = (int*)(d.img_max + 3 * (size_t)d.B);
     d.ckey = (u64*)(w + plan->off_ckey);
     d.rank = (uint32_t*)(w + plan->off_rank);
     d.row_anchor = (int*)(w + plan->off_row_anchor);
     d.row_box = (float4*)(w + plan->off_row_box);
+    d.row_stat = (uint4*)(w + plan->off_row_stat);
     d.mat = (uint32_t*)(w + plan->off_mat);
 }
 
@@ -286,8 +285,6 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
             if (e != cudaSuccess) return cuda_rc(e);                                        \
         }                                                                                   \
     } while (0)
-    e = cudaMemsetAsync((unsigned char*)workspace + plan.off_counters, 0, plan.counters_bytes, stream);
-    if (e != cudaSuccess) return cuda_rc(e);
     e = cudaMemsetAsync(out->status, 0, sizeof(int32_t), stream);
     if (e != cudaSuccess) return cuda_rc(e);
 
@@ -308,10 +305,10 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
             if (!d.lv[l].use_tma) continue;
             cuuint64_t gdim[2] = {(cuuint64_t)d.lv[l].HW, (cuuint64_t)d.B * d.A * d.NA};
             cuuint64_t gstr[1] = {(cuuint64_t)d.lv[l].HW * 4};
-            cuuint32_t box[2] = {(cuuint32_t)TILE_T, (cuuint32_t)d.NA};
+            cuuint32_t box[2] = {(cuuint32_t)TILE_SUB, (cuuint32_t)d.NA};
             cuuint32_t estr[2] = {1, 1};
             CUresult r = enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)d.lv[l].ptr, gdim, gstr, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return YOLOPP_E_CUDA + 999;
         }

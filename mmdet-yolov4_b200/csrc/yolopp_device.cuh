@@ -48,10 +48,11 @@ __device__ __forceinline__ float c_expf(float x) {
     return __fmul_rn(__fmul_rn(e, s1), s2);
 }
 
-// torch.sigmoid: 1 / (1 + exp(-x))
+// torch.sigmoid: 1 / (1 + exp(-x)). __frcp_rn is the correctly rounded reciprocal, i.e. bit-identical to the
+// IEEE division 1.0f / d, at about half the instructions.
 __device__ __forceinline__ float c_sigmoid(float x) {
     float e = c_expf(-x);
-    return __fdiv_rn(1.0f, __fadd_rn(1.0f, e));
+    return __frcp_rn(__fadd_rn(1.0f, e));
 }
 
 // ------------------------------------------------------------------------------------------------

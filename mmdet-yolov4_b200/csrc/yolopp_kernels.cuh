@@ -16,9 +16,11 @@ constexpr int MAXL = 8;
 constexpr int MAXA = 8;
 constexpr uint32_t RANK_INVALID = 0xFFFFFFFFu;
 
-constexpr int TILE_T = 60;       // positions per TMA tile: 240-byte rows (16-B multiple), row pitch = 4*odd banks
+constexpr int TILE_T = 64;       // positions per TMA tile = two 32-wide boxes with 128-byte rows (SWIZZLE_128B)
+constexpr int TILE_SUB = 32;     // positions per box
 constexpr int DEC_STAGES = 4;    // TMA pipeline depth
-constexpr int DEC_CWARPS = 8;    // consumer warps per CTA (+1 producer warp), one whole tile per warp
+constexpr int DEC_CWARPS = 12;   // consumer warps per CTA (+1 producer warp), one whole tile per warp
+constexpr int DEC_NFULL = 16;    // "tile landed" barriers, indexed by iteration mod DEC_NFULL (> DEC_CWARPS, see kernel)
 constexpr int DEC_BATCH = 4;     // admitted anchors whose logits a consumer pulls into registers at once
 constexpr int DEC_ROUNDS = 3;    // class sweeps held in registers (C <= 96); wider heads read the tile in place
 constexpr int DEC_THREADS = 32 * (1 + DEC_CWARPS);
@@ -43,6 +45,7 @@ struct LevelDev {
     int tpp;      // tiles per plane
     float sx, sy; // anchor-generator strides
     float cstride;// coder stride
+    float inv_w;  // 1 / W (position -> (x, y) without an integer division)
     float base[MAXA][4];
 };
 
@@ -72,10 +75,8 @@ struct DevParams {
     int* row_anchor;     // [B][R]
     float4* row_box;     // [B][R]
     uint32_t* mat;       // [B][R][C]   score bits of candidate (row, class), SCORE_NONE otherwise
-    uint32_t* img_max;   // [B]  f2ord(max coordinate over candidate boxes)            (zeroed per call)
-    uint32_t* img_best;  // [B]  max over candidates of  ord(score)                      (zeroed per call)
-    uint32_t* img_worst; // [B]  max over candidates of ~ord(score)                      (zeroed per call)
-    int* img_cnt;        // [B]  number of candidates                                    (zeroed per call)
+    uint4* row_stat;     // [B][R]  per row: (max ord(score), max ~ord(score), #candidates, 0) — plain stores, the
+                         //         per-image reduction happens in the NMS kernel (no same-address atomics)
     const float* scale;  // [B][4] or null
     // outputs
     float* o_dets;
@@ -222,6 +223,21 @@ struct TmapPack {
     CUtensorMap m[MAXL];
 };
 
+// (x, y) of position hw on a W-wide map: float estimate of hw / W, corrected to the exact quotient
+__device__ __forceinline__ void pos_xy(const LevelDev& lv, int hw, int& x, int& y) {
+    int q = __float2int_rz(__fmul_rn((float)hw, lv.inv_w));
+    int rem = hw - q * lv.W;
+    if (rem < 0) {
+        --q;
+        rem += lv.W;
+    } else if (rem >= lv.W) {
+        ++q;
+        rem -= lv.W;
+    }
+    x = rem;
+    y = q;
+}
+
 // One admitted anchor, processed by a whole warp: lanes 0..4 activate the box / objectness logits (`attr_v` is
 // the raw logit of attribute `lane` there), then the lanes sweep the classes: `cls(u)` returns the raw logit of
 // class u*32 + lane (registers, shared-memory tile or a global gather). Writes row r of the score matrix, the
@@ -237,9 +253,11 @@ __device__ __forceinline__ void process_anchor(const DevParams& P, const LevelDe
     const float conf = __shfl_sync(0xffffffffu, act, 4);
     if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) {  // yolo_head.py:365-376: row dropped
         for (int c = lane; c < P.C; c += 32) mrow[c] = SCORE_NONE;
+        if (lane == 0) P.row_stat[(size_t)b * P.R + r] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
-    const int y = hw / lv.W, x = hw - y * lv.W;
+    int x, y;
+    pos_xy(lv, hw, x, y);
     float4 bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
     if (P.rescale) bx = rescale_box(bx, P.scale + 4 * b);
     if (lane == 0) {
@@ -283,40 +301,144 @@ __device__ __forceinline__ void process_anchor(const DevParams& P, const LevelDe
             }
         }
     }
-    const unsigned any = __ballot_sync(0xffffffffu, npass > 0);
-    if (any) {
-        best = __reduce_max_sync(0xffffffffu, best);
-        worst = __reduce_max_sync(0xffffffffu, worst);
-        npass = __reduce_add_sync(0xffffffffu, npass);
-        if (lane == 0) {
-            atomicMax(&P.img_max[b], f2ord(box_max(bx)));  // boxes.max()  (mmcv batched_nms)
-            atomicMax(&P.img_best[b], best);
-            atomicMax(&P.img_worst[b], worst);
-            atomicAdd(&P.img_cnt[b], npass);
+    best = __reduce_max_sync(0xffffffffu, best);
+    worst = __reduce_max_sync(0xffffffffu, worst);
+    npass = __reduce_add_sync(0xffffffffu, npass);
+    if (lane == 0) P.row_stat[(size_t)b * P.R + r] = make_uint4(best, worst, (uint32_t)npass, 0u);
+}
+
+// Up to DEC_BATCH admitted anchors of one tile whose logits already sit in registers. Lane group g = lane / 8
+// owns anchor slot g for the box / objectness part (attribute k = lane % 8 < 5): ONE activation pass and ONE box
+// decode serve all four anchors; the class sweeps then run per anchor with all 32 lanes.
+//   av      this lane's raw logit of attribute k of anchor slot g
+//   tv[q][u] raw logit of class u*32 + lane of anchor slot q
+template <int MODE>
+__device__ __forceinline__ void process_batch(const DevParams& P, const LevelDev& lv, const SegDev& sg, int b, int a,
+                                              int hw0, int nb, const int (&pos)[DEC_BATCH],
+                                              const uint32_t (&rr)[DEC_BATCH], float av,
+                                              const float (&tv)[DEC_BATCH][DEC_ROUNDS], int lane) {
+    const int g = lane >> 3, k = lane & 7;
+    float act = 0.f;
+    if (k < 5 && g < nb) act = (MODE == 0 || k < 2 || k == 4) ? c_sigmoid(av) : c_expf(av);
+    const int gl = lane & ~7;
+    const float a0 = __shfl_sync(0xffffffffu, act, gl), a1 = __shfl_sync(0xffffffffu, act, gl + 1);
+    const float a2 = __shfl_sync(0xffffffffu, act, gl + 2), a3 = __shfl_sync(0xffffffffu, act, gl + 3);
+    const float conf_g = __shfl_sync(0xffffffffu, act, gl + 4);
+    const int pg = g == 0 ? pos[0] : (g == 1 ? pos[1] : (g == 2 ? pos[2] : pos[3]));
+    const uint32_t rg = g == 0 ? rr[0] : (g == 1 ? rr[1] : (g == 2 ? rr[2] : rr[3]));
+    const bool drop_g = (MODE == 1) && P.conf_thr > 0.f && !(conf_g >= P.conf_thr);  // yolo_head.py:365-376
+    if (g < nb && !drop_g && k == 0) {
+        const int hw = hw0 + pg;
+        int x, y;
+        pos_xy(lv, hw, x, y);
+        float4 bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
+        if (P.rescale) bx = rescale_box(bx, P.scale + 4 * b);
+        P.row_box[(size_t)b * P.R + rg] = bx;
+        if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + rg] = lv.n_off + hw * P.A + a;
+    }
+#pragma unroll
+    for (int q = 0; q < DEC_BATCH; ++q) {
+        if (q < nb) {
+            const float conf = __shfl_sync(0xffffffffu, conf_g, q * 8);
+            const bool drop = __shfl_sync(0xffffffffu, (int)drop_g, q * 8) != 0;
+            uint32_t* mrow = P.mat + ((size_t)b * P.R + rr[q]) * P.C;
+            uint32_t best = 0u, worst = 0u;
+            int npass = 0;
+            if (drop) {
+                for (int c = lane; c < P.C; c += 32) mrow[c] = SCORE_NONE;
+            } else if (P.agnostic) {
+                // cls_pred = conf_pred[:, None]  (yolocsp_head.py:360): one class, score = objectness
+                const bool pass = conf > P.score_thr;
+                if (lane == 0) {
+                    mrow[0] = pass ? __float_as_uint(conf) : SCORE_NONE;
+                    if (pass) {
+                        best = f2ord(conf);
+                        worst = ~best;
+                        npass = 1;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < DEC_ROUNDS; ++u) {
+                    const int c = u * 32 + lane;
+                    if (c < P.C) {
+                        const float sgm = c_sigmoid(tv[q][u]);
+                        float score;
+                        bool pass;
+                        if (MODE == 0) {
+                            score = fmul(sgm, conf);     // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
+                            pass = score > P.score_thr;  // bbox_nms.py:54
+                        } else {
+                            pass = sgm > P.score_thr;  // threshold on the class score alone (bbox_nms.py:54) ...
+                            score = fmul(sgm, conf);   // ... then scores * score_factors     (bbox_nms.py:57-62)
+                        }
+                        mrow[c] = pass ? __float_as_uint(score) : SCORE_NONE;
+                        if (pass) {
+                            const uint32_t o = f2ord(score);
+                            best = o > best ? o : best;
+                            worst = ~o > worst ? ~o : worst;
+                            ++npass;
+                        }
+                    }
+                }
+            }
+            best = __reduce_max_sync(0xffffffffu, best);
+            worst = __reduce_max_sync(0xffffffffu, worst);
+            npass = __reduce_add_sync(0xffffffffu, npass);
+            if (lane == 0) P.row_stat[(size_t)b * P.R + rr[q]] = make_uint4(best, worst, (uint32_t)npass, 0u);
         }
     }
 }
 
-// Persistent, warp-specialised: warp 0 streams (NA x TILE_T) tiles of the raw head tensor into a 4-stage smem
-// ring with TMA (L2 evict-first: the tensor is read exactly once) plus the tile's rank-map row with a 1-D bulk
-// copy. 8 consumer warps take whole tiles round-robin: a consumer pulls the logits of the tile's admitted
-// anchors into registers, hands the stage straight back to the producer, and only then does the math
-// (lanes over classes), so a stage is held for a few hundred cycles, not for the whole decode of the tile.
+// Shared-memory geometry of one pipeline stage (all offsets multiples of 1024 so that the 128-byte TMA swizzle
+// pattern is a function of the offset alone).
+struct StageGeom {
+    uint32_t sub_bytes;    // one (NA x 32) box, padded to 1024
+    uint32_t rank_off;     // 64-entry rank row
+    uint32_t desc_off;     // tile descriptor written by the producer
+    uint32_t stage_bytes;
+};
+__host__ __device__ inline StageGeom stage_geom(int NA) {
+    StageGeom g;
+    g.sub_bytes = ((uint32_t)NA * 128u + 1023u) & ~1023u;
+    g.rank_off = 2u * g.sub_bytes;
+    g.desc_off = g.rank_off + TILE_T * 4u;
+    g.stage_bytes = (g.desc_off + 16u + 1023u) & ~1023u;
+    return g;
+}
+// logit of attribute k at position p of the tile (SWIZZLE_128B: 16-byte chunk index XOR (row mod 8))
+__device__ __forceinline__ float tile_at(const unsigned char* stage, uint32_t sub_bytes, int k, int p) {
+    const int col = p & 31;
+    const uint32_t off = (uint32_t)(p >> 5) * sub_bytes + (uint32_t)k * 128u +
+                         ((uint32_t)(((col >> 2) ^ (k & 7)) << 4) | (uint32_t)((col & 3) << 2));
+    return *reinterpret_cast<const float*>(stage + off);
+}
+
+// Persistent, warp-specialised. Warp 0 is the producer: its 32 lanes work out the coordinates of the CTA's next
+// 32 tiles in parallel (the level lookup and the integer divisions are the long latency chain of a tile), then
+// lane 0 streams each (NA x 64) tile of the raw head tensor into a 4-stage shared-memory ring as two
+// 128B-swizzled TMA boxes (L2 evict-first: the tensor is read exactly once) plus the tile's rank-map row (1-D
+// bulk copy) and a 16-byte tile descriptor. 8 consumer warps take whole tiles round-robin: a consumer pulls the
+// logits of the tile's admitted anchors into registers, hands the stage straight back to the producer, and
+// only then does the math (lanes over classes), so a stage is held for a few hundred cycles.
 template <int MODE>
 __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_constant__ DevParams P,
                                                                   const __grid_constant__ TmapPack maps) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte aligned base (swizzle) — the launch reserves 1 KB of slack
+    unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int NA = P.NA;
-    const uint32_t tile_bytes = (uint32_t)NA * TILE_T * 4u;
-    const uint32_t rank_bytes = TILE_T * 4u;
-    const uint32_t stage_bytes = (tile_bytes + rank_bytes + 127u) & ~127u;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [DEC_CWARPS]: tile for consumer warp w has landed
-    uint64_t* empty = full + DEC_CWARPS;                      // [DEC_STAGES]: stage s may be refilled
-    unsigned char* stages = smem_raw + 128;
+    const StageGeom g = stage_geom(NA);
+    const uint32_t box_bytes = (uint32_t)NA * 128u;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [DEC_NFULL]: tile of iteration it (mod DEC_NFULL) has landed
+    uint64_t* empty = full + DEC_NFULL;                       // [DEC_STAGES]: stage s may be refilled
+    int* next_it = reinterpret_cast<int*>(empty + DEC_STAGES);  // next tile (iteration) a consumer may claim
+    unsigned char* stages = smem_raw + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int w = 0; w < DEC_CWARPS; ++w) mbar_init(&full[w], 1);
+        *next_it = 0;
+        for (int w = 0; w < DEC_NFULL; ++w) mbar_init(&full[w], 1);
         for (int s = 0; s < DEC_STAGES; ++s) mbar_init(&empty[s], 1);
         fence_mbar_init();
     }
@@ -325,55 +447,70 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
     const int total = P.tma_tiles;
     if (warp == 0) {
         // ---------------- producer ----------------
-        if (lane == 0) {
-            const uint64_t pol = l2_policy_evict_first();
-            int it = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-                const int s = it % DEC_STAGES;
-                const uint32_t ph = (uint32_t)(it / DEC_STAGES) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                int l = 0;
+        const uint64_t pol = l2_policy_evict_first();
+        for (int it0 = 0; blockIdx.x + (long long)it0 * gridDim.x < total; it0 += 32) {
+            // lane j: coordinates of iteration it0 + j
+            const long long tl = blockIdx.x + (long long)(it0 + lane) * gridDim.x;
+            int d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0;
+            if (tl < total) {
+                const int t = (int)tl;
                 for (int q = 0; q < P.L; ++q)
-                    if (P.lv[q].use_tma && t >= P.lv[q].tile0) l = q;
-                const LevelDev& lv = P.lv[l];
+                    if (P.lv[q].use_tma && t >= P.lv[q].tile0) d_l = q;
+                const LevelDev& lv = P.lv[d_l];
                 const int loc = t - lv.tile0;
-                const int plane = loc / lv.tpp;  // b*A + a
-                const int ht = loc - plane * lv.tpp;
-                const int bb = plane / P.A, a = plane - bb * P.A;
-                unsigned char* dst = stages + (size_t)s * stage_bytes;
-                const bool topk = P.seg[lv.seg].has_topk != 0;
-                uint64_t* fb = &full[it % DEC_CWARPS];
-                mbar_arrive_expect_tx(fb, tile_bytes + (topk ? rank_bytes : 0u));
-                tma_load_2d_hint(dst, &maps.m[l], ht * TILE_T, plane * NA, fb, pol);
-                if (topk)
-                    bulk_load_1d(dst + tile_bytes, P.rank + (size_t)bb * P.M_pad + lv.m_off + a * lv.HW + ht * TILE_T,
-                                 rank_bytes, fb);
+                d_plane = loc / lv.tpp;  // b*A + a
+                d_hw0 = (loc - d_plane * lv.tpp) * TILE_T;
+                d_b = d_plane / P.A;
+                d_a = d_plane - d_b * P.A;
+            }
+            for (int j = 0; j < 32; ++j) {
+                const int it = it0 + j;
+                if (blockIdx.x + (long long)it * gridDim.x >= total) break;
+                const int l = __shfl_sync(0xffffffffu, d_l, j), plane = __shfl_sync(0xffffffffu, d_plane, j);
+                const int hw0 = __shfl_sync(0xffffffffu, d_hw0, j), bb = __shfl_sync(0xffffffffu, d_b, j);
+                const int a = __shfl_sync(0xffffffffu, d_a, j);
+                if (lane == 0) {
+                    const int s = it % DEC_STAGES;
+                    const uint32_t ph = (uint32_t)(it / DEC_STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    const LevelDev& lv = P.lv[l];
+                    unsigned char* dst = stages + (size_t)s * g.stage_bytes;
+                    const bool topk = P.seg[lv.seg].has_topk != 0;
+                    const bool two = hw0 + TILE_SUB < lv.HW;  // the second box is not entirely out of bounds
+                    *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l, bb, a, hw0);
+                    uint64_t* fb = &full[it % DEC_NFULL];
+                    mbar_arrive_expect_tx(fb, box_bytes * (two ? 2u : 1u) + (topk ? TILE_T * 4u : 0u));
+                    tma_load_2d_hint(dst, &maps.m[l], hw0, plane * NA, fb, pol);
+                    if (two) tma_load_2d_hint(dst + g.sub_bytes, &maps.m[l], hw0 + TILE_SUB, plane * NA, fb, pol);
+                    if (topk)
+                        bulk_load_1d(dst + g.rank_off, P.rank + (size_t)bb * P.M_pad + lv.m_off + a * lv.HW + hw0,
+                                     TILE_T * 4u, fb);
+                }
             }
         }
         return;
     }
-    // ---------------- consumers: warp cw takes iterations it == cw (mod DEC_CWARPS) ----------------
-    const int cw = warp - 1;
+    // ---------------- consumers: whichever warp is free claims the CTA's next tile, in order ----------------
+    // Tiles carry 0..8 admitted anchors, so a static round-robin would let one heavy tile block its stage (and
+    // with it the in-order producer) while the other warps idle. A parity wait can only tell a barrier's current
+    // phase from the one before it, so a waiter must never be two phases ahead: claimed-but-unfinished
+    // iterations span at most [o, o + DEC_CWARPS] (o = oldest unfinished), hence "landed" barriers are indexed
+    // by iteration mod DEC_NFULL with DEC_NFULL > DEC_CWARPS — the previous user of a barrier is then finished.
+    static_assert(DEC_NFULL > DEC_CWARPS, "see comment");
     const bool in_regs = P.C <= 32 * DEC_ROUNDS;
-    for (int it = cw, t = blockIdx.x + cw * gridDim.x; t < total; it += DEC_CWARPS, t += DEC_CWARPS * gridDim.x) {
+    while (true) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(next_it, 1);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (blockIdx.x + (long long)it * gridDim.x >= total) break;
         const int s = it % DEC_STAGES;
-        int l = 0;
-        for (int q = 0; q < P.L; ++q)
-            if (P.lv[q].use_tma && t >= P.lv[q].tile0) l = q;
-        const LevelDev& lv = P.lv[l];
-        const int loc = t - lv.tile0;
-        const int plane = loc / lv.tpp;
-        const int ht = loc - plane * lv.tpp;
-        const int b = plane / P.A, a = plane - b * P.A;
-        const int hw0 = ht * TILE_T;
+        mbar_wait(&full[it % DEC_NFULL], (uint32_t)(it / DEC_NFULL) & 1u);
+        const unsigned char* stage = stages + (size_t)s * g.stage_bytes;
+        const int4 desc = *reinterpret_cast<const int4*>(stage + g.desc_off);
+        const LevelDev& lv = P.lv[desc.x];
+        const int b = desc.y, a = desc.z, hw0 = desc.w;
         const SegDev& sg = P.seg[lv.seg];
-
-        // "full" barriers are per CONSUMER WARP, not per stage: two warps alternate on each stage, and a parity
-        // wait can only tell the current phase from the one before it — a barrier must therefore be waited on
-        // by the same agent in every phase.
-        mbar_wait(&full[cw], (uint32_t)(it / DEC_CWARPS) & 1u);
-        const float* tile = reinterpret_cast<const float*>(stages + (size_t)s * stage_bytes);
-        const uint32_t* rk = reinterpret_cast<const uint32_t*>(stages + (size_t)s * stage_bytes + tile_bytes);
+        const uint32_t* rk = reinterpret_cast<const uint32_t*>(stage + g.rank_off);
 
         // admitted positions of the tile as a 64-bit mask
         uint32_t r_lo = RANK_INVALID, r_hi = RANK_INVALID;
@@ -381,7 +518,7 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
             const int p0 = lane, p1 = lane + 32;
             const int rbase = sg.row_off + (lv.n_off - P.lv[sg.first_level].n_off) + a;
             if (hw0 + p0 < lv.HW) r_lo = sg.has_topk ? rk[p0] : (uint32_t)(rbase + (hw0 + p0) * P.A);
-            if (p1 < TILE_T && hw0 + p1 < lv.HW) r_hi = sg.has_topk ? rk[p1] : (uint32_t)(rbase + (hw0 + p1) * P.A);
+            if (hw0 + p1 < lv.HW) r_hi = sg.has_topk ? rk[p1] : (uint32_t)(rbase + (hw0 + p1) * P.A);
         }
         uint32_t m_lo = __ballot_sync(0xffffffffu, r_lo != RANK_INVALID);
         uint32_t m_hi = __ballot_sync(0xffffffffu, r_hi != RANK_INVALID);
@@ -395,14 +532,12 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
             // pull up to DEC_BATCH admitted anchors out of the tile
             int pos[DEC_BATCH];
             uint32_t rr[DEC_BATCH];
-            float av[DEC_BATCH];
             float tv[DEC_BATCH][DEC_ROUNDS];
             int nb = 0;
 #pragma unroll
             for (int q = 0; q < DEC_BATCH; ++q) {
-                pos[q] = -1;
-                rr[q] = RANK_INVALID;
-                av[q] = 0.f;
+                pos[q] = 0;
+                rr[q] = 0u;
 #pragma unroll
                 for (int u = 0; u < DEC_ROUNDS; ++u) tv[q][u] = 0.f;
                 if (m_lo | m_hi) {
@@ -416,33 +551,38 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
                     }
                     pos[q] = ps;
                     rr[q] = __shfl_sync(0xffffffffu, ps < 32 ? r_lo : r_hi, ps & 31);
-                    if (lane < 5) av[q] = tile[lane * TILE_T + ps];
                     if (in_regs && !P.agnostic) {
 #pragma unroll
                         for (int u = 0; u < DEC_ROUNDS; ++u) {
                             const int c = u * 32 + lane;
-                            if (c < P.C) tv[q][u] = tile[(5 + c) * TILE_T + ps];
+                            if (c < P.C) tv[q][u] = tile_at(stage, g.sub_bytes, 5 + c, ps);
                         }
                     }
                     nb = q + 1;
                 }
             }
-            // last batch and everything is in registers: give the stage back before the math
-            if (in_regs && !(m_lo | m_hi)) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
-                released = true;
-            }
+            if (in_regs) {
+                // box / objectness logits: lane group (lane / 8) <-> anchor slot, lane % 8 <-> attribute
+                const int gq = lane >> 3, kq = lane & 7;
+                const int pg = gq == 0 ? pos[0] : (gq == 1 ? pos[1] : (gq == 2 ? pos[2] : pos[3]));
+                const float av = (kq < 5 && gq < nb) ? tile_at(stage, g.sub_bytes, kq, pg) : 0.f;
+                // last batch and everything is in registers: give the stage back before the math
+                if (!(m_lo | m_hi)) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                    released = true;
+                }
+                process_batch<MODE>(P, lv, sg, b, a, hw0, nb, pos, rr, av, tv, lane);
+            } else {
+                // wide heads (C > 96): classes are read from the tile in place, the stage is held meanwhile
 #pragma unroll
-            for (int q = 0; q < DEC_BATCH; ++q) {
-                if (q < nb) {
-                    const int ps = pos[q];
-                    if (in_regs) {
-                        process_anchor<MODE>(P, lv, sg, b, a, hw0 + ps, rr[q], lane, av[q],
-                                             [&](int u) -> float { return u == 0 ? tv[q][0] : (u == 1 ? tv[q][1] : tv[q][2]); });
-                    } else {
-                        process_anchor<MODE>(P, lv, sg, b, a, hw0 + ps, rr[q], lane, av[q],
-                                             [&](int u) -> float { return tile[(5 + u * 32 + lane) * TILE_T + ps]; });
+                for (int q = 0; q < DEC_BATCH; ++q) {
+                    if (q < nb) {
+                        const int ps = pos[q];
+                        const float av = lane < 5 ? tile_at(stage, g.sub_bytes, lane, ps) : 0.f;
+                        process_anchor<MODE>(P, lv, sg, b, a, hw0 + ps, rr[q], lane, av, [&](int u) -> float {
+                            return tile_at(stage, g.sub_bytes, 5 + u * 32 + lane, ps);
+                        });
                     }
                 }
             }
@@ -501,6 +641,7 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
     const float conf = c_sigmoid(__ldg(slab + 4 * HW + hw));
     if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) {
         for (int c = 0; c < P.C; ++c) mrow[c] = SCORE_NONE;
+        P.row_stat[(size_t)b * P.R + r] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     const float a0 = c_sigmoid(t0), a1 = c_sigmoid(t1);
@@ -544,12 +685,7 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
             }
         }
     }
-    if (npass > 0) {
-        atomicMax(&P.img_max[b], f2ord(box_max(bx)));
-        atomicMax(&P.img_best[b], best);
-        atomicMax(&P.img_worst[b], worst);
-        atomicAdd(&P.img_cnt[b], npass);
-    }
+    P.row_stat[(size_t)b * P.R + r] = make_uint4(best, worst, (uint32_t)npass, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -568,6 +704,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
     __shared__ TopSelSmem S;
     __shared__ u64 s_sup, s_masks[NMS_G];
     __shared__ int s_nk;
+    __shared__ uint32_t s_red[4];
     const int cap = P.keep_cap;
     u64* keys = reinterpret_cast<u64*>(nms_smem);                 // [NMS_KCAP] sorted chunk
     u64* ktmp = keys + NMS_KCAP;                                   // [NMS_KCAP] scratch of the select
@@ -591,23 +728,54 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
     const uint32_t* mat = P.mat + (size_t)b * slots;
     const float4* row_box = P.row_box + (size_t)b * P.R;
 
-    // candidate count and score range of the image were accumulated by the decode kernels
+    // candidate count, score range and boxes.max() of the image: reduction over the per-row statistics that the
+    // decode kernels stored
     if (tid == 0) {
         s_nk = 0;
         s_sup = 0ull;
+        s_red[0] = 0u;
+        s_red[1] = 0u;
+        s_red[2] = 0u;
+        s_red[3] = 0u;
     }
     __syncthreads();
-    const int ntot = P.img_cnt[b];
+    {
+        const uint4* rs = P.row_stat + (size_t)b * P.R;
+        uint32_t best = 0u, worst = 0u, mx = 0u, cnt = 0u;
+        for (int r = tid; r < P.R; r += NMS_THREADS) {
+            const uint4 st = rs[r];
+            if (st.z) {
+                best = st.x > best ? st.x : best;
+                worst = st.y > worst ? st.y : worst;
+                cnt += st.z;
+                const uint32_t o = f2ord(box_max(row_box[r]));  // boxes.max() runs over candidate boxes only
+                mx = o > mx ? o : mx;
+            }
+        }
+        best = __reduce_max_sync(0xffffffffu, best);
+        worst = __reduce_max_sync(0xffffffffu, worst);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (lane == 0 && cnt) {
+            atomicMax(&s_red[0], best);
+            atomicMax(&s_red[1], worst);
+            atomicMax(&s_red[2], mx);
+            atomicAdd(&s_red[3], cnt);
+        }
+    }
+    __syncthreads();
+    const int ntot = (int)s_red[3];
     if (tid == 0 && P.o_ncand) P.o_ncand[b] = ntot;
     if (ntot == 0) {
         if (tid == 0) P.o_count[b] = 0;
         return;
     }
-    const u64 gmin = (u64)(~P.img_best[b]) << 32;
-    const u64 gmax = ((u64)P.img_worst[b] << 32) | 0xFFFFFFFFull;
+    const u64 gmin = (u64)(~s_red[0]) << 32;
+    const u64 gmax = ((u64)s_red[1] << 32) | 0xFFFFFFFFull;
+    const uint32_t img_max_ord = s_red[2];
     const bool per_class = !(ntot < P.split_thr);  // regime of mmcv batched_nms
     const bool use_off = !P.nms_agnostic;
-    const float mp1 = fadd(ord2f(P.img_max[b]), 1.0f);  // max_coordinate + 1
+    const float mp1 = fadd(ord2f(img_max_ord), 1.0f);  // max_coordinate + 1
     const float thr = P.iou_thr, foff = P.foff;
 
     auto fetch = [=](int i, u64& key) -> bool {

@@ -17,7 +17,7 @@ for ln in dis.splitlines():
     if m: cur_fn = m.group(1); continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
     if m: cur_line = (os.path.basename(m.group(1)), int(m.group(2))); continue
-    if cur_fn and re.match(r'\s+/\*[0-9a-f]{4}\*/', ln):
+    if cur_fn and re.match(r'\s+/\*[0-9a-f]{4,}\*/', ln):
         lines_of[cur_fn].append(cur_line)
 fn = [f for f in lines_of if kname in f]
 assert fn, f'no function matching {kname}: {list(lines_of)[:20]}'
