@@ -24,8 +24,7 @@ __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b)
 
 // exp(x), <= 1.02 ulp, monotone; identical operation sequence on CPU (fmaf) and GPU (__fmaf_rn).
 __device__ __forceinline__ float c_expf(float x) {
-    if (!(x == x)) return x;
-    float xc = x < -104.0f ? -104.0f : x;
+    float xc = x < -104.0f ? -104.0f : x;  // (NaN compares false twice and is restored at the end: branch-free)
     xc = xc > 89.0f ? 89.0f : xc;
     float t = __fmaf_rn(xc, 1.44269502f, 12582912.0f);
     float j = __fsub_rn(t, 12582912.0f);
@@ -45,7 +44,8 @@ __device__ __forceinline__ float c_expf(float x) {
     int j2 = ji - j1;
     float s1 = __uint_as_float((uint32_t)(j1 + 127) << 23);
     float s2 = __uint_as_float((uint32_t)(j2 + 127) << 23);
-    return __fmul_rn(__fmul_rn(e, s1), s2);
+    float y = __fmul_rn(__fmul_rn(e, s1), s2);
+    return (x == x) ? y : x;
 }
 
 // torch.sigmoid: 1 / (1 + exp(-x)). __frcp_rn is the correctly rounded reciprocal, i.e. bit-identical to the

@@ -312,11 +312,15 @@ __device__ __forceinline__ void process_anchor(const DevParams& P, const LevelDe
 // decode serve all four anchors; the class sweeps then run per anchor with all 32 lanes.
 //   av      this lane's raw logit of attribute k of anchor slot g
 //   tv[q][u] raw logit of class u*32 + lane of anchor slot q
-template <int MODE>
+template <int MODE, int OFF>
 __device__ __forceinline__ void process_batch(const DevParams& P, const LevelDev& lv, const SegDev& sg, int b, int a,
-                                              int hw0, int nb, const int (&pos)[DEC_BATCH],
-                                              const uint32_t (&rr)[DEC_BATCH], float av,
-                                              const float (&tv)[DEC_BATCH][DEC_ROUNDS], int lane) {
+                                              int hw0, int nb_all, const int (&pos_all)[DEC_BATCH],
+                                              const uint32_t (&rr_all)[DEC_BATCH], float av,
+                                              const float (&tv_all)[DEC_BATCH][DEC_ROUNDS], int lane) {
+    // this pass serves anchor slots OFF .. OFF+3
+    const int nb = nb_all - OFF;
+    const int pos[4] = {pos_all[OFF], pos_all[OFF + 1], pos_all[OFF + 2], pos_all[OFF + 3]};
+    const uint32_t rr[4] = {rr_all[OFF], rr_all[OFF + 1], rr_all[OFF + 2], rr_all[OFF + 3]};
     const int g = lane >> 3, k = lane & 7;
     float act = 0.f;
     if (k < 5 && g < nb) act = (MODE == 0 || k < 2 || k == 4) ? c_sigmoid(av) : c_expf(av);
@@ -336,8 +340,17 @@ __device__ __forceinline__ void process_batch(const DevParams& P, const LevelDev
         P.row_box[(size_t)b * P.R + rg] = bx;
         if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + rg] = lv.n_off + hw * P.A + a;
     }
+    // class activations of all four slots in one straight-line block: 12 independent dependency chains keep the
+    // FMA pipe busy (a single sigmoid is ~35 dependent instructions). Empty slots compute on zeros.
+    float sgm[4][DEC_ROUNDS];
+    if (!P.agnostic) {
 #pragma unroll
-    for (int q = 0; q < DEC_BATCH; ++q) {
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int u = 0; u < DEC_ROUNDS; ++u) sgm[q][u] = c_sigmoid(tv_all[OFF + q][u]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
         if (q < nb) {
             const float conf = __shfl_sync(0xffffffffu, conf_g, q * 8);
             const bool drop = __shfl_sync(0xffffffffu, (int)drop_g, q * 8) != 0;
@@ -361,25 +374,22 @@ __device__ __forceinline__ void process_batch(const DevParams& P, const LevelDev
 #pragma unroll
                 for (int u = 0; u < DEC_ROUNDS; ++u) {
                     const int c = u * 32 + lane;
-                    if (c < P.C) {
-                        const float sgm = c_sigmoid(tv[q][u]);
-                        float score;
-                        bool pass;
-                        if (MODE == 0) {
-                            score = fmul(sgm, conf);     // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
-                            pass = score > P.score_thr;  // bbox_nms.py:54
-                        } else {
-                            pass = sgm > P.score_thr;  // threshold on the class score alone (bbox_nms.py:54) ...
-                            score = fmul(sgm, conf);   // ... then scores * score_factors     (bbox_nms.py:57-62)
-                        }
-                        mrow[c] = pass ? __float_as_uint(score) : SCORE_NONE;
-                        if (pass) {
-                            const uint32_t o = f2ord(score);
-                            best = o > best ? o : best;
-                            worst = ~o > worst ? ~o : worst;
-                            ++npass;
-                        }
+                    const float sv = sgm[q][u];
+                    float score;
+                    bool pass;
+                    if (MODE == 0) {
+                        score = fmul(sv, conf);      // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
+                        pass = score > P.score_thr;  // bbox_nms.py:54
+                    } else {
+                        pass = sv > P.score_thr;   // threshold on the class score alone (bbox_nms.py:54) ...
+                        score = fmul(sv, conf);    // ... then scores * score_factors     (bbox_nms.py:57-62)
                     }
+                    pass = pass && (c < P.C);
+                    if (c < P.C) mrow[c] = pass ? __float_as_uint(score) : SCORE_NONE;
+                    const uint32_t o = f2ord(score);
+                    best = (pass && o > best) ? o : best;
+                    worst = (pass && ~o > worst) ? ~o : worst;
+                    npass += pass ? 1 : 0;
                 }
             }
             best = __reduce_max_sync(0xffffffffu, best);
@@ -422,7 +432,7 @@ __device__ __forceinline__ float tile_at(const unsigned char* stage, uint32_t su
 // logits of the tile's admitted anchors into registers, hands the stage straight back to the producer, and
 // only then does the math (lanes over classes), so a stage is held for a few hundred cycles.
 template <int MODE>
-__global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_constant__ DevParams P,
+__global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid_constant__ DevParams P,
                                                                   const __grid_constant__ TmapPack maps) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned base (swizzle) — the launch reserves 1 KB of slack
@@ -564,15 +574,15 @@ __global__ void __launch_bounds__(DEC_THREADS) decode_tma_kernel(const __grid_co
             if (in_regs) {
                 // box / objectness logits: lane group (lane / 8) <-> anchor slot, lane % 8 <-> attribute
                 const int gq = lane >> 3, kq = lane & 7;
-                const int pg = gq == 0 ? pos[0] : (gq == 1 ? pos[1] : (gq == 2 ? pos[2] : pos[3]));
-                const float av = (kq < 5 && gq < nb) ? tile_at(stage, g.sub_bytes, kq, pg) : 0.f;
+                const int pg0 = gq == 0 ? pos[0] : (gq == 1 ? pos[1] : (gq == 2 ? pos[2] : pos[3]));
+                const float av0 = (kq < 5 && gq < nb) ? tile_at(stage, g.sub_bytes, kq, pg0) : 0.f;
                 // last batch and everything is in registers: give the stage back before the math
                 if (!(m_lo | m_hi)) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
                     released = true;
                 }
-                process_batch<MODE>(P, lv, sg, b, a, hw0, nb, pos, rr, av, tv, lane);
+                process_batch<MODE, 0>(P, lv, sg, b, a, hw0, nb, pos, rr, av0, tv, lane);
             } else {
                 // wide heads (C > 96): classes are read from the tile in place, the stage is held meanwhile
 #pragma unroll
