@@ -10,9 +10,10 @@ from .ops import get_bboxes_raw, coder_decode, sigmoid, exp
 from .heads import (YOLOCSPHead, YOLOV3Head, YOLOV4BBoxCoder, YOLOBBoxCoder, YOLOAnchorGenerator,
                     YOLOV4AnchorGenerator, patch_head)
 from . import synth
+from . import shard
 
 __all__ = [
     'MODE_CSP', 'MODE_V3', 'make_params', 'load_library', 'get_bboxes_raw', 'coder_decode', 'sigmoid', 'exp',
     'YOLOCSPHead', 'YOLOV3Head', 'YOLOV4BBoxCoder', 'YOLOBBoxCoder', 'YOLOAnchorGenerator', 'YOLOV4AnchorGenerator',
-    'patch_head', 'synth'
+    'patch_head', 'synth', 'shard'
 ]

@@ -85,6 +85,29 @@ def test_get_bboxes_matches_oracle(name):
     compare(p, res, orc, name)
 
 
+@pytest.mark.parametrize('name', cases.GOLDEN_CASES)
+def test_get_bboxes_matches_reference_golden(name):
+    """CUDA path == the committed golden vectors that the reference's OWN source produced
+    (tests/golden/make_golden.py, canonical transcendental): bit-exact boxes, scores, labels, anchors, order."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', f'{name}.npz'))
+    case = cases.CASES[name]
+    p, levels, res = run_cuda(case)
+    assert int(res['status'][0]) == 0
+    np.testing.assert_array_equal(res['count'], g['canon_count'])
+    np.testing.assert_array_equal(res['num_candidates'], g['canon_ncand'])
+    for b in range(p.batch):
+        n = int(g['canon_count'][b])
+        np.testing.assert_array_equal(_u32(res['dets'][b, :n]), g['canon_dets_bits'][b, :n])
+        np.testing.assert_array_equal(res['labels'][b, :n], g['canon_labels'][b, :n])
+        if bool(g['has_anchors']):
+            np.testing.assert_array_equal(res['anchors'][b, :n], g['canon_anchors'][b, :n])
+        # and within north_star's 1e-5 relative of the reference exactly as it runs (torch CPU sigmoid)
+        if n:
+            a, o = g['asis_dets'][b, :n].astype(np.float64), res['dets'][b, :n].astype(np.float64)
+            assert (np.abs(a - o) / np.maximum(np.abs(a), 1e-3)).max() <= 1e-5
+
+
 def test_coder_decode_matches_oracle():
     import yolopp
     rng = np.random.RandomState(1)
