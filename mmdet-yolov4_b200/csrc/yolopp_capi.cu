@@ -126,11 +126,15 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     int max_k = 0;
     for (int s = 0; s < d.nsegs; ++s)
         if (d.seg[s].has_topk && d.seg[s].k > max_k) max_k = d.seg[s].k;
-    int kcap = 2048;
+    int kcap = 4096;  // >= 2k: room for the survivors of the sampled pivot (~1.5k expected)
     while (kcap < 2 * max_k) kcap <<= 1;
     d.sel_kcap = kcap;
     plan->sel_smem = (size_t)kcap * 8 * 2;  // sorted keys + scatter scratch
-    plan->nms_smem = (size_t)NMS_KCAP * 8 * 2 + (size_t)d.keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)d.keep_cap * 24;
+    plan->nms_smem = (size_t)NMS_KCAP * 8 * 2 + (size_t)d.keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)d.keep_cap * 28 +
+                     (size_t)d.C * 4;
+    plan->nms_smem = align_up(plan->nms_smem, 16);
+    d.nms_rowkeys_off = (int)plan->nms_smem;
+    plan->nms_smem += (size_t)NMS_KCAP * 8;
 
     // which kernel decodes which level
     const StageGeom geom = stage_geom(NA);

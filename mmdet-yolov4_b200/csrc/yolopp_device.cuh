@@ -279,17 +279,27 @@ __device__ __forceinline__ void block_minmax(u64 vmin, u64 vmax, u64& omin, u64&
     __syncthreads();
 }
 
-// Writes into out[0..cnt) — SORTED ascending — a prefix of the ascending order of the eligible keys
-// (eligible: fetch(i,key) && lo_incl <= key <= hi_incl) that holds at least min(m, #eligible) keys; cnt <= cap.
+// Writes into out[0..cnt) — SORTED ascending — a prefix of the ascending order of the eligible keys (eligible:
+// delivered by the source and lo_incl <= key <= hi_incl) that holds at least min(m, #eligible) keys; cnt <= cap.
+//
+// A Source streams its keys in groups through ONE vector load per group and a cheap prefilter, so that the hot
+// loop is "load, subtract, compare" and 64-bit keys are only built for the (rare) survivors:
+//     typename Source::Raw            raw group (e.g. uint4 of four score words)
+//     Raw      load(int g)  const     vector load of group g
+//     unsigned mask(Raw, int g) const bit v set: element v of the group MAY be eligible (must not miss any)
+//     u64      key(Raw, int v, int g) const   64-bit key of element v
+//     int      groups()     const
 // Fast path (bucket sort): one histogram pass over the 11 bits below the common prefix of [lo_incl, hi_incl],
 // an exclusive scan, one scatter pass (keys land grouped by bucket), and a ranking step inside each bucket.
 // Falls back to the exact 8-bit radix select + bitonic sort when the pivot bucket does not fit in `cap`.
 // Requires unique keys, cap a power of two >= m, blockDim.x in {256, 512, 1024}; `tmp` is scratch of `cap`
 // keys; all threads call.
-template <class Fetch>
-__device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 hi_incl, int m, u64* out, u64* tmp,
-                                    int cap, TopSelSmem& S) {
+template <class Source>
+__device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl, u64 hi_incl, int m, u64* out, u64* tmp, int cap,
+                                    TopSelSmem& S) {
+    typedef typename Source::Raw Raw;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
+    const int n_groups = src.groups();
     const u64 x = lo_incl ^ hi_incl;
     int shift = 0;
     if (x) {
@@ -298,27 +308,92 @@ __device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 h
     }
     const u64 base = lo_incl >> shift;
     for (int i = tid; i < TS_BINS; i += nth) S.hist[i] = 0;
+    if (tid == 0) S.count = 0;
     __syncthreads();
-    constexpr int U = 8;  // independent loads in flight per thread
-    for (int b0 = 0; b0 < n_slots; b0 += nth * U) {
-        u64 key[U];
-        bool ok[U];
+    constexpr int U = 4;  // independent vector loads in flight per thread
+    // Pass 1 — the only trip to global memory in the common case: stream the source, keep the survivors of the
+    // prefilter + exact range test in `out` (the stash). Each thread first marks its own survivors (a short,
+    // atomics-free divergent loop), then ONE warp scan + ONE shared-memory atomic per warp and iteration
+    // hand out the stash slots.
+    static_assert(U * Source::V <= 32, "survivor bitmask");
+    for (int b0 = 0; b0 < n_groups; b0 += nth * U) {
+        Raw raw[U];
 #pragma unroll
         for (int q = 0; q < U; ++q) {
-            const int i = b0 + q * nth + tid;
-            key[q] = 0;
-            ok[q] = (i < n_slots) && fetch(i, key[q]);
+            const int gi = b0 + q * nth + tid;
+            if (gi < n_groups) raw[q] = src.load(gi);
         }
+        unsigned emask = 0u;  // bit q*V+v: element v of group q is eligible
 #pragma unroll
-        for (int q = 0; q < U; ++q)
-            if (ok[q] && key[q] >= lo_incl && key[q] <= hi_incl) atomicAdd(&S.hist[(int)((key[q] >> shift) - base)], 1);
+        for (int q = 0; q < U; ++q) {
+            const int gi = b0 + q * nth + tid;
+            unsigned mk = gi < n_groups ? src.mask(raw[q], gi) : 0u;
+            while (mk) {
+                const int v = __ffs(mk) - 1;
+                mk &= mk - 1;
+                const u64 k = src.key(raw[q], v, gi);
+                if (k >= lo_incl && k <= hi_incl) emask |= 1u << (q * Source::V + v);
+            }
+        }
+        const int c = __popc(emask);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        const int wtot = __shfl_sync(0xffffffffu, incl, 31);
+        if (wtot) {
+            int sp = 0;
+            if (lane == 31) sp = atomicAdd(&S.count, wtot);
+            sp = __shfl_sync(0xffffffffu, sp, 31) + incl - c;
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                unsigned mq = (emask >> (q * Source::V)) & ((1u << Source::V) - 1u);
+                const int gi = b0 + q * nth + tid;
+                while (mq) {
+                    const int v = __ffs(mq) - 1;
+                    mq &= mq - 1;
+                    if (sp < cap) out[sp] = src.key(raw[q], v, gi);
+                    ++sp;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int n_stash = S.count;
+    const bool stash_ok = n_stash <= cap;
+    if (stash_ok) {
+        for (int i = tid; i < n_stash; i += nth) atomicAdd(&S.hist[(int)((out[i] >> shift) - base)], 1);
+    } else {
+        // too many eligible keys for the stash (no tight bound was available): histogram straight from the source
+        for (int b0 = 0; b0 < n_groups; b0 += nth * U) {
+            Raw raw[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int gi = b0 + q * nth + tid;
+                if (gi < n_groups) raw[q] = src.load(gi);
+            }
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int gi = b0 + q * nth + tid;
+                unsigned mk = gi < n_groups ? src.mask(raw[q], gi) : 0u;
+                while (mk) {
+                    const int v = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    const u64 k = src.key(raw[q], v, gi);
+                    if (k >= lo_incl && k <= hi_incl) atomicAdd(&S.hist[(int)((k >> shift) - base)], 1);
+                }
+            }
+        }
     }
     __syncthreads();
     // exclusive scan of the histogram (in place) + pivot bucket: per-thread partial sums -> warp scan -> block scan
     const int per = TS_BINS / nth;  // 2, 4 or 8
     int loc[8], s = 0;
-    for (int q = 0; q < per; ++q) {
-        loc[q] = S.hist[tid * per + q];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        loc[q] = q < per ? S.hist[tid * per + q] : 0;
         s += loc[q];
     }
     int incl = s;
@@ -341,14 +416,17 @@ __device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 h
     const int excl = woff + incl - s;
     {
         int cum = excl;
-        for (int q = 0; q < per; ++q) {
-            S.hist[tid * per + q] = cum;  // exclusive offset of the bucket
-            if (cum < m && m <= cum + loc[q]) {
-                S.kb = tid * per + q;
-                S.above = cum;
-                S.bsize = loc[q];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (q < per) {
+                S.hist[tid * per + q] = cum;  // exclusive offset of the bucket
+                if (cum < m && m <= cum + loc[q]) {
+                    S.kb = tid * per + q;
+                    S.above = cum;
+                    S.bsize = loc[q];
+                }
+                cum += loc[q];
             }
-            cum += loc[q];
         }
     }
     __syncthreads();
@@ -356,28 +434,40 @@ __device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 h
     int cnt;
     if (above + bsize <= cap) {
         // scatter: hist[bucket] is the running cursor of the bucket, keys land grouped by bucket in tmp
-        for (int b0 = 0; b0 < n_slots; b0 += nth * U) {
-            u64 key[U];
-            bool ok[U];
-#pragma unroll
-            for (int q = 0; q < U; ++q) {
-                const int i = b0 + q * nth + tid;
-                key[q] = 0;
-                ok[q] = (i < n_slots) && fetch(i, key[q]);
+        if (stash_ok) {
+            // every survivor of the first pass sits in `out`: no second trip to global memory
+            for (int i = tid; i < n_stash; i += nth) {
+                const u64 k = out[i];
+                const int bk = (int)((k >> shift) - base);
+                if (bk <= kb) tmp[atomicAdd(&S.hist[bk], 1)] = k;
             }
+            __syncthreads();  // `out` is rewritten by the ranking step below
+        } else {
+            for (int b0 = 0; b0 < n_groups; b0 += nth * U) {
+                Raw raw[U];
 #pragma unroll
-            for (int q = 0; q < U; ++q) {
-                if (ok[q] && key[q] >= lo_incl && key[q] <= hi_incl) {
-                    const int bk = (int)((key[q] >> shift) - base);
-                    if (bk <= kb) {
-                        const int pos = atomicAdd(&S.hist[bk], 1);
-                        tmp[pos] = key[q];
+                for (int q = 0; q < U; ++q) {
+                    const int gi = b0 + q * nth + tid;
+                    if (gi < n_groups) raw[q] = src.load(gi);
+                }
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    const int gi = b0 + q * nth + tid;
+                    unsigned mk = gi < n_groups ? src.mask(raw[q], gi) : 0u;
+                    while (mk) {
+                        const int v = __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        const u64 k = src.key(raw[q], v, gi);
+                        if (k >= lo_incl && k <= hi_incl) {
+                            const int bk = (int)((k >> shift) - base);
+                            if (bk <= kb) tmp[atomicAdd(&S.hist[bk], 1)] = k;
+                        }
                     }
                 }
             }
         }
         __syncthreads();
-        cnt = above + bsize;
+            cnt = above + bsize;
         // rank inside the bucket: after the scatter hist[bk] is the END of bucket bk, hist[bk-1] its start
         for (int pos = tid; pos < cnt; pos += nth) {
             const u64 key = tmp[pos];
@@ -388,11 +478,18 @@ __device__ int select_sorted_prefix(Fetch fetch, int n_slots, u64 lo_incl, u64 h
             out[rnk] = key;
         }
         __syncthreads();
-    } else {
+        } else {
+        // slow, exact path: element-wise view of the source
         const bool has_lo = lo_incl > 0;
-        auto f2 = [&](int i, u64& key) -> bool { return fetch(i, key) && key <= hi_incl; };
-        u64 T = radix_select(f2, n_slots, has_lo, lo_incl - 1, m, S.rs);
-        cnt = gather_le(f2, n_slots, has_lo, lo_incl - 1, T, out, cap, S.rs);
+        auto f1 = [&](int i, u64& key) -> bool {
+            const int gi = i / Source::V, v = i % Source::V;
+            const Raw r = src.load(gi);
+            if (!((src.mask(r, gi) >> v) & 1u)) return false;
+            key = src.key(r, v, gi);
+            return key <= hi_incl;
+        };
+        u64 T = radix_select(f1, n_groups * Source::V, has_lo, lo_incl - 1, m, S.rs);
+        cnt = gather_le(f1, n_groups * Source::V, has_lo, lo_incl - 1, T, out, cap, S.rs);
         const int p2 = next_pow2(cnt);
         for (int i = cnt + tid; i < p2; i += nth) out[i] = ~0ull;
         __syncthreads();

@@ -28,7 +28,7 @@ constexpr int DEC_THREADS = 32 * (1 + DEC_CWARPS);
 constexpr int SEL_THREADS = 1024;
 constexpr int SEL_MAX_K = 4096;  // largest nms_pre the select kernel sorts in shared memory
 
-constexpr int NMS_THREADS = 1024;
+constexpr int NMS_THREADS = 512;
 constexpr int NMS_KCAP = 2048;   // sorted-chunk buffer (keys)
 constexpr int NMS_CH = 1024;     // candidates staged (boxes) per chunk
 constexpr int NMS_G = 64;        // candidates resolved per round
@@ -66,6 +66,7 @@ struct DevParams {
     float score_thr, conf_thr, iou_thr, foff;
     int split_thr, nms_agnostic, m_eff, keep_cap, out_cap, rescale;
     int sel_kcap;  // key buffer (power of two) of the select kernel
+    int nms_rowkeys_off;  // byte offset of the sorted row-best keys inside the NMS kernel's dynamic smem
     int tma_tiles, ldg_blocks;
     LevelDev lv[MAXL];
     SegDev seg[MAXL];
@@ -88,12 +89,125 @@ struct DevParams {
     int* o_status;
 };
 
+// ---- key sources of the bucket select (see select_sorted_prefix) --------------------------------------------
+// objectness keys of a top-k segment, two per 16-byte load; keys above `hi` (incl. the ~0 padding) are masked
+struct CkeySource {
+    typedef ulonglong2 Raw;
+    static constexpr int V = 2;
+    const ulonglong2* p;
+    int n;
+    u64 hi;
+    __device__ __forceinline__ Raw load(int g) const { return p[g]; }
+    __device__ __forceinline__ unsigned mask(const Raw& r, int) const { return (r.x <= hi ? 1u : 0u) | (r.y <= hi ? 2u : 0u); }
+    __device__ __forceinline__ u64 key(const Raw& r, int v, int) const { return v ? r.y : r.x; }
+    __device__ __forceinline__ int groups() const { return n; }
+};
+// every `stride`-th objectness key (pivot sample)
+struct CkeySampleSource {
+    typedef u64 Raw;
+    static constexpr int V = 1;
+    const u64* p;
+    int n, stride;
+    __device__ __forceinline__ Raw load(int g) const { return p[(size_t)g * stride]; }
+    __device__ __forceinline__ unsigned mask(const Raw& r, int) const { return r != ~0ull ? 1u : 0u; }
+    __device__ __forceinline__ u64 key(const Raw& r, int, int) const { return r; }
+    __device__ __forceinline__ int groups() const { return n; }
+};
+// score matrix of one image, four entries per 16-byte load. Scores are non-negative floats, so their bit
+// patterns order like the values: the window [lo, lo+span] on the raw word rejects almost every entry with one
+// subtract + compare (SCORE_NONE = 0xFFFFFFFF is above every window).
+struct MatSource {
+    typedef uint4 Raw;
+    static constexpr int V = 4;
+    const uint32_t* m;
+    int slots;
+    bool vec4;
+    uint32_t lo, span;
+    __device__ __forceinline__ Raw load(int g) const {
+        if (vec4) return reinterpret_cast<const uint4*>(m)[g];
+        uint4 r;
+        r.x = (g * 4 + 0 < slots) ? m[g * 4 + 0] : SCORE_NONE;
+        r.y = (g * 4 + 1 < slots) ? m[g * 4 + 1] : SCORE_NONE;
+        r.z = (g * 4 + 2 < slots) ? m[g * 4 + 2] : SCORE_NONE;
+        r.w = (g * 4 + 3 < slots) ? m[g * 4 + 3] : SCORE_NONE;
+        return r;
+    }
+    __device__ __forceinline__ unsigned mask(const Raw& r, int) const {
+        return (r.x - lo <= span ? 1u : 0u) | (r.y - lo <= span ? 2u : 0u) | (r.z - lo <= span ? 4u : 0u) |
+               (r.w - lo <= span ? 8u : 0u);
+    }
+    __device__ __forceinline__ u64 key(const Raw& r, int v, int g) const {
+        const uint32_t sb = v == 0 ? r.x : (v == 1 ? r.y : (v == 2 ? r.z : r.w));
+        return make_key(__uint_as_float(sb), (uint32_t)(g * 4 + v));
+    }
+    __device__ __forceinline__ int groups() const { return (slots + 3) / 4; }
+};
+// score-matrix entries of a LIST of rows (the rows whose best score can still matter), four per 16-byte load.
+// The flat index of the group's first entry travels with the raw words, so building a survivor's key costs a
+// handful of instructions (no division on the divergent path).
+struct RowListRaw {
+    uint4 v;
+    uint32_t flat0;
+};
+struct RowListSource {
+    typedef RowListRaw Raw;
+    static constexpr int V = 4;
+    const uint32_t* m;   // score matrix of the image
+    const u64* rows;     // low word = row index
+    int nrows, C;
+    int nsub;            // 32-group (= 128-class) slabs per row: group g -> slab g >> 5, chunk g & 31
+    bool vec4;           // C % 4 == 0: rows are 16-byte aligned
+    uint32_t lo, span;
+    // a warp's 32 consecutive groups are the 32 chunks of ONE slab of one row: no division on the load path
+    __device__ __forceinline__ Raw load(int g) const {
+        const int slab = g >> 5, jl = g & 31;
+        const int i = nsub == 1 ? slab : slab / nsub;
+        const int j = nsub == 1 ? jl : (slab - i * nsub) * 32 + jl;
+        Raw r;
+        r.flat0 = (uint32_t)rows[i] * (uint32_t)C + (uint32_t)(4 * j);
+        r.v = make_uint4(SCORE_NONE, SCORE_NONE, SCORE_NONE, SCORE_NONE);
+        if (4 * j < C) {
+            const uint32_t* p = m + r.flat0;
+            if (vec4) {
+                r.v = *reinterpret_cast<const uint4*>(p);
+            } else {
+                r.v.x = p[0];
+                r.v.y = (4 * j + 1 < C) ? p[1] : SCORE_NONE;
+                r.v.z = (4 * j + 2 < C) ? p[2] : SCORE_NONE;
+                r.v.w = (4 * j + 3 < C) ? p[3] : SCORE_NONE;
+            }
+        }
+        return r;
+    }
+    __device__ __forceinline__ unsigned mask(const Raw& r, int) const {
+        return (r.v.x - lo <= span ? 1u : 0u) | (r.v.y - lo <= span ? 2u : 0u) | (r.v.z - lo <= span ? 4u : 0u) |
+               (r.v.w - lo <= span ? 8u : 0u);
+    }
+    __device__ __forceinline__ u64 key(const Raw& r, int v, int) const {
+        const uint32_t sb = v == 0 ? r.v.x : (v == 1 ? r.v.y : (v == 2 ? r.v.z : r.v.w));
+        // scores are non-negative: ~ord(score) == ~bits & 0x7FFFFFFF
+        return ((u64)((~sb) & 0x7FFFFFFFu) << 32) | (u64)(r.flat0 + (uint32_t)v);
+    }
+    __device__ __forceinline__ int groups() const { return nrows * nsub * 32; }
+};
+// best score of every row that owns a candidate (row_stat.x), key = (~ord(best) << 32) | row
+struct RowBestSource {
+    typedef uint4 Raw;
+    static constexpr int V = 1;
+    const uint4* rs;
+    int R;
+    __device__ __forceinline__ Raw load(int g) const { return rs[g]; }
+    __device__ __forceinline__ unsigned mask(const Raw& r, int) const { return r.z ? 1u : 0u; }
+    __device__ __forceinline__ u64 key(const Raw& r, int, int g) const { return ((u64)(~r.x) << 32) | (u64)(uint32_t)g; }
+    __device__ __forceinline__ int groups() const { return R; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // K0: objectness top-k
 // ------------------------------------------------------------------------------------------------
 // One CTA per (top-k segment, image). Keys are (~ord(conf) << 32 | n): ascending = (conf desc, anchor asc) —
 // the canonical order of conf_pred.topk(nms_pre) (yolocsp_head.py:350-355 / yolo_head.py:281-302).
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_constant__ DevParams P) {
+__global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_constant__ DevParams P) {
     extern __shared__ __align__(16) unsigned char sel_smem[];
     __shared__ TopSelSmem S;
     u64* sel = reinterpret_cast<u64*>(sel_smem);
@@ -141,13 +255,32 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const __grid_consta
     u64 gmin, gmax;
     block_minmax(kmin, kmax, gmin, gmax, S);  // also orders the global writes above (block barrier)
 
-    const u64* kp = ckey + sg.m_begin;
-    auto fetch = [=](int i, u64& key) -> bool {
-        key = kp[i];
-        return key != ~0ull;
-    };
-    const int cnt = select_sorted_prefix(fetch, sg.m_end - sg.m_begin, gmin, gmax, sg.k, sel, sel + P.sel_kcap,
-                                         P.sel_kcap, S);
+    // keys are fetched two at a time (16-byte loads); m_begin is 4-aligned, an odd tail reads one padding key (~0)
+    CkeySource src;
+    src.p = reinterpret_cast<const ulonglong2*>(ckey + sg.m_begin);
+    src.n = (sg.m_end - sg.m_begin + 1) / 2;
+    src.hi = gmax;
+    // Pivot from a 1-in-16 sample: the objectness distribution is extremely skewed (most anchors share a few
+    // histogram buckets), so the exact select only looks at keys up to ~1.5x the expected k-th key. If the
+    // sample pivot turns out too tight (cnt < k) the select is redone over the whole range.
+    {
+        CkeySampleSource ss;
+        ss.p = ckey + sg.m_begin;
+        ss.stride = 16;
+        ss.n = (sg.m_end - sg.m_begin) / 16;
+        const int ks = (sg.k * 3 + 31) / 32 + 16;  // 1.5 * k / 16 + slack
+        if (ss.n >= 4 * ks && ks <= P.sel_kcap) {
+            const int gs = select_sorted_prefix(ss, gmin, gmax, ks, sel, sel + P.sel_kcap, P.sel_kcap, S);
+            if (gs >= ks) src.hi = sel[ks - 1];
+            __syncthreads();
+        }
+    }
+    int cnt = select_sorted_prefix(src, gmin, src.hi, sg.k, sel, sel + P.sel_kcap, P.sel_kcap, S);
+    if (cnt < sg.k && src.hi != gmax) {
+        __syncthreads();
+        src.hi = gmax;
+        cnt = select_sorted_prefix(src, gmin, gmax, sg.k, sel, sel + P.sel_kcap, P.sel_kcap, S);
+    }
     const int k = cnt < sg.k ? cnt : sg.k;
     const int first = sg.first_level, nl = sg.num_levels, A = P.A;
     for (int i = tid; i < k; i += SEL_THREADS) {
@@ -709,7 +842,7 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
 //                   still on the offset boxes.
 // In both regimes the result order is (score desc, flat index asc) and only the first max_num are returned,
 // so candidates are visited in that global order and the pass stops once `cap` boxes are kept.
-__global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_constant__ DevParams P) {
+__global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_constant__ DevParams P) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ TopSelSmem S;
     __shared__ u64 s_sup, s_masks[NMS_G];
@@ -731,6 +864,9 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
     float* ky2 = kx2 + cap;
     float* kar = ky2 + cap;
     int* kcl = reinterpret_cast<int*>(kar + cap);                  // [cap]
+    int* knext = kcl + cap;                                        // [cap] previous kept box of the same class
+    int* chead = knext + cap;                                      // [C]   latest kept box of each class (-1: none)
+    u64* rowkeys = reinterpret_cast<u64*>(nms_smem + P.nms_rowkeys_off);  // [NMS_KCAP] best rows, sorted
 
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = P.C;
@@ -784,25 +920,64 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
     const u64 gmax = ((u64)s_red[1] << 32) | 0xFFFFFFFFull;
     const uint32_t img_max_ord = s_red[2];
     const bool per_class = !(ntot < P.split_thr);  // regime of mmcv batched_nms
+    for (int c = tid; c < C; c += NMS_THREADS) chead[c] = -1;
     const bool use_off = !P.nms_agnostic;
     const float mp1 = fadd(ord2f(img_max_ord), 1.0f);  // max_coordinate + 1
     const float thr = P.iou_thr, foff = P.foff;
 
-    auto fetch = [=](int i, u64& key) -> bool {
-        const uint32_t sb = mat[i];
-        key = make_key(__uint_as_float(sb), (uint32_t)i);
-        return sb != SCORE_NONE;
-    };
+    MatSource msrc;
+    msrc.m = mat;
+    msrc.slots = slots;
+    msrc.vec4 = ((slots & 3) == 0);
+    msrc.lo = 0u;
+    msrc.span = 0xFFFFFFFEu;
 
     int processed = 0;
     u64 lo = gmin;
+    // Upper key bounds for the chunks: the W-th best ROW maximum is a lower bound of the W-th best candidate
+    // score (each of those rows owns a candidate at least that good), so when a chunk must reach cumulative
+    // rank W every key above rowkeys[W-1] is rejected by the 32-bit window instead of going through the
+    // histogram. The (up to NMS_KCAP) best rows are selected and sorted once.
+    int nrows_sorted = 0;
+    {
+        RowBestSource rsrc;
+        rsrc.rs = P.row_stat + (size_t)b * P.R;
+        rsrc.R = P.R;
+        const int mrows = P.R < NMS_KCAP ? P.R : NMS_KCAP;
+        nrows_sorted = select_sorted_prefix(rsrc, gmin & 0xFFFFFFFF00000000ull, gmax, mrows, rowkeys, ktmp, NMS_KCAP, S);
+        nrows_sorted = nrows_sorted < mrows ? nrows_sorted : mrows;
+        __syncthreads();
+    }
     // the first chunk only needs a little more than `cap` candidates; later chunks (heavy suppression) are full
     int chunk = cap + (cap >> 2) + 64;
     chunk = chunk < NMS_CH ? chunk : NMS_CH;
     while (processed < ntot && s_nk < cap) {
         const int want = min(chunk, ntot - processed);
         chunk = NMS_CH;
-        const int got = select_sorted_prefix(fetch, slots, lo, gmax, want, keys, ktmp, NMS_KCAP, S);
+        const int wc = processed + want;  // cumulative rank this chunk must reach
+        const u64 hi = wc <= nrows_sorted ? (rowkeys[wc - 1] | 0xFFFFFFFFull) : gmax;
+        {
+            // key high word = ~ord(score); for a non-negative score ord = bits | 0x80000000
+            const uint32_t best_bits = (~(uint32_t)(lo >> 32)) & 0x7FFFFFFFu, worst_bits = (~(uint32_t)(hi >> 32)) & 0x7FFFFFFFu;
+            msrc.lo = worst_bits;
+            msrc.span = best_bits - worst_bits;
+        }
+        int got;
+        if (wc <= nrows_sorted) {
+            // only the wc best rows can hold one of the wc best candidates: scan just their matrix rows
+            RowListSource rl;
+            rl.m = mat;
+            rl.rows = rowkeys;
+            rl.nrows = wc;
+            rl.C = C;
+            rl.nsub = (C + 127) / 128;
+            rl.vec4 = ((C & 3) == 0);
+            rl.lo = msrc.lo;
+            rl.span = msrc.span;
+            got = select_sorted_prefix(rl, lo, hi, want, keys, ktmp, NMS_KCAP, S);
+        } else {
+            got = select_sorted_prefix(msrc, lo, hi, want, keys, ktmp, NMS_KCAP, S);
+        }
         const int m = got < NMS_CH ? got : NMS_CH;  // boxes staged this round (a prefix of the sorted order)
         if (m == 0) break;
         for (int i = tid; i < m; i += NMS_THREADS) {
@@ -828,8 +1003,34 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
         for (int s0 = 0; s0 < m; s0 += NMS_G) {
             const int nk = s_nk;
             if (nk >= cap) break;
-            // ---- phase A: the group's 64 candidates against the kept list (16 kept-subsets x 64 candidates)
-            {
+            // ---- phase A: the group's 64 candidates against the kept list
+            if (per_class) {
+                // classes are independent: walk the chain of kept boxes of the candidate's own class (a handful)
+                if (tid < NMS_G) {
+                    const int j = s0 + tid;
+                    bool sup = false;
+                    if (j < m) {
+                        Box bj;
+                        bj.x1 = cx1[j];
+                        bj.y1 = cy1[j];
+                        bj.x2 = cx2[j];
+                        bj.y2 = cy2[j];
+                        bj.area = car[j];
+                        for (int k = chead[ccl[j]]; k >= 0 && !sup; k = knext[k]) {
+                            Box bk;
+                            bk.x1 = kx1[k];
+                            bk.y1 = ky1[k];
+                            bk.x2 = kx2[k];
+                            bk.y2 = ky2[k];
+                            bk.area = kar[k];
+                            sup = iou_gt(bk, bj, thr, foff);
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, sup);
+                    if (lane == 0 && bal) atomicOr(&s_sup, (u64)bal << ((warp & 1) * 32));
+                }
+            } else {
+                // one problem over all classes' offset boxes: 16 kept-subsets x 64 candidates
                 const int j = s0 + (tid & (NMS_G - 1));
                 const bool valid = j < m;
                 Box bj;
@@ -838,7 +1039,6 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
                 bj.x2 = valid ? cx2[j] : 0.f;
                 bj.y2 = valid ? cy2[j] : 0.f;
                 bj.area = valid ? car[j] : 0.f;
-                const int cj = valid ? ccl[j] : -1;
                 bool sup = false;
                 for (int k = tid >> 6; k < nk; k += NMS_THREADS / NMS_G) {
                     Box bk;
@@ -847,8 +1047,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
                     bk.x2 = kx2[k];
                     bk.y2 = ky2[k];
                     bk.area = kar[k];
-                    const bool same = !per_class || (kcl[k] == cj);
-                    if (valid && !sup && same && iou_gt(bk, bj, thr, foff)) sup = true;
+                    if (valid && !sup && iou_gt(bk, bj, thr, foff)) sup = true;
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, sup);
                 if (lane == 0 && bal) atomicOr(&s_sup, (u64)bal << ((warp & 1) * 32));
@@ -894,18 +1093,27 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
                 u64 alive = validm & ~s_sup;
                 const u64 ma = s_masks[lane], mb = s_masks[lane + 32];
                 const int room = cap - nk;
-                u64 keptm = 0ull, rem = alive;
-                int kept_here = 0;
-                while (rem) {
-                    const int i = __ffsll((long long)rem) - 1;
-                    if (++kept_here > room) break;  // later boxes cannot enter the first `cap` kept
-                    keptm |= 1ull << i;
-                    const u64 src = i < 32 ? ma : mb;
-                    const unsigned lo32 = __shfl_sync(0xffffffffu, (unsigned)src, i & 31);
-                    const unsigned hi32 = __shfl_sync(0xffffffffu, (unsigned)(src >> 32), i & 31);
-                    alive &= ~(((u64)hi32 << 32) | (u64)lo32);
-                    rem = (i >= 63) ? 0ull : (alive & ~((2ull << i) - 1ull));
+                // the shuffle sources are compile-time constants, so all 128 shuffles are in flight at once and the
+                // serial chain is two bit operations per candidate
+                u64 keptm = 0ull;
+                const unsigned ma_lo = (unsigned)ma, ma_hi = (unsigned)(ma >> 32);
+                const unsigned mb_lo = (unsigned)mb, mb_hi = (unsigned)(mb >> 32);
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const unsigned lo32 = __shfl_sync(0xffffffffu, ma_lo, i), hi32 = __shfl_sync(0xffffffffu, ma_hi, i);
+                    const bool kp = (alive >> i) & 1ull;
+                    keptm |= kp ? (1ull << i) : 0ull;
+                    alive &= kp ? ~(((u64)hi32 << 32) | (u64)lo32) : ~0ull;
                 }
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const unsigned lo32 = __shfl_sync(0xffffffffu, mb_lo, i), hi32 = __shfl_sync(0xffffffffu, mb_hi, i);
+                    const bool kp = (alive >> (i + 32)) & 1ull;
+                    keptm |= kp ? (1ull << (i + 32)) : 0ull;
+                    alive &= kp ? ~(((u64)hi32 << 32) | (u64)lo32) : ~0ull;
+                }
+                // only the first `room` kept boxes can enter the first `cap` kept (later ones never affect earlier)
+                for (int kc = __popcll(keptm); kc > room; --kc) keptm &= ~(1ull << (63 - __clzll((long long)keptm)));
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int jj = h * 32 + lane;
@@ -919,6 +1127,7 @@ __global__ void __launch_bounds__(NMS_THREADS) nms_image_kernel(const __grid_con
                         kar[kidx] = car[gj];
                         kcl[kidx] = ccl[gj];
                         kkey[kidx] = keys[gj];
+                        knext[kidx] = atomicExch(&chead[ccl[gj]], kidx);  // push on the class chain (order irrelevant)
                     }
                 }
                 if (lane == 0) {
