@@ -193,7 +193,7 @@ def run_reference(args):
                          'the reference itself is Python+mmcv and cannot be installed here (mmcv-full absent)')),
                 cpu_baseline=dict(value=ips, unit=UNIT, cores=cores, kind='port', sample=sample),
                 e2e=dict(value=ips, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -354,14 +354,32 @@ def run_yolopp(args):
                 p90_ms=sorted(step_ms)[int(0.9 * (K - 1))], higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', config=config_dict(args, case), clocks=clocks, e2e=e2e,
                 gpu_launches=info.kernel_launches * K, roofline=roofline, cpu_baseline=cpu_baseline)
-    print(json.dumps(line))
+    emit(line)
     if distributed:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else any library prints (NCCL banners, warnings)
+    was diverted to stderr at start-up."""
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the duration of the run (native libraries write to fd 1 directly)
     if args.impl == 'reference':
         return run_reference(args)
     return run_yolopp(args)
