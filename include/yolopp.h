@@ -165,17 +165,38 @@ int yolopp_coder_decode(int mode, const float* bboxes, const float* pred, float 
                         void* stream);
 
 /*
- * mmcv.ops.nms.batched_nms on device (also backs multiclass_nms and nms).
- *   boxes  DEVICE [n][4], scores DEVICE [n], idxs DEVICE [n] int64 (NULL = class agnostic / plain nms)
- *   keep   DEVICE [n] int64: indices into the inputs, in the reference's output order
- *   dets   DEVICE [n][5]
- *   num_keep DEVICE [1] int32
- * `max_num` <= 0 keeps all. workspace from yolopp_nms_workspace_bytes(n).
+ * mmcv.ops.nms.batched_nms on device — also backs mmcv.ops.nms.nms (idxs == NULL, split_thr = INT_MAX).
+ * Replaces the third-party call at mmdet/core/post_processing/bbox_nms.py:84 and the direct callers
+ * (rpn_head.py:247, cascade_rpn_head.py:670, ...). Same semantics as the in-path NMS: class-offset boxes
+ * boxes + idx*(max+1) unless class_agnostic, ONE greedy pass when n < split_thr else classes independent,
+ * result in (score desc, index asc) order, first max_num kept.
+ *   boxes  DEVICE [n][4] fp32 (16-byte aligned), scores DEVICE [n], idxs DEVICE [n] int64 in [0, num_labels) or NULL
+ *   dets   DEVICE [cap][5], keep DEVICE [cap] int64 (indices into the inputs), cap = min(4096, max_num if
+ *          0 < max_num < n else n)  — the kept list lives in shared memory, so max_num must be <= 4096
+ *   num_keep DEVICE int32[2]: [0] = number kept, [1] = 0 or YOLOPP_E_OVERFLOW (no max_num given and more than
+ *          4096 boxes survive)
  */
-size_t yolopp_nms_workspace_bytes(int64_t n);
-int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, float iou_thr,
-                       int nms_offset, int split_thr, int class_agnostic, int max_num, float* dets, int64_t* keep,
-                       int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream);
+int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, int32_t num_labels,
+                       float iou_thr, int nms_offset, int split_thr, int class_agnostic, int max_num, float* dets,
+                       int64_t* keep, int32_t* num_keep, void* stream);
+
+/*
+ * multiclass_nms (mmdet/core/post_processing/bbox_nms.py:7-93) on device, for the other heads that share the
+ * back-end: (row, class) expansion, scores > score_thr, optional score_factors AFTER the threshold, batched_nms,
+ * first max_num.
+ *   multi_bboxes DEVICE [n][4] (boxes_per_class = 0) or [n][C][4] (boxes_per_class = 1), 16-byte aligned
+ *   multi_scores DEVICE [n][C+1] (last column = background, ignored); score_factors DEVICE [n] or NULL
+ *   dets DEVICE [cap][5], labels DEVICE [cap] int64, flat_inds DEVICE [cap] int64 (row*C + class; may be NULL),
+ *   num_keep DEVICE int32[2] ([0] count, [1] 0 or YOLOPP_E_OVERFLOW), num_candidates DEVICE [1] (may be NULL);
+ *   cap = min(4096, effective max_num or n*C)
+ *   workspace >= yolopp_nms_workspace_bytes(n, C), 256-byte aligned
+ */
+size_t yolopp_nms_workspace_bytes(int64_t n, int32_t num_classes);
+int yolopp_multiclass_nms(const float* multi_bboxes, int boxes_per_class, const float* multi_scores, int64_t n,
+                          int32_t num_classes, float score_thr, const float* score_factors, float iou_thr,
+                          int nms_offset, int split_thr, int class_agnostic, int nms_max_num, int max_num, float* dets,
+                          int64_t* labels, int64_t* flat_inds, int32_t* num_keep, int32_t* num_candidates,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * Bit-reproducible synthetic head tensors (bench / tests): element i of a level tensor gets

@@ -437,18 +437,131 @@ int yolopp_synth_level(float* out, int32_t batch, int32_t num_anchors, int32_t n
     return cuda_rc(cudaGetLastError());
 }
 
-// batched_nms standalone: implemented in yolopp_nms_capi.cuh (same kernels, generic inputs)
-size_t yolopp_nms_workspace_bytes(int64_t n) {
-    (void)n;
-    return 0;
+// ---------------------------------------------------------------------------------------------------
+// standalone NMS entry points: the per-image NMS kernel with B = 1
+// ---------------------------------------------------------------------------------------------------
+static size_t nms_only_smem(int keep_cap, int nlab, int* rowkeys_off) {
+    size_t sm = (size_t)NMS_KCAP * 8 * 2 + (size_t)keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)keep_cap * 28 + (size_t)nlab * 4;
+    sm = align_up(sm, 16);
+    *rowkeys_off = (int)sm;
+    return sm + (size_t)NMS_KCAP * 8;
 }
-int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, float iou_thr,
-                       int nms_offset, int split_thr, int class_agnostic, int max_num, float* dets, int64_t* keep,
-                       int32_t* num_keep, void* workspace, size_t workspace_bytes, void* stream) {
-    (void)boxes; (void)scores; (void)idxs; (void)n; (void)iou_thr; (void)nms_offset; (void)split_thr;
-    (void)class_agnostic; (void)max_num; (void)dets; (void)keep; (void)num_keep; (void)workspace;
-    (void)workspace_bytes; (void)stream;
-    return YOLOPP_E_INVALID;  // TODO(round 1, later milestone)
+
+static int launch_nms_only(DevParams& d, int nlab, cudaStream_t stream) {
+    int off = 0;
+    const size_t smem = nms_only_smem(d.keep_cap, nlab, &off);
+    d.nms_rowkeys_off = off;
+    if (smem > 220 * 1024) return YOLOPP_E_INVALID;
+    cudaError_t e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_rc(e);
+    nms_image_kernel<<<1, NMS_THREADS, smem, stream>>>(d);
+    return cuda_rc(cudaGetLastError());
+}
+
+size_t yolopp_nms_workspace_bytes(int64_t n, int32_t num_classes) {
+    if (n < 0 || num_classes < 0) return 0;
+    // multiclass_nms: score matrix + per-row statistics; batched_nms / nms (num_classes == 0): nothing
+    return num_classes == 0 ? 256 : align_up((size_t)n * num_classes * 4, 256) + align_up((size_t)n * 16, 256) + 256;
+}
+
+int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, int32_t num_labels,
+                       float iou_thr, int nms_offset, int split_thr, int class_agnostic, int max_num, float* dets,
+                       int64_t* keep, int32_t* num_keep, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || n >= (1ll << 31) || !num_keep || (nms_offset != 0 && nms_offset != 1)) return YOLOPP_E_INVALID;
+    int rc = device_check();
+    if (rc != YOLOPP_OK) return rc;
+    if (n == 0) return cuda_rc(cudaMemsetAsync(num_keep, 0, 2 * sizeof(int32_t), stream));
+    if (!boxes || !scores || !dets || !keep || (((uintptr_t)boxes) & 15)) return YOLOPP_E_INVALID;
+    const int nlab = idxs ? num_labels : 1;
+    if (nlab < 1 || nlab > YOLOPP_MAX_CLASSES) return YOLOPP_E_INVALID;
+    long long cap = (max_num > 0 && max_num < n) ? max_num : n;
+    if (max_num > NMS_MAX_KEEP) return YOLOPP_E_INVALID;  // kept list lives in shared memory
+    if (cap > NMS_MAX_KEEP) cap = NMS_MAX_KEEP;           // "keep all": overflow is reported in num_keep[1]
+    cudaError_t e0 = cudaMemsetAsync(num_keep, 0, 2 * sizeof(int32_t), stream);
+    if (e0 != cudaSuccess) return cuda_rc(e0);
+    DevParams d;
+    memset(&d, 0, sizeof(d));
+    d.B = 1;
+    d.R = (int)n;
+    d.C = 1;
+    d.generic = 1;
+    d.num_labels = nlab;
+    d.g_scores = scores;
+    d.g_labels = (const long long*)idxs;
+    d.row_box = (float4*)boxes;
+    d.iou_thr = iou_thr;
+    d.foff = (float)nms_offset;
+    d.split_thr = split_thr;
+    d.nms_agnostic = (class_agnostic || !idxs) ? 1 : 0;
+    d.m_eff = max_num > 0 ? max_num : -1;
+    d.keep_cap = (int)cap;
+    d.out_cap = (int)cap;
+    d.o_dets = dets;
+    d.o_keep = (long long*)keep;
+    d.o_count = num_keep;
+    d.o_status = num_keep + 1;
+    return launch_nms_only(d, nlab, stream);
+}
+
+int yolopp_multiclass_nms(const float* multi_bboxes, int boxes_per_class, const float* multi_scores, int64_t n,
+                          int32_t num_classes, float score_thr, const float* score_factors, float iou_thr,
+                          int nms_offset, int split_thr, int class_agnostic, int nms_max_num, int max_num, float* dets,
+                          int64_t* labels, int64_t* flat_inds, int32_t* num_keep, int32_t* num_candidates,
+                          void* workspace, size_t workspace_bytes, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || num_classes < 1 || num_classes > YOLOPP_MAX_CLASSES || n * num_classes >= (1ll << 31) || !num_keep ||
+        (nms_offset != 0 && nms_offset != 1))
+        return YOLOPP_E_INVALID;
+    int rc = device_check();
+    if (rc != YOLOPP_OK) return rc;
+    if (n == 0) {
+        if (num_candidates) cudaMemsetAsync(num_candidates, 0, sizeof(int32_t), stream);
+        return cuda_rc(cudaMemsetAsync(num_keep, 0, 2 * sizeof(int32_t), stream));
+    }
+    if (!multi_bboxes || !multi_scores || !dets || !labels || (((uintptr_t)multi_bboxes) & 15)) return YOLOPP_E_INVALID;
+    if (!workspace || workspace_bytes < yolopp_nms_workspace_bytes(n, num_classes) || (((uintptr_t)workspace) & 255))
+        return YOLOPP_E_WORKSPACE;
+    int m_eff = -1;
+    if (max_num > 0) m_eff = max_num;
+    if (nms_max_num > 0) m_eff = (m_eff > 0 && m_eff < nms_max_num) ? m_eff : nms_max_num;
+    const long long total = n * num_classes;
+    long long cap = (m_eff > 0 && m_eff < total) ? m_eff : total;
+    if (m_eff > NMS_MAX_KEEP) return YOLOPP_E_INVALID;
+    if (cap > NMS_MAX_KEEP) cap = NMS_MAX_KEEP;  // "keep all": overflow is reported in num_keep[1]
+    cudaError_t e0 = cudaMemsetAsync(num_keep, 0, 2 * sizeof(int32_t), stream);
+    if (e0 != cudaSuccess) return cuda_rc(e0);
+    unsigned char* w = (unsigned char*)workspace;
+    uint32_t* mat = (uint32_t*)w;
+    uint4* row_stat = (uint4*)(w + align_up((size_t)total * 4, 256));
+    multiclass_prep_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(multi_scores, score_factors, (const float4*)multi_bboxes,
+                                                                        boxes_per_class ? 1 : 0, (int)n, num_classes,
+                                                                        score_thr, mat, row_stat);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_rc(e);
+    DevParams d;
+    memset(&d, 0, sizeof(d));
+    d.B = 1;
+    d.R = (int)n;
+    d.C = num_classes;
+    d.boxes_per_class = boxes_per_class ? 1 : 0;
+    d.row_box = (float4*)multi_bboxes;
+    d.row_stat = row_stat;
+    d.mat = mat;
+    d.iou_thr = iou_thr;
+    d.foff = (float)nms_offset;
+    d.split_thr = split_thr;
+    d.nms_agnostic = class_agnostic ? 1 : 0;
+    d.m_eff = m_eff;
+    d.keep_cap = (int)cap;
+    d.out_cap = (int)cap;
+    d.o_dets = dets;
+    d.o_labels = (long long*)labels;
+    d.o_keep = (long long*)flat_inds;
+    d.o_count = num_keep;
+    d.o_status = num_keep + 1;
+    d.o_ncand = num_candidates;
+    return launch_nms_only(d, num_classes, stream);
 }
 
 }  // extern "C"

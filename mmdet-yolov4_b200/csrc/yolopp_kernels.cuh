@@ -79,6 +79,13 @@ struct DevParams {
     uint4* row_stat;     // [B][R]  per row: (max ord(score), max ~ord(score), #candidates, 0) — plain stores, the
                          //         per-image reduction happens in the NMS kernel (no same-address atomics)
     const float* scale;  // [B][4] or null
+    // standalone NMS entry points (yolopp_batched_nms / yolopp_multiclass_nms): B = 1
+    int generic;               // 1: candidates are the n input boxes themselves (C = 1), scores may be any float
+    int boxes_per_class;       // multi_bboxes is (n, 4C): the box of candidate (row, class) is boxes[row*C + class]
+    int num_labels;            // generic: labels are in [0, num_labels)
+    const float* g_scores;     // generic: [n]
+    const long long* g_labels; // generic: [n] or null (one class)
+    long long* o_keep;         // kept candidate (flat) indices, in output order; may be null
     // outputs
     float* o_dets;
     long long* o_labels;
@@ -871,8 +878,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = P.C;
     const int slots = P.R * C;
-    const uint32_t* mat = P.mat + (size_t)b * slots;
+    const bool generic = P.generic != 0;
+    const uint32_t* mat = generic ? reinterpret_cast<const uint32_t*>(P.g_scores) : P.mat + (size_t)b * slots;
     const float4* row_box = P.row_box + (size_t)b * P.R;
+    const int nlab = generic ? P.num_labels : C;
 
     // candidate count, score range and boxes.max() of the image: reduction over the per-row statistics that the
     // decode kernels stored
@@ -886,16 +895,29 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     }
     __syncthreads();
     {
-        const uint4* rs = P.row_stat + (size_t)b * P.R;
         uint32_t best = 0u, worst = 0u, mx = 0u, cnt = 0u;
-        for (int r = tid; r < P.R; r += NMS_THREADS) {
-            const uint4 st = rs[r];
-            if (st.z) {
-                best = st.x > best ? st.x : best;
-                worst = st.y > worst ? st.y : worst;
-                cnt += st.z;
-                const uint32_t o = f2ord(box_max(row_box[r]));  // boxes.max() runs over candidate boxes only
-                mx = o > mx ? o : mx;
+        if (!generic) {
+            const uint4* rs = P.row_stat + (size_t)b * P.R;
+            for (int r = tid; r < P.R; r += NMS_THREADS) {
+                const uint4 st = rs[r];
+                if (st.z) {
+                    best = st.x > best ? st.x : best;
+                    worst = st.y > worst ? st.y : worst;
+                    cnt += st.z;
+                    // boxes.max() runs over candidate boxes only (precomputed per row when boxes are per class)
+                    const uint32_t o = st.w ? st.w : f2ord(box_max(row_box[r]));
+                    mx = o > mx ? o : mx;
+                }
+            }
+        } else {
+            // every input box is a candidate: key range over all scores, boxes.max() over all boxes
+            for (int i = tid; i < slots; i += NMS_THREADS) {
+                const uint32_t o = f2ord(__uint_as_float(mat[i]));
+                best = o > best ? o : best;
+                worst = ~o > worst ? ~o : worst;
+                const uint32_t bo = f2ord(box_max(row_box[i]));
+                mx = bo > mx ? bo : mx;
+                ++cnt;
             }
         }
         best = __reduce_max_sync(0xffffffffu, best);
@@ -920,7 +942,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     const u64 gmax = ((u64)s_red[1] << 32) | 0xFFFFFFFFull;
     const uint32_t img_max_ord = s_red[2];
     const bool per_class = !(ntot < P.split_thr);  // regime of mmcv batched_nms
-    for (int c = tid; c < C; c += NMS_THREADS) chead[c] = -1;
+    for (int c = tid; c < nlab; c += NMS_THREADS) chead[c] = -1;
     const bool use_off = !P.nms_agnostic;
     const float mp1 = fadd(ord2f(img_max_ord), 1.0f);  // max_coordinate + 1
     const float thr = P.iou_thr, foff = P.foff;
@@ -939,7 +961,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     // rank W every key above rowkeys[W-1] is rejected by the 32-bit window instead of going through the
     // histogram. The (up to NMS_KCAP) best rows are selected and sorted once.
     int nrows_sorted = 0;
-    {
+    if (!generic) {
         RowBestSource rsrc;
         rsrc.rs = P.row_stat + (size_t)b * P.R;
         rsrc.R = P.R;
@@ -959,8 +981,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         {
             // key high word = ~ord(score); for a non-negative score ord = bits | 0x80000000
             const uint32_t best_bits = (~(uint32_t)(lo >> 32)) & 0x7FFFFFFFu, worst_bits = (~(uint32_t)(hi >> 32)) & 0x7FFFFFFFu;
-            msrc.lo = worst_bits;
-            msrc.span = best_bits - worst_bits;
+            if (!generic) {  // (arbitrary-sign scores keep the full window; the exact 64-bit test still applies)
+                msrc.lo = worst_bits;
+                msrc.span = best_bits - worst_bits;
+            }
         }
         int got;
         if (wc <= nrows_sorted) {
@@ -982,8 +1006,9 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         if (m == 0) break;
         for (int i = tid; i < m; i += NMS_THREADS) {
             const uint32_t flat = key_flat(keys[i]);
-            const int r = (int)(flat / (uint32_t)C), c = (int)(flat - (uint32_t)r * (uint32_t)C);
-            const float4 bx = row_box[r];
+            const int r = (int)(flat / (uint32_t)C);
+            const int c = generic ? (P.g_labels ? (int)P.g_labels[flat] : 0) : (int)(flat - (uint32_t)r * (uint32_t)C);
+            const float4 bx = row_box[P.boxes_per_class ? flat : (uint32_t)r];
             float x1 = bx.x, y1 = bx.y, x2 = bx.z, y2 = bx.w;
             if (use_off) {  // boxes + idxs.to(boxes) * (max_coordinate + 1)
                 const float off = fmul((float)c, mp1);
@@ -1143,26 +1168,69 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     }
     // outputs: dets = (boxes[keep], scores[keep]), labels[keep]  (bbox_nms.py:84-93)
     int nk = s_nk;
+    // "keep all" (no max_num) but the kept list is full while candidates remain: report, do not truncate silently
+    if (P.m_eff <= 0 && nk >= cap && processed < ntot && tid == 0 && P.o_status) atomicMax(P.o_status, 3);
     if (nk > P.out_cap) {
         nk = P.out_cap;
-        if (tid == 0) atomicMax(P.o_status, 3);  // YOLOPP_E_OVERFLOW
+        if (tid == 0 && P.o_status) atomicMax(P.o_status, 3);  // YOLOPP_E_OVERFLOW
     }
     for (int i = tid; i < nk; i += NMS_THREADS) {
         const u64 key = kkey[i];
         const uint32_t flat = key_flat(key);
-        const int r = (int)(flat / (uint32_t)C), c = (int)(flat - (uint32_t)r * (uint32_t)C);
-        const float4 bx = row_box[r];
+        const int r = (int)(flat / (uint32_t)C);
+        const int c = generic ? kcl[i] : (int)(flat - (uint32_t)r * (uint32_t)C);
+        const float4 bx = row_box[P.boxes_per_class ? flat : (uint32_t)r];
         float* d = P.o_dets + ((size_t)b * P.out_cap + i) * 5;
         d[0] = bx.x;
         d[1] = bx.y;
         d[2] = bx.z;
         d[3] = bx.w;
         d[4] = key_score(key);
-        P.o_labels[(size_t)b * P.out_cap + i] = (long long)c;
+        if (P.o_labels) P.o_labels[(size_t)b * P.out_cap + i] = (long long)c;
+        if (P.o_keep) P.o_keep[(size_t)b * P.out_cap + i] = (long long)flat;
         if (P.o_anchors) P.o_anchors[(size_t)b * P.out_cap + i] = P.row_anchor[(size_t)b * P.R + r];
         if (P.o_rows) P.o_rows[(size_t)b * P.out_cap + i] = r;
     }
     if (tid == 0) P.o_count[b] = nk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multiclass_nms front half (bbox_nms.py:34-62): threshold, optional score_factors, per-row statistics.
+// One warp per row of multi_scores (n, C+1); writes the (row, class) score matrix the NMS kernel streams.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) multiclass_prep_kernel(const float* __restrict__ multi_scores,
+                                                              const float* __restrict__ score_factors,
+                                                              const float4* __restrict__ boxes, int per_class, int n,
+                                                              int C, float score_thr, uint32_t* __restrict__ mat,
+                                                              uint4* __restrict__ row_stat) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const float* srow = multi_scores + (size_t)r * (C + 1);  // last column = background, ignored (bbox_nms.py:42)
+    const float fac = score_factors ? score_factors[r] : 1.0f;
+    uint32_t best = 0u, worst = 0u, mx = 0u;
+    int npass = 0;
+    for (int c = lane; c < C; c += 32) {
+        float sc = srow[c];
+        const bool pass = sc > score_thr;             // valid_mask = scores > score_thr  (bbox_nms.py:54)
+        if (score_factors) sc = fmul(sc, fac);        // scores * score_factors AFTER the threshold (:57-62)
+        mat[(size_t)r * C + c] = pass ? __float_as_uint(sc) : SCORE_NONE;
+        if (pass) {
+            const uint32_t o = f2ord(sc);
+            best = o > best ? o : best;
+            worst = ~o > worst ? ~o : worst;
+            ++npass;
+            if (per_class) {
+                const uint32_t bo = f2ord(box_max(boxes[(size_t)r * C + c]));
+                mx = bo > mx ? bo : mx;
+            }
+        }
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    worst = __reduce_max_sync(0xffffffffu, worst);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    npass = __reduce_add_sync(0xffffffffu, npass);
+    if (lane == 0) row_stat[r] = make_uint4(best, worst, (uint32_t)npass, mx);
 }
 
 // ------------------------------------------------------------------------------------------------

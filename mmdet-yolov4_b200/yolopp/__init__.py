@@ -9,11 +9,12 @@ from ._capi import MODE_CSP, MODE_V3, make_params, load_library
 from .ops import get_bboxes_raw, coder_decode, sigmoid, exp
 from .heads import (YOLOCSPHead, YOLOV3Head, YOLOV4BBoxCoder, YOLOBBoxCoder, YOLOAnchorGenerator,
                     YOLOV4AnchorGenerator, patch_head)
+from .nms import multiclass_nms, batched_nms, nms
 from . import synth
 from . import shard
 
 __all__ = [
     'MODE_CSP', 'MODE_V3', 'make_params', 'load_library', 'get_bboxes_raw', 'coder_decode', 'sigmoid', 'exp',
     'YOLOCSPHead', 'YOLOV3Head', 'YOLOV4BBoxCoder', 'YOLOBBoxCoder', 'YOLOAnchorGenerator', 'YOLOV4AnchorGenerator',
-    'patch_head', 'synth', 'shard'
+    'patch_head', 'multiclass_nms', 'batched_nms', 'nms', 'synth', 'shard'
 ]

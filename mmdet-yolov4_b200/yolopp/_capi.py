@@ -210,11 +210,14 @@ def load_library(path=None):
     lib.yolopp_coder_decode.restype = ctypes.c_int
     lib.yolopp_coder_decode.argtypes = [ctypes.c_int, c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p]
     lib.yolopp_nms_workspace_bytes.restype = c_size_t
-    lib.yolopp_nms_workspace_bytes.argtypes = [c_int64]
+    lib.yolopp_nms_workspace_bytes.argtypes = [c_int64, c_int32]
     lib.yolopp_batched_nms.restype = ctypes.c_int
-    lib.yolopp_batched_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, ctypes.c_int, ctypes.c_int,
-                                       ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
-                                       c_void_p]
+    lib.yolopp_batched_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.yolopp_multiclass_nms.restype = ctypes.c_int
+    lib.yolopp_multiclass_nms.argtypes = [c_void_p, ctypes.c_int, c_void_p, c_int64, c_int32, c_float, c_void_p, c_float,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.yolopp_synth_level.restype = ctypes.c_int
     lib.yolopp_synth_level.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, ctypes.POINTER(c_float),
                                        ctypes.POINTER(c_float), c_uint64, c_void_p]
@@ -231,7 +234,8 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = ('yolopp_abi_version', 'yolopp_strerror', 'yolopp_workspace_bytes', 'yolopp_get_bboxes',
                     'yolopp_get_bboxes_profiled', 'yolopp_describe',
-                    'yolopp_coder_decode', 'yolopp_nms_workspace_bytes', 'yolopp_batched_nms', 'yolopp_synth_level',
+                    'yolopp_coder_decode', 'yolopp_nms_workspace_bytes', 'yolopp_batched_nms', 'yolopp_multiclass_nms',
+                    'yolopp_synth_level',
                     'yolopp_sigmoid', 'yolopp_exp')
 
 

@@ -191,3 +191,91 @@ def test_full_size_batch64_properties():
         assert n == res['count'][b]
         np.testing.assert_array_equal(_u32(res['dets'][b, :n]), _u32(orc['dets'][b]))
         np.testing.assert_array_equal(res['anchors'][b, :n], orc['anchors'][b])
+
+
+# ----------------------------------------------------------------------------------------------------
+# standalone NMS entry points (multiclass_nms / batched_nms / nms shims) vs the oracle
+# ----------------------------------------------------------------------------------------------------
+def _rand_boxes(rng, n, span=300., wh=90.):
+    xy = rng.rand(n, 2).astype(np.float32) * span - 20
+    sz = rng.rand(n, 2).astype(np.float32) * wh + 1
+    return np.concatenate([xy, xy + sz], 1)
+
+
+@pytest.mark.parametrize('n,ncls,split_thr,max_num,agnostic,offset', [
+    (0, 3, 10000, -1, False, 0), (1, 1, 10000, -1, False, 0), (700, 5, 10000, -1, False, 0), (700, 5, 100, -1, False, 0),
+    (3000, 20, 10000, 300, False, 0), (3000, 20, 1000, 300, False, 0), (2500, 4, 10000, 100, True, 0),
+    (900, 3, 10000, -1, False, 1), (12000, 80, 10000, 500, False, 0),
+])
+def test_batched_nms_matches_oracle(n, ncls, split_thr, max_num, agnostic, offset):
+    import yolopp
+    rng = np.random.RandomState(n + ncls)
+    boxes = _rand_boxes(rng, n)
+    scores = rng.rand(n).astype(np.float32)
+    if n > 10:
+        scores[rng.randint(0, n, 20)] = scores[0]  # exact ties
+    idxs = rng.randint(0, ncls, n).astype(np.int64)
+    cfg = dict(type='nms', iou_threshold=0.5, split_thr=split_thr)
+    if max_num > 0:
+        cfg['max_num'] = max_num
+    if agnostic:
+        cfg['class_agnostic'] = True
+    if offset:
+        cfg['offset'] = offset
+    dets, keep = yolopp.batched_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(),
+                                    torch.from_numpy(idxs).cuda(), cfg)
+    od, ok = oracle.batched_nms(boxes, scores, idxs, 0.5, offset=offset, split_thr=split_thr, class_agnostic=agnostic,
+                                max_num=max_num)
+    np.testing.assert_array_equal(keep.cpu().numpy(), ok)
+    np.testing.assert_array_equal(_u32(dets.cpu().numpy()), _u32(od))
+
+
+def test_nms_matches_oracle_and_torchvision():
+    import yolopp
+    rng = np.random.RandomState(5)
+    boxes = _rand_boxes(rng, 2000)
+    scores = (rng.rand(2000).astype(np.float32) - 0.3)  # negative scores too
+    dets, inds = yolopp.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.45)
+    keep = oracle.nms(boxes, scores, 0.45)
+    np.testing.assert_array_equal(inds.cpu().numpy(), keep)
+    np.testing.assert_array_equal(_u32(dets.cpu().numpy()[:, 4]), _u32(scores[keep]))
+    dets2, inds2 = yolopp.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.45, max_num=50)
+    np.testing.assert_array_equal(inds2.cpu().numpy(), keep[:50])
+
+
+@pytest.mark.parametrize('n,C,per_class,factors,thr,max_num', [
+    (500, 8, False, False, 0.05, 100), (500, 8, True, False, 0.05, 100), (1500, 80, False, True, 0.3, 200),
+    (300, 4, False, False, 0.999, 100), (300, 20, False, False, 0.5, -1),
+])
+def test_multiclass_nms_matches_oracle(n, C, per_class, factors, thr, max_num):
+    import yolopp
+    rng = np.random.RandomState(n + C)
+    boxes = _rand_boxes(rng, n * (C if per_class else 1)).reshape(n, -1)
+    scores = rng.rand(n, C + 1).astype(np.float32)
+    sf = rng.rand(n).astype(np.float32) if factors else None
+    cfg = dict(type='nms', iou_threshold=0.5)
+    out = yolopp.multiclass_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), thr, cfg, max_num,
+                                score_factors=None if sf is None else torch.from_numpy(sf).cuda(), return_inds=True)
+    od, ol, oi, oflat, ncand = oracle.multiclass_nms(boxes, scores, thr, 0.5, max_num=max_num, score_factors=sf)
+    if ncand == 0:
+        assert out[0].shape == (0, 4) and out[1].numel() == 0
+        return
+    dets, labels, inds = out
+    np.testing.assert_array_equal(labels.cpu().numpy(), ol)
+    np.testing.assert_array_equal(inds.cpu().numpy(), oi)
+    np.testing.assert_array_equal(_u32(dets.cpu().numpy()), _u32(od))
+
+
+def test_keep_all_overflow_is_reported_not_truncated():
+    """No max_num and more than 4096 survivors: the ops raise instead of silently truncating."""
+    import yolopp
+    rng = np.random.RandomState(9)
+    n = 6000
+    boxes = np.concatenate([np.arange(n, dtype=np.float32)[:, None] * 10 + np.zeros((n, 2), np.float32),
+                            np.arange(n, dtype=np.float32)[:, None] * 10 + 5 + np.zeros((n, 2), np.float32)], 1)
+    scores = rng.rand(n).astype(np.float32)
+    with pytest.raises(RuntimeError):
+        yolopp.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.5)
+    dets, inds = yolopp.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.5, max_num=4096)
+    assert inds.numel() == 4096
+    np.testing.assert_array_equal(inds.cpu().numpy(), oracle.nms(boxes, scores, 0.5)[:4096])
