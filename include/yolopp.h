@@ -150,8 +150,9 @@ typedef struct yolopp_plan_info {
     int32_t decode_ctas_per_sm;
     int32_t kernel_launches;     /* kernels launched per yolopp_get_bboxes call */
     int32_t reserved0;
-    int64_t tma_bytes_per_image; /* algorithmic bytes read per image by the TMA decode kernel: 4*A*(5+C)*sum(HW) */
-    int64_t ldg_bytes_per_image; /* ... by the generic decode kernel */
+    int64_t tma_bytes_per_image; /* algorithmic bytes read per image by the persistent decode kernel (TMA tiles +
+                                    gather tiles of unaligned levels): 4*A*(5+C)*sum(HW) over its levels */
+    int64_t ldg_bytes_per_image; /* ... by the generic decode kernel (dense admission) */
     int64_t workspace_bytes;
 } yolopp_plan_info;
 int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info);

@@ -142,23 +142,31 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     const bool tma_fits = plan->dec_smem <= 200 * 1024 && NA <= 256;
     plan->dec_ctas_per_sm = plan->dec_smem <= 110 * 1024 ? 2 : 1;
     int tma_tiles = 0, ldg_blocks = 0;
+    // persistent decode kernel: sparse-admission levels — TMA tiles where the plane stride is 16-byte aligned,
+    // gather tiles (enumerated first, their latency hides under the streaming) where it is not
     for (int l = 0; l < d.L; ++l) {
         LevelDev& lv = d.lv[l];
         const SegDev& sg = d.seg[lv.seg];
         const bool sparse = sg.has_topk && (long long)sg.k * 4 <= sg.N;
-        lv.use_tma = (tma_fits && sparse && (lv.HW % 4 == 0)) ? 1 : 0;
-        if (lv.use_tma) {
-            lv.tpp = (lv.HW + TILE_T - 1) / TILE_T;
-            lv.tile0 = tma_tiles;
-            long long t = (long long)lv.tpp * d.B * d.A;
-            CHECK_ARG(tma_tiles + t < (1ll << 30));
-            tma_tiles += (int)t;
-        } else {
-            lv.tpp = (lv.HW + 127) / 128;
-            lv.tile0 = ldg_blocks;
-            long long t = (long long)lv.tpp * d.B * d.A;
-            CHECK_ARG(ldg_blocks + t < (1ll << 30));
-            ldg_blocks += (int)t;
+        lv.use_tma = (tma_fits && sparse) ? ((lv.HW % 4 == 0) ? 1 : 2) : 0;
+    }
+    for (int pass = 2; pass >= 0; --pass) {
+        for (int l = 0; l < d.L; ++l) {
+            LevelDev& lv = d.lv[l];
+            if (lv.use_tma != pass) continue;
+            if (lv.use_tma) {
+                lv.tpp = (lv.HW + TILE_T - 1) / TILE_T;
+                lv.tile0 = tma_tiles;
+                long long t = (long long)lv.tpp * d.B * d.A;
+                CHECK_ARG(tma_tiles + t < (1ll << 30));
+                tma_tiles += (int)t;
+            } else {
+                lv.tpp = (lv.HW + 127) / 128;
+                lv.tile0 = ldg_blocks;
+                long long t = (long long)lv.tpp * d.B * d.A;
+                CHECK_ARG(ldg_blocks + t < (1ll << 30));
+                ldg_blocks += (int)t;
+            }
         }
     }
     d.tma_tiles = tma_tiles;
@@ -268,7 +276,7 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
     for (int l = 0; l < d.L; ++l) {
         if (!level_ptrs[l]) return YOLOPP_E_INVALID;
         d.lv[l].ptr = level_ptrs[l];
-        if (d.lv[l].use_tma && ((uintptr_t)level_ptrs[l] & 15) != 0) return YOLOPP_E_INVALID;
+        if (d.lv[l].use_tma == 1 && ((uintptr_t)level_ptrs[l] & 15) != 0) return YOLOPP_E_INVALID;
     }
     bind_workspace(&plan, workspace);
     d.scale = scale_factors;
@@ -306,7 +314,7 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
         TmapPack maps;
         memset(&maps, 0, sizeof(maps));
         for (int l = 0; l < d.L; ++l) {
-            if (!d.lv[l].use_tma) continue;
+            if (d.lv[l].use_tma != 1) continue;
             cuuint64_t gdim[2] = {(cuuint64_t)d.lv[l].HW, (cuuint64_t)d.B * d.A * d.NA};
             cuuint64_t gstr[1] = {(cuuint64_t)d.lv[l].HW * 4};
             cuuint32_t box[2] = {(cuuint32_t)TILE_SUB, (cuuint32_t)d.NA};
@@ -374,8 +382,8 @@ int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info) {
     info->workspace_bytes = (int64_t)plan.total;
     for (int l = 0; l < d.L; ++l) {
         int64_t bytes = (int64_t)4 * d.A * d.NA * d.lv[l].HW;
+        if (d.lv[l].use_tma == 1) info->tma_level_mask |= 1 << l;
         if (d.lv[l].use_tma) {
-            info->tma_level_mask |= 1 << l;
             info->tma_bytes_per_image += bytes;
         } else {
             info->ldg_bytes_per_image += bytes;

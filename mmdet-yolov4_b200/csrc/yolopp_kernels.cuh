@@ -19,11 +19,11 @@ constexpr uint32_t RANK_INVALID = 0xFFFFFFFFu;
 constexpr int TILE_T = 64;       // positions per TMA tile = two 32-wide boxes with 128-byte rows (SWIZZLE_128B)
 constexpr int TILE_SUB = 32;     // positions per box
 constexpr int DEC_STAGES = 4;    // TMA pipeline depth
-constexpr int DEC_CWARPS = 12;   // consumer warps per CTA (+1 producer warp), one whole tile per warp
-constexpr int DEC_NFULL = 16;    // "tile landed" barriers, indexed by iteration mod DEC_NFULL (> DEC_CWARPS, see kernel)
+constexpr int DEC_PWARPS = 2;    // producer warps per CTA: warp p issues the tiles of iterations it == p (mod 2)
+constexpr int DEC_CWARPS = 10;   // consumer warps per CTA, one whole tile per warp
 constexpr int DEC_BATCH = 4;     // admitted anchors whose logits a consumer pulls into registers at once
 constexpr int DEC_ROUNDS = 3;    // class sweeps held in registers (C <= 96); wider heads read the tile in place
-constexpr int DEC_THREADS = 32 * (1 + DEC_CWARPS);
+constexpr int DEC_THREADS = 32 * (DEC_PWARPS + DEC_CWARPS);
 
 constexpr int SEL_THREADS = 1024;
 constexpr int SEL_MAX_K = 4096;  // largest nms_pre the select kernel sorts in shared memory
@@ -40,7 +40,7 @@ struct LevelDev {
     int n_off;    // offset of this level in the concatenated anchor index n = n_off + (y*W+x)*A + a
     int m_off;    // offset in the plane-major, 4-element aligned index m = m_off + a*HW + hw
     int seg;      // top-k segment this level belongs to
-    int use_tma;  // decoded by decode_tma_kernel (else decode_ldg_kernel)
+    int use_tma;  // 1: TMA tiles of decode_tma_kernel, 2: gather tiles of decode_tma_kernel, 0: decode_ldg_kernel
     int tile0;    // first tile id of this level in its kernel's tile enumeration
     int tpp;      // tiles per plane
     float sx, sy; // anchor-generator strides
@@ -580,32 +580,40 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
     const int NA = P.NA;
     const StageGeom g = stage_geom(NA);
     const uint32_t box_bytes = (uint32_t)NA * 128u;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [DEC_NFULL]: tile of iteration it (mod DEC_NFULL) has landed
-    uint64_t* empty = full + DEC_NFULL;                       // [DEC_STAGES]: stage s may be refilled
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [DEC_STAGES]: the tile streamed into stage s has landed
+    uint64_t* empty = full + DEC_STAGES;                      // [DEC_STAGES]: stage s may be refilled
     int* next_it = reinterpret_cast<int*>(empty + DEC_STAGES);  // next tile (iteration) a consumer may claim
     unsigned char* stages = smem_raw + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         *next_it = 0;
-        for (int w = 0; w < DEC_NFULL; ++w) mbar_init(&full[w], 1);
-        for (int s = 0; s < DEC_STAGES; ++s) mbar_init(&empty[s], 1);
+        for (int s = 0; s < DEC_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+            reinterpret_cast<int4*>(stages + (size_t)s * g.stage_bytes + g.desc_off)->w = -1;  // "no tile yet"
+        }
         fence_mbar_init();
     }
     __syncthreads();
 
     const int total = P.tma_tiles;
-    if (warp == 0) {
-        // ---------------- producer ----------------
+    if (warp < DEC_PWARPS) {
+        // ---------------- producers: warp p owns the iterations it == p (mod DEC_PWARPS), i.e. stages p, p+2 ----------------
+        static_assert(DEC_STAGES % DEC_PWARPS == 0, "a stage must belong to one producer warp");
         const uint64_t pol = l2_policy_evict_first();
-        for (int it0 = 0; blockIdx.x + (long long)it0 * gridDim.x < total; it0 += 32) {
-            // lane j: coordinates of iteration it0 + j
-            const long long tl = blockIdx.x + (long long)(it0 + lane) * gridDim.x;
+        for (int k0 = 0; blockIdx.x + (long long)(k0 * DEC_PWARPS + warp) * gridDim.x < total; k0 += 32) {
+            // lane j: coordinates of this warp's iteration number k0 + j
+            const long long tl = blockIdx.x + (long long)((k0 + lane) * DEC_PWARPS + warp) * gridDim.x;
             int d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0;
             if (tl < total) {
                 const int t = (int)tl;
+                int best0 = -1;  // the level with the largest first-tile id <= t (gather levels are enumerated first)
                 for (int q = 0; q < P.L; ++q)
-                    if (P.lv[q].use_tma && t >= P.lv[q].tile0) d_l = q;
+                    if (P.lv[q].use_tma && t >= P.lv[q].tile0 && P.lv[q].tile0 > best0) {
+                        best0 = P.lv[q].tile0;
+                        d_l = q;
+                    }
                 const LevelDev& lv = P.lv[d_l];
                 const int loc = t - lv.tile0;
                 d_plane = loc / lv.tpp;  // b*A + a
@@ -614,7 +622,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                 d_a = d_plane - d_b * P.A;
             }
             for (int j = 0; j < 32; ++j) {
-                const int it = it0 + j;
+                const int it = (k0 + j) * DEC_PWARPS + warp;
                 if (blockIdx.x + (long long)it * gridDim.x >= total) break;
                 const int l = __shfl_sync(0xffffffffu, d_l, j), plane = __shfl_sync(0xffffffffu, d_plane, j);
                 const int hw0 = __shfl_sync(0xffffffffu, d_hw0, j), bb = __shfl_sync(0xffffffffu, d_b, j);
@@ -625,16 +633,21 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                     mbar_wait(&empty[s], ph ^ 1u);
                     const LevelDev& lv = P.lv[l];
                     unsigned char* dst = stages + (size_t)s * g.stage_bytes;
-                    const bool topk = P.seg[lv.seg].has_topk != 0;
-                    const bool two = hw0 + TILE_SUB < lv.HW;  // the second box is not entirely out of bounds
-                    *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l, bb, a, hw0);
-                    uint64_t* fb = &full[it % DEC_NFULL];
-                    mbar_arrive_expect_tx(fb, box_bytes * (two ? 2u : 1u) + (topk ? TILE_T * 4u : 0u));
-                    tma_load_2d_hint(dst, &maps.m[l], hw0, plane * NA, fb, pol);
-                    if (two) tma_load_2d_hint(dst + g.sub_bytes, &maps.m[l], hw0 + TILE_SUB, plane * NA, fb, pol);
-                    if (topk)
-                        bulk_load_1d(dst + g.rank_off, P.rank + (size_t)bb * P.M_pad + lv.m_off + a * lv.HW + hw0,
-                                     TILE_T * 4u, fb);
+                    // descriptor first (it carries the iteration number the consumer matches), then arm the barrier
+                    *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l | (a << 8), bb, hw0, it);
+                    uint64_t* fb = &full[s];
+                    if (lv.use_tma == 2) {
+                        mbar_arrive(fb);  // gather tile: nothing to stream, the consumer reads global memory itself
+                    } else {
+                        const bool topk = P.seg[lv.seg].has_topk != 0;
+                        const bool two = hw0 + TILE_SUB < lv.HW;  // the second box is not entirely out of bounds
+                        mbar_arrive_expect_tx(fb, box_bytes * (two ? 2u : 1u) + (topk ? TILE_T * 4u : 0u));
+                        tma_load_2d_hint(dst, &maps.m[l], hw0, plane * NA, fb, pol);
+                        if (two) tma_load_2d_hint(dst + g.sub_bytes, &maps.m[l], hw0 + TILE_SUB, plane * NA, fb, pol);
+                        if (topk)
+                            bulk_load_1d(dst + g.rank_off, P.rank + (size_t)bb * P.M_pad + lv.m_off + a * lv.HW + hw0,
+                                         TILE_T * 4u, fb);
+                    }
                 }
             }
         }
@@ -642,11 +655,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
     }
     // ---------------- consumers: whichever warp is free claims the CTA's next tile, in order ----------------
     // Tiles carry 0..8 admitted anchors, so a static round-robin would let one heavy tile block its stage (and
-    // with it the in-order producer) while the other warps idle. A parity wait can only tell a barrier's current
-    // phase from the one before it, so a waiter must never be two phases ahead: claimed-but-unfinished
-    // iterations span at most [o, o + DEC_CWARPS] (o = oldest unfinished), hence "landed" barriers are indexed
-    // by iteration mod DEC_NFULL with DEC_NFULL > DEC_CWARPS — the previous user of a barrier is then finished.
-    static_assert(DEC_NFULL > DEC_CWARPS, "see comment");
+    // with it the in-order producers) while the other warps idle. Several warps therefore wait on the same
+    // stage barrier for DIFFERENT fills, and a parity wait can only tell a barrier's current phase from the one
+    // before it. The tile descriptor disambiguates: the producer writes the iteration number into the stage
+    // header before arming the barrier, which it can only do after the previous fill of that stage was consumed;
+    // a consumer first waits until the header shows ITS iteration (the barrier is then in that fill's phase or
+    // later), and only then does the parity wait.
     const bool in_regs = P.C <= 32 * DEC_ROUNDS;
     while (true) {
         int it = 0;
@@ -654,12 +668,41 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         it = __shfl_sync(0xffffffffu, it, 0);
         if (blockIdx.x + (long long)it * gridDim.x >= total) break;
         const int s = it % DEC_STAGES;
-        mbar_wait(&full[it % DEC_NFULL], (uint32_t)(it / DEC_NFULL) & 1u);
         const unsigned char* stage = stages + (size_t)s * g.stage_bytes;
+        {
+            const volatile int* dit = reinterpret_cast<const volatile int*>(stage + g.desc_off) + 3;
+            while (*dit != it) __nanosleep(64);
+        }
+        mbar_wait(&full[s], (uint32_t)(it / DEC_STAGES) & 1u);
         const int4 desc = *reinterpret_cast<const int4*>(stage + g.desc_off);
-        const LevelDev& lv = P.lv[desc.x];
-        const int b = desc.y, a = desc.z, hw0 = desc.w;
+        const LevelDev& lv = P.lv[desc.x & 0xFF];
+        const int b = desc.y, a = desc.x >> 8, hw0 = desc.z;
         const SegDev& sg = P.seg[lv.seg];
+        if (lv.use_tma == 2) {
+            // gather tile (plane stride not 16-byte aligned, e.g. 19x19): the stage is not used
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            const float* slab = lv.ptr + (size_t)(b * P.A + a) * NA * lv.HW;
+            const size_t HW = (size_t)lv.HW;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int hw = hw0 + h * 32 + lane;
+                uint32_t r = RANK_INVALID;
+                if (hw < lv.HW) r = row_of(P, lv, b, a, hw);
+                unsigned adm = __ballot_sync(0xffffffffu, r != RANK_INVALID);
+                while (adm) {
+                    const int src = __ffs(adm) - 1;
+                    adm &= adm - 1;
+                    const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+                    const int hwp = hw0 + h * 32 + src;
+                    const float av = lane < 5 ? __ldg(slab + (size_t)lane * HW + hwp) : 0.f;
+                    process_anchor<MODE>(P, lv, sg, b, a, hwp, rr, lane, av, [&](int u) -> float {
+                        return __ldg(slab + (size_t)(5 + u * 32 + lane) * HW + hwp);
+                    });
+                }
+            }
+            continue;
+        }
         const uint32_t* rk = reinterpret_cast<const uint32_t*>(stage + g.rank_off);
 
         // admitted positions of the tile as a 64-bit mask

@@ -39,7 +39,8 @@ def test_planning_calls_need_no_device():
     assert info.anchors_per_image == 22743 and info.rows_per_image == 1000 and info.num_attrib == 85
     assert info.tma_level_mask == 0b011          # 76^2 and 38^2 planes are 16-byte aligned, 19^2 is not
     assert info.tma_bytes_per_image + info.ldg_bytes_per_image == 7732620  # 4*3*85*7581
-    assert info.kernel_launches == 4
+    assert info.kernel_launches == 3             # select, persistent decode (TMA + gather tiles), per-image NMS
+    assert info.ldg_blocks == 0 and info.ldg_bytes_per_image == 0
     # no top-k -> no select kernel, everything through the generic decode kernel
     p2 = cases.build_params(cases.CASES['csp320_nopre_dense'])
     i2 = capi.describe(p2)
