@@ -445,6 +445,12 @@ int yolopp_synth_level(float* out, int32_t batch, int32_t num_anchors, int32_t n
     return cuda_rc(cudaGetLastError());
 }
 
+#ifdef YPP_PROFILE
+int yolopp_prof_read(long long* host, int n) {
+    return (int)cudaMemcpyFromSymbol(host, ypp::g_prof, sizeof(long long) * (size_t)n);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------------
 // standalone NMS entry points: the per-image NMS kernel with B = 1
 // ---------------------------------------------------------------------------------------------------

@@ -20,7 +20,13 @@ constexpr int TILE_T = 64;       // positions per TMA tile = two 32-wide boxes w
 constexpr int TILE_SUB = 32;     // positions per box
 constexpr int DEC_STAGES = 4;    // TMA pipeline depth
 constexpr int DEC_PWARPS = 2;    // producer warps per CTA: warp p issues the tiles of iterations it == p (mod 2)
-constexpr int DEC_CWARPS = 10;   // consumer warps per CTA, one whole tile per warp
+#ifndef YPP_CWARPS
+#define YPP_CWARPS 8
+#endif
+#ifndef YPP_SLEEP
+#define YPP_SLEEP 64
+#endif
+constexpr int DEC_CWARPS = YPP_CWARPS;  // consumer warps per CTA, one whole tile per warp
 constexpr int DEC_BATCH = 4;     // admitted anchors whose logits a consumer pulls into registers at once
 constexpr int DEC_ROUNDS = 3;    // class sweeps held in registers (C <= 96); wider heads read the tile in place
 constexpr int DEC_THREADS = 32 * (DEC_PWARPS + DEC_CWARPS);
@@ -553,7 +559,7 @@ __host__ __device__ inline StageGeom stage_geom(int NA) {
     g.sub_bytes = ((uint32_t)NA * 128u + 1023u) & ~1023u;
     g.rank_off = 2u * g.sub_bytes;
     g.desc_off = g.rank_off + TILE_T * 4u;
-    g.stage_bytes = (g.desc_off + 16u + 1023u) & ~1023u;
+    g.stage_bytes = (g.desc_off + 32u + 1023u) & ~1023u;
     return g;
 }
 // logit of attribute k at position p of the tile (SWIZZLE_128B: 16-byte chunk index XOR (row mod 8))
@@ -571,6 +577,14 @@ __device__ __forceinline__ float tile_at(const unsigned char* stage, uint32_t su
 // bulk copy) and a 16-byte tile descriptor. 8 consumer warps take whole tiles round-robin: a consumer pulls the
 // logits of the tile's admitted anchors into registers, hands the stage straight back to the producer, and
 // only then does the math (lanes over classes), so a stage is held for a few hundred cycles.
+#ifdef YPP_PROFILE
+// per-tile timestamps (profiling build only): [tile][0..5] = issue start, issued, landed, released, done, smid
+__device__ long long g_prof[(1 << 16) * 8];
+#define YPP_STAMP(t, i) do { if (lane == 0 && (t) < (1 << 16)) g_prof[(size_t)(t) * 8 + (i)] = clock64(); } while (0)
+#else
+#define YPP_STAMP(t, i) do { } while (0)
+#endif
+
 template <int MODE>
 __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid_constant__ DevParams P,
                                                                   const __grid_constant__ TmapPack maps) {
@@ -605,7 +619,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         for (int k0 = 0; blockIdx.x + (long long)(k0 * DEC_PWARPS + warp) * gridDim.x < total; k0 += 32) {
             // lane j: coordinates of this warp's iteration number k0 + j
             const long long tl = blockIdx.x + (long long)((k0 + lane) * DEC_PWARPS + warp) * gridDim.x;
-            int d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0;
+            int d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0, d_hw = 0, d_rbase = 0, d_topk = 0;
             if (tl < total) {
                 const int t = (int)tl;
                 int best0 = -1;  // the level with the largest first-tile id <= t (gather levels are enumerated first)
@@ -620,6 +634,10 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                 d_hw0 = (loc - d_plane * lv.tpp) * TILE_T;
                 d_b = d_plane / P.A;
                 d_a = d_plane - d_b * P.A;
+                const SegDev& sg = P.seg[lv.seg];
+                d_hw = lv.HW;
+                d_topk = sg.has_topk;
+                d_rbase = sg.row_off + (lv.n_off - P.lv[sg.first_level].n_off) + d_a;  // row of position 0 (no top-k)
             }
             for (int j = 0; j < 32; ++j) {
                 const int it = (k0 + j) * DEC_PWARPS + warp;
@@ -627,20 +645,26 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                 const int l = __shfl_sync(0xffffffffu, d_l, j), plane = __shfl_sync(0xffffffffu, d_plane, j);
                 const int hw0 = __shfl_sync(0xffffffffu, d_hw0, j), bb = __shfl_sync(0xffffffffu, d_b, j);
                 const int a = __shfl_sync(0xffffffffu, d_a, j);
+                const int hwn = __shfl_sync(0xffffffffu, d_hw, j), rbase = __shfl_sync(0xffffffffu, d_rbase, j);
+                const int tk = __shfl_sync(0xffffffffu, d_topk, j);
                 if (lane == 0) {
                     const int s = it % DEC_STAGES;
                     const uint32_t ph = (uint32_t)(it / DEC_STAGES) & 1u;
+                    YPP_STAMP(blockIdx.x + it * gridDim.x, 0);
                     mbar_wait(&empty[s], ph ^ 1u);
+                    YPP_STAMP(blockIdx.x + it * gridDim.x, 1);
                     const LevelDev& lv = P.lv[l];
                     unsigned char* dst = stages + (size_t)s * g.stage_bytes;
-                    // descriptor first (it carries the iteration number the consumer matches), then arm the barrier
+                    // descriptor first (it carries the iteration number the consumer matches and everything the
+                    // consumer needs before it can release the stage), then arm the barrier
+                    *reinterpret_cast<int4*>(dst + g.desc_off + 16) = make_int4(hwn, rbase, tk, lv.use_tma);
                     *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l | (a << 8), bb, hw0, it);
                     uint64_t* fb = &full[s];
                     if (lv.use_tma == 2) {
                         mbar_arrive(fb);  // gather tile: nothing to stream, the consumer reads global memory itself
                     } else {
-                        const bool topk = P.seg[lv.seg].has_topk != 0;
-                        const bool two = hw0 + TILE_SUB < lv.HW;  // the second box is not entirely out of bounds
+                        const bool topk = tk != 0;
+                        const bool two = hw0 + TILE_SUB < hwn;  // the second box is not entirely out of bounds
                         mbar_arrive_expect_tx(fb, box_bytes * (two ? 2u : 1u) + (topk ? TILE_T * 4u : 0u));
                         tma_load_2d_hint(dst, &maps.m[l], hw0, plane * NA, fb, pol);
                         if (two) tma_load_2d_hint(dst + g.sub_bytes, &maps.m[l], hw0 + TILE_SUB, plane * NA, fb, pol);
@@ -671,17 +695,21 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         const unsigned char* stage = stages + (size_t)s * g.stage_bytes;
         {
             const volatile int* dit = reinterpret_cast<const volatile int*>(stage + g.desc_off) + 3;
-            while (*dit != it) __nanosleep(64);
+            while (*dit != it) __nanosleep(YPP_SLEEP);
         }
         mbar_wait(&full[s], (uint32_t)(it / DEC_STAGES) & 1u);
+        YPP_STAMP(blockIdx.x + it * gridDim.x, 2);
         const int4 desc = *reinterpret_cast<const int4*>(stage + g.desc_off);
-        const LevelDev& lv = P.lv[desc.x & 0xFF];
+        const int4 desc2 = *reinterpret_cast<const int4*>(stage + g.desc_off + 16);
         const int b = desc.y, a = desc.x >> 8, hw0 = desc.z;
-        const SegDev& sg = P.seg[lv.seg];
-        if (lv.use_tma == 2) {
+        const int lvl = desc.x & 0xFF, HWn = desc2.x, rbase = desc2.y;
+        const bool topk = desc2.z != 0;
+        if (desc2.w == 2) {
             // gather tile (plane stride not 16-byte aligned, e.g. 19x19): the stage is not used
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            const LevelDev& lv = P.lv[lvl];
+            const SegDev& sg = P.seg[lv.seg];
             const float* slab = lv.ptr + (size_t)(b * P.A + a) * NA * lv.HW;
             const size_t HW = (size_t)lv.HW;
 #pragma unroll
@@ -705,65 +733,66 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         }
         const uint32_t* rk = reinterpret_cast<const uint32_t*>(stage + g.rank_off);
 
-        // admitted positions of the tile as a 64-bit mask
+        // admitted positions of the tile as a 64-bit mask (everything needed comes from the stage header: no
+        // parameter-space lookups before the stage is released)
         uint32_t r_lo = RANK_INVALID, r_hi = RANK_INVALID;
         {
             const int p0 = lane, p1 = lane + 32;
-            const int rbase = sg.row_off + (lv.n_off - P.lv[sg.first_level].n_off) + a;
-            if (hw0 + p0 < lv.HW) r_lo = sg.has_topk ? rk[p0] : (uint32_t)(rbase + (hw0 + p0) * P.A);
-            if (hw0 + p1 < lv.HW) r_hi = sg.has_topk ? rk[p1] : (uint32_t)(rbase + (hw0 + p1) * P.A);
+            if (hw0 + p0 < HWn) r_lo = topk ? rk[p0] : (uint32_t)(rbase + (hw0 + p0) * P.A);
+            if (hw0 + p1 < HWn) r_hi = topk ? rk[p1] : (uint32_t)(rbase + (hw0 + p1) * P.A);
         }
         uint32_t m_lo = __ballot_sync(0xffffffffu, r_lo != RANK_INVALID);
         uint32_t m_hi = __ballot_sync(0xffffffffu, r_hi != RANK_INVALID);
+        YPP_STAMP(blockIdx.x + it * gridDim.x, 6);
         bool released = false;
         if (!(m_lo | m_hi)) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             released = true;
+            YPP_STAMP(blockIdx.x + it * gridDim.x, 3);
         }
         while (m_lo | m_hi) {
-            // pull up to DEC_BATCH admitted anchors out of the tile
+            // pick up to DEC_BATCH admitted positions (uniform scalar work) ...
             int pos[DEC_BATCH];
-            uint32_t rr[DEC_BATCH];
-            float tv[DEC_BATCH][DEC_ROUNDS];
             int nb = 0;
 #pragma unroll
             for (int q = 0; q < DEC_BATCH; ++q) {
-                pos[q] = 0;
-                rr[q] = 0u;
-#pragma unroll
-                for (int u = 0; u < DEC_ROUNDS; ++u) tv[q][u] = 0.f;
-                if (m_lo | m_hi) {
-                    int ps;
-                    if (m_lo) {
-                        ps = __ffs(m_lo) - 1;
-                        m_lo &= m_lo - 1;
-                    } else {
-                        ps = 32 + __ffs(m_hi) - 1;
-                        m_hi &= m_hi - 1;
-                    }
-                    pos[q] = ps;
-                    rr[q] = __shfl_sync(0xffffffffu, ps < 32 ? r_lo : r_hi, ps & 31);
-                    if (in_regs && !P.agnostic) {
-#pragma unroll
-                        for (int u = 0; u < DEC_ROUNDS; ++u) {
-                            const int c = u * 32 + lane;
-                            if (c < P.C) tv[q][u] = tile_at(stage, g.sub_bytes, 5 + c, ps);
-                        }
-                    }
+                const bool has = (m_lo | m_hi) != 0u;
+                int ps = m_lo ? (__ffs(m_lo) - 1) : (32 + __ffs(m_hi) - 1);
+                if (has) {
+                    if (m_lo) m_lo &= m_lo - 1;
+                    else m_hi &= m_hi - 1;
                     nb = q + 1;
                 }
+                pos[q] = has ? ps : 0;
             }
+            // ... then pull their logits out of the tile in one straight-line block of independent loads
+            // (empty slots read position 0: harmless, and it keeps the block free of branches)
+            uint32_t rr[DEC_BATCH];
+            float tv[DEC_BATCH][DEC_ROUNDS];
+#pragma unroll
+            for (int q = 0; q < DEC_BATCH; ++q) {
+                rr[q] = __shfl_sync(0xffffffffu, pos[q] < 32 ? r_lo : r_hi, pos[q] & 31);
+#pragma unroll
+                for (int u = 0; u < DEC_ROUNDS; ++u) {
+                    const int c = u * 32 + lane;
+                    tv[q][u] = (in_regs && !P.agnostic && c < P.C) ? tile_at(stage, g.sub_bytes, 5 + c, pos[q]) : 0.f;
+                }
+            }
+            const LevelDev& lv = P.lv[lvl];
+            const SegDev& sg = P.seg[lv.seg];
             if (in_regs) {
                 // box / objectness logits: lane group (lane / 8) <-> anchor slot, lane % 8 <-> attribute
                 const int gq = lane >> 3, kq = lane & 7;
                 const int pg0 = gq == 0 ? pos[0] : (gq == 1 ? pos[1] : (gq == 2 ? pos[2] : pos[3]));
                 const float av0 = (kq < 5 && gq < nb) ? tile_at(stage, g.sub_bytes, kq, pg0) : 0.f;
+                YPP_STAMP(blockIdx.x + it * gridDim.x, 7);
                 // last batch and everything is in registers: give the stage back before the math
                 if (!(m_lo | m_hi)) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
                     released = true;
+                    YPP_STAMP(blockIdx.x + it * gridDim.x, 3);
                 }
                 process_batch<MODE, 0>(P, lv, sg, b, a, hw0, nb, pos, rr, av0, tv, lane);
             } else {
@@ -783,7 +812,16 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         if (!released) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            YPP_STAMP(blockIdx.x + it * gridDim.x, 3);
         }
+        YPP_STAMP(blockIdx.x + it * gridDim.x, 4);
+#ifdef YPP_PROFILE
+        if (lane == 0 && blockIdx.x + it * gridDim.x < (1 << 16)) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_prof[(size_t)(blockIdx.x + it * gridDim.x) * 8 + 5] = smid;
+        }
+#endif
     }
 }
 

@@ -21,7 +21,7 @@ MODE_V3 = 1
 OK, E_INVALID, E_WORKSPACE, E_OVERFLOW, E_NO_DEVICE, E_CUDA = 0, 1, 2, 3, 4, 1000
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(PKG_DIR), 'csrc', 'libyolopp.so')
+LIB_PATH = os.environ.get('YOLOPP_LIB') or os.path.join(os.path.dirname(PKG_DIR), 'csrc', 'libyolopp.so')
 
 
 class YoloppParams(ctypes.Structure):
