@@ -1236,6 +1236,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
                         knext[kidx] = atomicExch(&chead[ccl[gj]], kidx);  // push on the class chain (order irrelevant)
                     }
                 }
+                __syncwarp();  // every lane has read s_sup / s_masks before lane 0 resets them
                 if (lane == 0) {
                     s_nk = nk + __popcll(keptm);
                     s_sup = 0ull;

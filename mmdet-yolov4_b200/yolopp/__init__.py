@@ -8,7 +8,7 @@ from . import _capi
 from ._capi import MODE_CSP, MODE_V3, make_params, load_library
 from .ops import get_bboxes_raw, coder_decode, sigmoid, exp
 from .heads import (YOLOCSPHead, YOLOV3Head, YOLOV4BBoxCoder, YOLOBBoxCoder, YOLOAnchorGenerator,
-                    YOLOV4AnchorGenerator, patch_head)
+                    YOLOV4AnchorGenerator, patch_head, bbox2result)
 from .nms import multiclass_nms, batched_nms, nms
 from . import synth
 from . import shard
@@ -16,5 +16,5 @@ from . import shard
 __all__ = [
     'MODE_CSP', 'MODE_V3', 'make_params', 'load_library', 'get_bboxes_raw', 'coder_decode', 'sigmoid', 'exp',
     'YOLOCSPHead', 'YOLOV3Head', 'YOLOV4BBoxCoder', 'YOLOBBoxCoder', 'YOLOAnchorGenerator', 'YOLOV4AnchorGenerator',
-    'patch_head', 'multiclass_nms', 'batched_nms', 'nms', 'synth', 'shard'
+    'patch_head', 'bbox2result', 'multiclass_nms', 'batched_nms', 'nms', 'synth', 'shard'
 ]

@@ -305,3 +305,15 @@ def patch_head(head):
 
     head.get_bboxes = types.MethodType(get_bboxes, head)
     return head
+
+
+def bbox2result(bboxes, labels, num_classes):
+    """mmdet.core.bbox2result (mmdet/core/bbox/transforms.py:99-116): list of `num_classes` arrays (k_c, 5).
+    Accepts the host arrays of `get_results_host` (no further device traffic) or device tensors (one D2H each,
+    like the reference)."""
+    if bboxes.shape[0] == 0:
+        return [np.zeros((0, 5), dtype=np.float32) for _ in range(num_classes)]
+    if isinstance(bboxes, torch.Tensor):
+        bboxes = bboxes.detach().cpu().numpy()
+        labels = labels.detach().cpu().numpy()
+    return [bboxes[labels == i, :] for i in range(num_classes)]

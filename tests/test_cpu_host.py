@@ -156,3 +156,15 @@ def test_two_rank_sharding_with_gloo(tmp_path):
     outs = [pr.communicate(timeout=240)[0] for pr in procs]
     assert all(pr.returncode == 0 for pr in procs), outs
     assert 'SHARD_OK' in outs[0]
+
+
+def test_bbox2result_split():
+    """Same contract as mmdet.core.bbox2result (mmdet/core/bbox/transforms.py:99-116)."""
+    import yolopp
+    dets = np.arange(20, dtype=np.float32).reshape(4, 5)
+    labels = np.array([2, 0, 2, 1], np.int64)
+    out = yolopp.bbox2result(dets, labels, 3)
+    assert [o.shape for o in out] == [(1, 5), (1, 5), (2, 5)]
+    np.testing.assert_array_equal(out[2], dets[[0, 2]])
+    empty = yolopp.bbox2result(np.zeros((0, 5), np.float32), np.zeros((0, ), np.int64), 3)
+    assert [o.shape for o in empty] == [(0, 5)] * 3 and empty[0].dtype == np.float32

@@ -279,3 +279,22 @@ def test_keep_all_overflow_is_reported_not_truncated():
     dets, inds = yolopp.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.5, max_num=4096)
     assert inds.numel() == 4096
     np.testing.assert_array_equal(inds.cpu().numpy(), oracle.nms(boxes, scores, 0.5)[:4096])
+
+
+def test_get_results_host_and_bbox2result():
+    """simple_test's tail (single_stage.py:102-111): one pinned D2H of the detections, then the per-class split."""
+    import yolopp
+    case = cases.CASES['csp608_sparse']
+    p = cases.build_params(case)
+    levels = yolopp.synth.synth_levels(p, case['seed'], case['dist'])
+    head = yolopp.YOLOCSPHead(num_classes=80, test_cfg=cases.ref_cfg(case))
+    metas = [dict(scale_factor=1.0) for _ in range(p.batch)]
+    res = head.get_results_host(levels, metas)
+    orc = oracle.get_bboxes(p, [x.cpu().numpy() for x in levels])
+    for b, (dets, labels) in enumerate(res):
+        np.testing.assert_array_equal(_u32(dets), _u32(orc['dets'][b]))
+        np.testing.assert_array_equal(labels, orc['labels'][b])
+        per_class = yolopp.bbox2result(dets, labels, 80)
+        assert len(per_class) == 80 and sum(len(x) for x in per_class) == len(labels)
+        for c in range(80):
+            np.testing.assert_array_equal(per_class[c], orc['dets'][b][orc['labels'][b] == c])
