@@ -449,6 +449,9 @@ int yolopp_synth_level(float* out, int32_t batch, int32_t num_anchors, int32_t n
 int yolopp_prof_read(long long* host, int n) {
     return (int)cudaMemcpyFromSymbol(host, ypp::g_prof, sizeof(long long) * (size_t)n);
 }
+int yolopp_ssp_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_ssp, sizeof(long long) * 2 * 64 * 4 * 10); }
+int yolopp_ssp2_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_ssp2, sizeof(long long) * 2 * 64 * 4 * 4); }
+int yolopp_phase_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_phase, sizeof(long long) * 2 * 256 * 16); }
 #endif
 
 // ---------------------------------------------------------------------------------------------------

@@ -244,7 +244,18 @@ struct TopSelSmem {
     int kb, above, bsize, count;
     u64 red[2][32];
     SelectSmem rs;  // fallback radix select
+#ifdef YPP_PROFILE
+    int prof_kernel, prof_call;
+#endif
 };
+#ifdef YPP_PROFILE
+// stage timestamps of select_sorted_prefix (profiling build only): [kernel][image][call][stage]
+__device__ long long g_ssp[2][64][4][10];
+__device__ long long g_ssp2[2][64][4][4];  // pass 1 as seen by thread 0: load + test | vote + slots | stash writes | end
+#define YPP_SSP(i) do { if (threadIdx.x == 0 && S.prof_call < 4) g_ssp[S.prof_kernel][blockIdx.x + blockIdx.y][S.prof_call][i] = clock64(); } while (0)
+#else
+#define YPP_SSP(i) do { } while (0)
+#endif
 
 // block-wide min / max of 64-bit values (all threads call; result broadcast)
 __device__ __forceinline__ void block_minmax(u64 vmin, u64 vmax, u64& omin, u64& omax, TopSelSmem& S) {
@@ -307,15 +318,23 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
         shift = hb > 10 ? hb - 10 : 0;
     }
     const u64 base = lo_incl >> shift;
+    YPP_SSP(0);
     for (int i = tid; i < TS_BINS; i += nth) S.hist[i] = 0;
     if (tid == 0) S.count = 0;
     __syncthreads();
-    constexpr int U = 4;  // independent vector loads in flight per thread
-    // Pass 1 — the only trip to global memory in the common case: stream the source, keep the survivors of the
-    // prefilter + exact range test in `out` (the stash). Each thread first marks its own survivors (a short,
-    // atomics-free divergent loop), then ONE warp scan + ONE shared-memory atomic per warp and iteration
-    // hand out the stash slots.
-    static_assert(U * Source::V <= 32, "survivor bitmask");
+    YPP_SSP(1);
+    constexpr int U = Source::U, V = Source::V;  // U independent vector loads in flight per thread
+    static_assert(U * V <= 32 && (V & (V - 1)) == 0, "survivor bitmask");
+    // Pass 1 — the only trip to global memory in the common case: stream the source, keep the eligible keys in
+    // `out` (the stash). The eligibility test is exact and branch-free (Source::exact), survivors are rare: per
+    // batch ONE warp vote, and only when some lane holds a survivor one warp scan + one shared-memory atomic
+    // hand out the stash slots; a survivor's key is rebuilt from its (cached) element.
+#ifdef YPP_PROFILE
+    long long pt[4] = {0, 0, 0, 0}, pt_t = clock64();
+#define YPP_ACC(i) do { long long t2 = clock64(); pt[i] += t2 - pt_t; pt_t = t2; } while (0)
+#else
+#define YPP_ACC(i) do { } while (0)
+#endif
     for (int b0 = 0; b0 < n_groups; b0 += nth * U) {
         Raw raw[U];
 #pragma unroll
@@ -327,40 +346,40 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
 #pragma unroll
         for (int q = 0; q < U; ++q) {
             const int gi = b0 + q * nth + tid;
-            unsigned mk = gi < n_groups ? src.mask(raw[q], gi) : 0u;
-            while (mk) {
-                const int v = __ffs(mk) - 1;
-                mk &= mk - 1;
-                const u64 k = src.key(raw[q], v, gi);
-                if (k >= lo_incl && k <= hi_incl) emask |= 1u << (q * Source::V + v);
-            }
+            if (gi < n_groups) emask |= src.exact(raw[q], gi, lo_incl, hi_incl) << (q * V);
         }
-        const int c = __popc(emask);
-        int incl = c;
+        const bool any = __any_sync(0xffffffffu, emask != 0u);
+        YPP_ACC(0);
+        if (any) {
+            const int c = __popc(emask);
+            int incl = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        const int wtot = __shfl_sync(0xffffffffu, incl, 31);
-        if (wtot) {
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
             int sp = 0;
-            if (lane == 31) sp = atomicAdd(&S.count, wtot);
+            if (lane == 31) sp = atomicAdd(&S.count, incl);
             sp = __shfl_sync(0xffffffffu, sp, 31) + incl - c;
-#pragma unroll
-            for (int q = 0; q < U; ++q) {
-                unsigned mq = (emask >> (q * Source::V)) & ((1u << Source::V) - 1u);
-                const int gi = b0 + q * nth + tid;
-                while (mq) {
-                    const int v = __ffs(mq) - 1;
-                    mq &= mq - 1;
-                    if (sp < cap) out[sp] = src.key(raw[q], v, gi);
-                    ++sp;
-                }
+            YPP_ACC(1);
+            while (emask) {
+                const int pos = __ffs(emask) - 1;
+                emask &= emask - 1;
+                if (sp < cap) out[sp] = src.key_at(b0 + (pos / V) * nth + tid, pos % V);
+                ++sp;
             }
+            __syncwarp();
+            YPP_ACC(2);
         }
     }
+#ifdef YPP_PROFILE
+    if (threadIdx.x == 0 && S.prof_call < 4) {
+        long long* g = g_ssp2[S.prof_kernel][blockIdx.x + blockIdx.y][S.prof_call];
+        g[0] = pt[0]; g[1] = pt[1]; g[2] = pt[2]; g[3] = clock64();
+    }
+#endif
     __syncthreads();
+    YPP_SSP(2);
     const int n_stash = S.count;
     const bool stash_ok = n_stash <= cap;
     if (stash_ok) {
@@ -374,20 +393,22 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
                 const int gi = b0 + q * nth + tid;
                 if (gi < n_groups) raw[q] = src.load(gi);
             }
+            unsigned emask = 0u;
 #pragma unroll
             for (int q = 0; q < U; ++q) {
                 const int gi = b0 + q * nth + tid;
-                unsigned mk = gi < n_groups ? src.mask(raw[q], gi) : 0u;
-                while (mk) {
-                    const int v = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    const u64 k = src.key(raw[q], v, gi);
-                    if (k >= lo_incl && k <= hi_incl) atomicAdd(&S.hist[(int)((k >> shift) - base)], 1);
-                }
+                if (gi < n_groups) emask |= src.exact(raw[q], gi, lo_incl, hi_incl) << (q * V);
+            }
+            while (emask) {
+                const int pos = __ffs(emask) - 1;
+                emask &= emask - 1;
+                const u64 k = src.key_at(b0 + (pos / V) * nth + tid, pos % V);
+                atomicAdd(&S.hist[(int)((k >> shift) - base)], 1);
             }
         }
     }
     __syncthreads();
+    YPP_SSP(3);
     // exclusive scan of the histogram (in place) + pivot bucket: per-thread partial sums -> warp scan -> block scan
     const int per = TS_BINS / nth;  // 2, 4 or 8
     int loc[8], s = 0;
@@ -430,6 +451,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
         }
     }
     __syncthreads();
+    YPP_SSP(4);
     const int kb = S.kb, above = S.above, bsize = S.bsize;
     int cnt;
     if (above + bsize <= cap) {
@@ -450,24 +472,24 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
                     const int gi = b0 + q * nth + tid;
                     if (gi < n_groups) raw[q] = src.load(gi);
                 }
+                unsigned emask = 0u;
 #pragma unroll
                 for (int q = 0; q < U; ++q) {
                     const int gi = b0 + q * nth + tid;
-                    unsigned mk = gi < n_groups ? src.mask(raw[q], gi) : 0u;
-                    while (mk) {
-                        const int v = __ffs(mk) - 1;
-                        mk &= mk - 1;
-                        const u64 k = src.key(raw[q], v, gi);
-                        if (k >= lo_incl && k <= hi_incl) {
-                            const int bk = (int)((k >> shift) - base);
-                            if (bk <= kb) tmp[atomicAdd(&S.hist[bk], 1)] = k;
-                        }
-                    }
+                    if (gi < n_groups) emask |= src.exact(raw[q], gi, lo_incl, hi_incl) << (q * V);
+                }
+                while (emask) {
+                    const int pos = __ffs(emask) - 1;
+                    emask &= emask - 1;
+                    const u64 k = src.key_at(b0 + (pos / V) * nth + tid, pos % V);
+                    const int bk = (int)((k >> shift) - base);
+                    if (bk <= kb) tmp[atomicAdd(&S.hist[bk], 1)] = k;
                 }
             }
         }
         __syncthreads();
-            cnt = above + bsize;
+        YPP_SSP(5);
+        cnt = above + bsize;
         // rank inside the bucket: after the scatter hist[bk] is the END of bucket bk, hist[bk-1] its start
         for (int pos = tid; pos < cnt; pos += nth) {
             const u64 key = tmp[pos];
@@ -482,11 +504,11 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
         // slow, exact path: element-wise view of the source
         const bool has_lo = lo_incl > 0;
         auto f1 = [&](int i, u64& key) -> bool {
-            const int gi = i / Source::V, v = i % Source::V;
+            const int gi = i / V, v = i % V;
             const Raw r = src.load(gi);
-            if (!((src.mask(r, gi) >> v) & 1u)) return false;
-            key = src.key(r, v, gi);
-            return key <= hi_incl;
+            if (!((src.exact(r, gi, lo_incl, hi_incl) >> v) & 1u)) return false;
+            key = src.key_at(gi, v);
+            return true;
         };
         u64 T = radix_select(f1, n_groups * Source::V, has_lo, lo_incl - 1, m, S.rs);
         cnt = gather_le(f1, n_groups * Source::V, has_lo, lo_incl - 1, T, out, cap, S.rs);
@@ -495,6 +517,17 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
         __syncthreads();
         bitonic_sort(out, p2);
     }
+    YPP_SSP(6);
+#ifdef YPP_PROFILE
+    if (threadIdx.x == 0) {
+        if (S.prof_call < 4) {
+            g_ssp[S.prof_kernel][blockIdx.x + blockIdx.y][S.prof_call][7] = n_stash;
+            g_ssp[S.prof_kernel][blockIdx.x + blockIdx.y][S.prof_call][8] = cnt;
+            g_ssp[S.prof_kernel][blockIdx.x + blockIdx.y][S.prof_call][9] = n_groups;
+        }
+        ++S.prof_call;
+    }
+#endif
     return cnt;
 }
 

@@ -64,6 +64,14 @@ struct SegDev {
     int m_begin, m_end;  // plane-major index range of the segment
 };
 
+#ifdef YPP_PROFILE
+// per-CTA phase timestamps of the per-image kernels (profiling build only): [kernel][image][phase]
+__device__ long long g_phase[2][256][16];
+#define YPP_PHASE(k, blk, i) do { if (threadIdx.x == 0 && (blk) < 256) g_phase[k][blk][i] = clock64(); } while (0)
+#else
+#define YPP_PHASE(k, blk, i) do { } while (0)
+#endif
+
 struct DevParams {
     int mode, B, L, A, C, NA, agnostic;  // C = effective classes (1 when class agnostic)
     int nsegs, ntopk;
@@ -103,39 +111,72 @@ struct DevParams {
 };
 
 // ---- key sources of the bucket select (see select_sorted_prefix) --------------------------------------------
-// objectness keys of a top-k segment, two per 16-byte load; keys above `hi` (incl. the ~0 padding) are masked
+// objectness keys of a top-k segment, two per 16-byte load (the ~0 alignment padding is above every `hi`)
 struct CkeySource {
     typedef ulonglong2 Raw;
-    static constexpr int V = 2;
+    static constexpr int V = 2, U = 4;
     const ulonglong2* p;
     int n;
-    u64 hi;
     __device__ __forceinline__ Raw load(int g) const { return p[g]; }
-    __device__ __forceinline__ unsigned mask(const Raw& r, int) const { return (r.x <= hi ? 1u : 0u) | (r.y <= hi ? 2u : 0u); }
-    __device__ __forceinline__ u64 key(const Raw& r, int v, int) const { return v ? r.y : r.x; }
+    __device__ __forceinline__ unsigned exact(const Raw& r, int, u64 lo, u64 hi) const {
+        return ((r.x >= lo && r.x <= hi) ? 1u : 0u) | ((r.y >= lo && r.y <= hi) ? 2u : 0u);
+    }
+    __device__ __forceinline__ u64 key_at(int g, int v) const { return reinterpret_cast<const u64*>(p)[2 * g + v]; }
     __device__ __forceinline__ int groups() const { return n; }
 };
 // every `stride`-th objectness key (pivot sample)
 struct CkeySampleSource {
     typedef u64 Raw;
-    static constexpr int V = 1;
+    static constexpr int V = 1, U = 4;
     const u64* p;
     int n, stride;
     __device__ __forceinline__ Raw load(int g) const { return p[(size_t)g * stride]; }
-    __device__ __forceinline__ unsigned mask(const Raw& r, int) const { return r != ~0ull ? 1u : 0u; }
-    __device__ __forceinline__ u64 key(const Raw& r, int, int) const { return r; }
+    __device__ __forceinline__ unsigned exact(const Raw& r, int, u64 lo, u64 hi) const { return (r >= lo && r <= hi) ? 1u : 0u; }
+    __device__ __forceinline__ u64 key_at(int g, int) const { return p[(size_t)g * stride]; }
     __device__ __forceinline__ int groups() const { return n; }
 };
-// score matrix of one image, four entries per 16-byte load. Scores are non-negative floats, so their bit
-// patterns order like the values: the window [lo, lo+span] on the raw word rejects almost every entry with one
-// subtract + compare (SCORE_NONE = 0xFFFFFFFF is above every window).
+// Window test shared by the two score-matrix sources. Scores are non-negative floats (bit patterns order like the
+// values), key = ((0x7FFFFFFF - bits) << 32) | flat, so lo <= key <= hi is a window on the raw word plus a flat
+// index test on its two end values; SCORE_NONE = 0xFFFFFFFF is above every window. Branch-free: the hot loop of
+// the candidate scan is "load, subtract, compare".
+struct ScoreWindow {
+    uint32_t worst, span, best;  // raw-word window [worst, worst + span], best = worst + span
+    uint32_t lo_flat, hi_flat;   // flat bounds that apply at word == best / word == worst
+    bool ends;                   // some flat bound is not trivial
+    __device__ __forceinline__ void set(u64 lo, u64 hi) {
+        best = (~(uint32_t)(lo >> 32)) & 0x7FFFFFFFu;
+        worst = (~(uint32_t)(hi >> 32)) & 0x7FFFFFFFu;
+        span = best - worst;
+        lo_flat = (uint32_t)lo;
+        hi_flat = (uint32_t)hi;
+        ends = lo_flat != 0u || hi_flat != 0xFFFFFFFFu;
+    }
+    __device__ __forceinline__ unsigned test4(const uint4& w, uint32_t flat0) const {
+        unsigned mk = (w.x - worst <= span ? 1u : 0u) | (w.y - worst <= span ? 2u : 0u) | (w.z - worst <= span ? 4u : 0u) |
+                      (w.w - worst <= span ? 8u : 0u);
+        if (ends) {
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const bool out = (ws[v] == best && flat0 + v < lo_flat) || (ws[v] == worst && flat0 + v > hi_flat);
+                mk &= out ? ~(1u << v) : ~0u;
+            }
+        }
+        return mk;
+    }
+};
+__device__ __forceinline__ u64 score_key(uint32_t bits, uint32_t flat) {
+    return ((u64)((~bits) & 0x7FFFFFFFu) << 32) | (u64)flat;  // == make_key for a non-negative score
+}
+// score matrix of one image, four entries per 16-byte load. `windowed` = scores are known non-negative (the
+// pipeline's own matrix); the standalone NMS entries accept any float and build the 64-bit key per element.
 struct MatSource {
     typedef uint4 Raw;
-    static constexpr int V = 4;
+    static constexpr int V = 4, U = 4;
     const uint32_t* m;
     int slots;
-    bool vec4;
-    uint32_t lo, span;
+    bool vec4, windowed;
+    ScoreWindow win;
     __device__ __forceinline__ Raw load(int g) const {
         if (vec4) return reinterpret_cast<const uint4*>(m)[g];
         uint4 r;
@@ -145,73 +186,85 @@ struct MatSource {
         r.w = (g * 4 + 3 < slots) ? m[g * 4 + 3] : SCORE_NONE;
         return r;
     }
-    __device__ __forceinline__ unsigned mask(const Raw& r, int) const {
-        return (r.x - lo <= span ? 1u : 0u) | (r.y - lo <= span ? 2u : 0u) | (r.z - lo <= span ? 4u : 0u) |
-               (r.w - lo <= span ? 8u : 0u);
+    __device__ __forceinline__ unsigned exact(const Raw& r, int g, u64 lo, u64 hi) const {
+        if (windowed) return win.test4(r, (uint32_t)(g * 4));
+        const uint32_t ws[4] = {r.x, r.y, r.z, r.w};
+        unsigned mk = 0u;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            if (ws[v] != SCORE_NONE) {
+                const u64 k = make_key(__uint_as_float(ws[v]), (uint32_t)(g * 4 + v));
+                mk |= (k >= lo && k <= hi) ? (1u << v) : 0u;
+            }
+        }
+        return mk;
     }
-    __device__ __forceinline__ u64 key(const Raw& r, int v, int g) const {
-        const uint32_t sb = v == 0 ? r.x : (v == 1 ? r.y : (v == 2 ? r.z : r.w));
-        return make_key(__uint_as_float(sb), (uint32_t)(g * 4 + v));
+    __device__ __forceinline__ u64 key_at(int g, int v) const {
+        const uint32_t flat = (uint32_t)(g * 4 + v);
+        return make_key(__uint_as_float(m[flat]), flat);
     }
     __device__ __forceinline__ int groups() const { return (slots + 3) / 4; }
 };
 // score-matrix entries of a LIST of rows (the rows whose best score can still matter), four per 16-byte load.
-// The flat index of the group's first entry travels with the raw words, so building a survivor's key costs a
-// handful of instructions (no division on the divergent path).
-struct RowListRaw {
-    uint4 v;
-    uint32_t flat0;
-};
 struct RowListSource {
-    typedef RowListRaw Raw;
-    static constexpr int V = 4;
+    typedef uint4 Raw;
+    static constexpr int V = 4, U = 4;
     const uint32_t* m;   // score matrix of the image
     const u64* rows;     // low word = row index
     int nrows, C;
     int nsub;            // 32-group (= 128-class) slabs per row: group g -> slab g >> 5, chunk g & 31
     bool vec4;           // C % 4 == 0: rows are 16-byte aligned
-    uint32_t lo, span;
-    // a warp's 32 consecutive groups are the 32 chunks of ONE slab of one row: no division on the load path
-    __device__ __forceinline__ Raw load(int g) const {
+    ScoreWindow win;
+    // flat index of the group's first entry; a warp's 32 consecutive groups are the 32 chunks of ONE slab of one
+    // row (no division on the load path); chunks past the row's end report C (nothing to load)
+    __device__ __forceinline__ uint32_t flat0(int g, int& cls0) const {
         const int slab = g >> 5, jl = g & 31;
         const int i = nsub == 1 ? slab : slab / nsub;
         const int j = nsub == 1 ? jl : (slab - i * nsub) * 32 + jl;
-        Raw r;
-        r.flat0 = (uint32_t)rows[i] * (uint32_t)C + (uint32_t)(4 * j);
-        r.v = make_uint4(SCORE_NONE, SCORE_NONE, SCORE_NONE, SCORE_NONE);
-        if (4 * j < C) {
-            const uint32_t* p = m + r.flat0;
+        cls0 = 4 * j;
+        return (uint32_t)rows[i] * (uint32_t)C + (uint32_t)(4 * j);
+    }
+    __device__ __forceinline__ Raw load(int g) const {
+        int c0;
+        const uint32_t f0 = flat0(g, c0);
+        Raw r = make_uint4(SCORE_NONE, SCORE_NONE, SCORE_NONE, SCORE_NONE);
+        if (c0 < C) {
+            const uint32_t* p = m + f0;
             if (vec4) {
-                r.v = *reinterpret_cast<const uint4*>(p);
+                r = *reinterpret_cast<const uint4*>(p);
             } else {
-                r.v.x = p[0];
-                r.v.y = (4 * j + 1 < C) ? p[1] : SCORE_NONE;
-                r.v.z = (4 * j + 2 < C) ? p[2] : SCORE_NONE;
-                r.v.w = (4 * j + 3 < C) ? p[3] : SCORE_NONE;
+                r.x = p[0];
+                r.y = (c0 + 1 < C) ? p[1] : SCORE_NONE;
+                r.z = (c0 + 2 < C) ? p[2] : SCORE_NONE;
+                r.w = (c0 + 3 < C) ? p[3] : SCORE_NONE;
             }
         }
         return r;
     }
-    __device__ __forceinline__ unsigned mask(const Raw& r, int) const {
-        return (r.v.x - lo <= span ? 1u : 0u) | (r.v.y - lo <= span ? 2u : 0u) | (r.v.z - lo <= span ? 4u : 0u) |
-               (r.v.w - lo <= span ? 8u : 0u);
+    __device__ __forceinline__ unsigned exact(const Raw& r, int g, u64, u64) const {
+        int c0;
+        const uint32_t f0 = win.ends ? flat0(g, c0) : 0u;
+        return win.test4(r, f0);
     }
-    __device__ __forceinline__ u64 key(const Raw& r, int v, int) const {
-        const uint32_t sb = v == 0 ? r.v.x : (v == 1 ? r.v.y : (v == 2 ? r.v.z : r.v.w));
-        // scores are non-negative: ~ord(score) == ~bits & 0x7FFFFFFF
-        return ((u64)((~sb) & 0x7FFFFFFFu) << 32) | (u64)(r.flat0 + (uint32_t)v);
+    __device__ __forceinline__ u64 key_at(int g, int v) const {
+        int c0;
+        const uint32_t flat = flat0(g, c0) + (uint32_t)v;
+        return score_key(m[flat], flat);
     }
     __device__ __forceinline__ int groups() const { return nrows * nsub * 32; }
 };
 // best score of every row that owns a candidate (row_stat.x), key = (~ord(best) << 32) | row
 struct RowBestSource {
     typedef uint4 Raw;
-    static constexpr int V = 1;
+    static constexpr int V = 1, U = 4;
     const uint4* rs;
     int R;
     __device__ __forceinline__ Raw load(int g) const { return rs[g]; }
-    __device__ __forceinline__ unsigned mask(const Raw& r, int) const { return r.z ? 1u : 0u; }
-    __device__ __forceinline__ u64 key(const Raw& r, int, int g) const { return ((u64)(~r.x) << 32) | (u64)(uint32_t)g; }
+    __device__ __forceinline__ unsigned exact(const Raw& r, int g, u64 lo, u64 hi) const {
+        const u64 k = ((u64)(~r.x) << 32) | (u64)(uint32_t)g;
+        return (r.z && k >= lo && k <= hi) ? 1u : 0u;
+    }
+    __device__ __forceinline__ u64 key_at(int g, int) const { return ((u64)(~rs[g].x) << 32) | (u64)(uint32_t)g; }
     __device__ __forceinline__ int groups() const { return R; }
 };
 
@@ -230,6 +283,10 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     u64* ckey = P.ckey + (size_t)b * P.M_pad;
     uint32_t* rank = P.rank + (size_t)b * P.M_pad;
 
+    YPP_PHASE(0, b, 0);
+#ifdef YPP_PROFILE
+    if (threadIdx.x == 0) { S.prof_kernel = 0; S.prof_call = 0; }
+#endif
     // pass 0: objectness of every anchor of the segment -> composite key; rank map cleared; key range.
     // Loads are issued in batches of 8 per thread so that one DRAM round trip covers 8 anchors.
     u64 kmin = ~0ull, kmax = 0ull;
@@ -267,12 +324,13 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     }
     u64 gmin, gmax;
     block_minmax(kmin, kmax, gmin, gmax, S);  // also orders the global writes above (block barrier)
+    YPP_PHASE(0, b, 1);
 
     // keys are fetched two at a time (16-byte loads); m_begin is 4-aligned, an odd tail reads one padding key (~0)
     CkeySource src;
     src.p = reinterpret_cast<const ulonglong2*>(ckey + sg.m_begin);
     src.n = (sg.m_end - sg.m_begin + 1) / 2;
-    src.hi = gmax;
+    u64 hi_sel = gmax;
     // Pivot from a 1-in-16 sample: the objectness distribution is extremely skewed (most anchors share a few
     // histogram buckets), so the exact select only looks at keys up to ~1.5x the expected k-th key. If the
     // sample pivot turns out too tight (cnt < k) the select is redone over the whole range.
@@ -284,14 +342,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
         const int ks = (sg.k * 3 + 31) / 32 + 16;  // 1.5 * k / 16 + slack
         if (ss.n >= 4 * ks && ks <= P.sel_kcap) {
             const int gs = select_sorted_prefix(ss, gmin, gmax, ks, sel, sel + P.sel_kcap, P.sel_kcap, S);
-            if (gs >= ks) src.hi = sel[ks - 1];
+            if (gs >= ks) hi_sel = sel[ks - 1];
             __syncthreads();
         }
     }
-    int cnt = select_sorted_prefix(src, gmin, src.hi, sg.k, sel, sel + P.sel_kcap, P.sel_kcap, S);
-    if (cnt < sg.k && src.hi != gmax) {
+    YPP_PHASE(0, b, 2);
+    int cnt = select_sorted_prefix(src, gmin, hi_sel, sg.k, sel, sel + P.sel_kcap, P.sel_kcap, S);
+    YPP_PHASE(0, b, 3);
+    if (cnt < sg.k && hi_sel != gmax) {
         __syncthreads();
-        src.hi = gmax;
         cnt = select_sorted_prefix(src, gmin, gmax, sg.k, sel, sel + P.sel_kcap, P.sel_kcap, S);
     }
     const int k = cnt < sg.k ? cnt : sg.k;
@@ -310,6 +369,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
         rank[lv.m_off + a * lv.HW + hw] = (uint32_t)(sg.row_off + i);
         P.row_anchor[(size_t)b * P.R + sg.row_off + i] = n;
     }
+    YPP_PHASE(0, b, 4);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -585,6 +645,9 @@ __device__ long long g_prof[(1 << 16) * 8];
 #define YPP_STAMP(t, i) do { } while (0)
 #endif
 
+// Tile of a CTA's iteration `it` (round-robin over the CTAs: neighbouring tiles are in flight at the same time).
+__device__ __forceinline__ long long dec_tile_of(int it) { return blockIdx.x + (long long)it * gridDim.x; }
+
 template <int MODE>
 __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid_constant__ DevParams P,
                                                                   const __grid_constant__ TmapPack maps) {
@@ -615,10 +678,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
     if (warp < DEC_PWARPS) {
         // ---------------- producers: warp p owns the iterations it == p (mod DEC_PWARPS), i.e. stages p, p+2 ----------------
         static_assert(DEC_STAGES % DEC_PWARPS == 0, "a stage must belong to one producer warp");
-        const uint64_t pol = l2_policy_evict_first();
-        for (int k0 = 0; blockIdx.x + (long long)(k0 * DEC_PWARPS + warp) * gridDim.x < total; k0 += 32) {
+        for (int k0 = 0; dec_tile_of(k0 * DEC_PWARPS + warp) < total; k0 += 32) {
             // lane j: coordinates of this warp's iteration number k0 + j
-            const long long tl = blockIdx.x + (long long)((k0 + lane) * DEC_PWARPS + warp) * gridDim.x;
+            const long long tl = dec_tile_of((k0 + lane) * DEC_PWARPS + warp);
             int d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0, d_hw = 0, d_rbase = 0, d_topk = 0;
             if (tl < total) {
                 const int t = (int)tl;
@@ -641,7 +703,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             }
             for (int j = 0; j < 32; ++j) {
                 const int it = (k0 + j) * DEC_PWARPS + warp;
-                if (blockIdx.x + (long long)it * gridDim.x >= total) break;
+                if (dec_tile_of(it) >= total) break;
                 const int l = __shfl_sync(0xffffffffu, d_l, j), plane = __shfl_sync(0xffffffffu, d_plane, j);
                 const int hw0 = __shfl_sync(0xffffffffu, d_hw0, j), bb = __shfl_sync(0xffffffffu, d_b, j);
                 const int a = __shfl_sync(0xffffffffu, d_a, j);
@@ -650,9 +712,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                 if (lane == 0) {
                     const int s = it % DEC_STAGES;
                     const uint32_t ph = (uint32_t)(it / DEC_STAGES) & 1u;
-                    YPP_STAMP(blockIdx.x + it * gridDim.x, 0);
+                    YPP_STAMP(dec_tile_of(it), 0);
                     mbar_wait(&empty[s], ph ^ 1u);
-                    YPP_STAMP(blockIdx.x + it * gridDim.x, 1);
+                    YPP_STAMP(dec_tile_of(it), 1);
                     const LevelDev& lv = P.lv[l];
                     unsigned char* dst = stages + (size_t)s * g.stage_bytes;
                     // descriptor first (it carries the iteration number the consumer matches and everything the
@@ -666,8 +728,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                         const bool topk = tk != 0;
                         const bool two = hw0 + TILE_SUB < hwn;  // the second box is not entirely out of bounds
                         mbar_arrive_expect_tx(fb, box_bytes * (two ? 2u : 1u) + (topk ? TILE_T * 4u : 0u));
-                        tma_load_2d_hint(dst, &maps.m[l], hw0, plane * NA, fb, pol);
-                        if (two) tma_load_2d_hint(dst + g.sub_bytes, &maps.m[l], hw0 + TILE_SUB, plane * NA, fb, pol);
+                        // No L2 eviction hint on purpose: plane rows are in general not 128-byte aligned, so
+                        // neighbouring tiles share the lines at their common edge; with evict_first the second
+                        // tile re-fetched them from DRAM (measured: 635 MB read per launch instead of 512 MB).
+                        tma_load_2d(dst, &maps.m[l], hw0, plane * NA, fb);
+                        if (two) tma_load_2d(dst + g.sub_bytes, &maps.m[l], hw0 + TILE_SUB, plane * NA, fb);
                         if (topk)
                             bulk_load_1d(dst + g.rank_off, P.rank + (size_t)bb * P.M_pad + lv.m_off + a * lv.HW + hw0,
                                          TILE_T * 4u, fb);
@@ -690,7 +755,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         int it = 0;
         if (lane == 0) it = atomicAdd(next_it, 1);
         it = __shfl_sync(0xffffffffu, it, 0);
-        if (blockIdx.x + (long long)it * gridDim.x >= total) break;
+        if (dec_tile_of(it) >= total) break;
         const int s = it % DEC_STAGES;
         const unsigned char* stage = stages + (size_t)s * g.stage_bytes;
         {
@@ -698,7 +763,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             while (*dit != it) __nanosleep(YPP_SLEEP);
         }
         mbar_wait(&full[s], (uint32_t)(it / DEC_STAGES) & 1u);
-        YPP_STAMP(blockIdx.x + it * gridDim.x, 2);
+        YPP_STAMP(dec_tile_of(it), 2);
         const int4 desc = *reinterpret_cast<const int4*>(stage + g.desc_off);
         const int4 desc2 = *reinterpret_cast<const int4*>(stage + g.desc_off + 16);
         const int b = desc.y, a = desc.x >> 8, hw0 = desc.z;
@@ -743,13 +808,13 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         }
         uint32_t m_lo = __ballot_sync(0xffffffffu, r_lo != RANK_INVALID);
         uint32_t m_hi = __ballot_sync(0xffffffffu, r_hi != RANK_INVALID);
-        YPP_STAMP(blockIdx.x + it * gridDim.x, 6);
+        YPP_STAMP(dec_tile_of(it), 6);
         bool released = false;
         if (!(m_lo | m_hi)) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             released = true;
-            YPP_STAMP(blockIdx.x + it * gridDim.x, 3);
+            YPP_STAMP(dec_tile_of(it), 3);
         }
         while (m_lo | m_hi) {
             // pick up to DEC_BATCH admitted positions (uniform scalar work) ...
@@ -786,13 +851,13 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                 const int gq = lane >> 3, kq = lane & 7;
                 const int pg0 = gq == 0 ? pos[0] : (gq == 1 ? pos[1] : (gq == 2 ? pos[2] : pos[3]));
                 const float av0 = (kq < 5 && gq < nb) ? tile_at(stage, g.sub_bytes, kq, pg0) : 0.f;
-                YPP_STAMP(blockIdx.x + it * gridDim.x, 7);
+                YPP_STAMP(dec_tile_of(it), 7);
                 // last batch and everything is in registers: give the stage back before the math
                 if (!(m_lo | m_hi)) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
                     released = true;
-                    YPP_STAMP(blockIdx.x + it * gridDim.x, 3);
+                    YPP_STAMP(dec_tile_of(it), 3);
                 }
                 process_batch<MODE, 0>(P, lv, sg, b, a, hw0, nb, pos, rr, av0, tv, lane);
             } else {
@@ -812,14 +877,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         if (!released) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
-            YPP_STAMP(blockIdx.x + it * gridDim.x, 3);
+            YPP_STAMP(dec_tile_of(it), 3);
         }
-        YPP_STAMP(blockIdx.x + it * gridDim.x, 4);
+        YPP_STAMP(dec_tile_of(it), 4);
 #ifdef YPP_PROFILE
-        if (lane == 0 && blockIdx.x + it * gridDim.x < (1 << 16)) {
+        if (lane == 0 && dec_tile_of(it) < (1 << 16)) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            g_prof[(size_t)(blockIdx.x + it * gridDim.x) * 8 + 5] = smid;
+            g_prof[(size_t)dec_tile_of(it) * 8 + 5] = smid;
         }
 #endif
     }
@@ -966,6 +1031,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
 
     // candidate count, score range and boxes.max() of the image: reduction over the per-row statistics that the
     // decode kernels stored
+    YPP_PHASE(1, b, 0);
+#ifdef YPP_PROFILE
+    if (threadIdx.x == 0) { S.prof_kernel = 1; S.prof_call = 0; }
+#endif
     if (tid == 0) {
         s_nk = 0;
         s_sup = 0ull;
@@ -1013,6 +1082,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         }
     }
     __syncthreads();
+    YPP_PHASE(1, b, 1);
     const int ntot = (int)s_red[3];
     if (tid == 0 && P.o_ncand) P.o_ncand[b] = ntot;
     if (ntot == 0) {
@@ -1032,8 +1102,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     msrc.m = mat;
     msrc.slots = slots;
     msrc.vec4 = ((slots & 3) == 0);
-    msrc.lo = 0u;
-    msrc.span = 0xFFFFFFFEu;
+    const bool nonneg = s_red[1] <= 0x7FFFFFFFu;  // every candidate score is >= +0: raw words order like the keys
+    msrc.windowed = nonneg;  // (the standalone entries accept scores of any sign: exact 64-bit test per element)
 
     int processed = 0;
     u64 lo = gmin;
@@ -1054,21 +1124,18 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     // the first chunk only needs a little more than `cap` candidates; later chunks (heavy suppression) are full
     int chunk = cap + (cap >> 2) + 64;
     chunk = chunk < NMS_CH ? chunk : NMS_CH;
+    YPP_PHASE(1, b, 2);
+#ifdef YPP_PROFILE
+    int prof_chunks = 0, prof_groups = 0;
+    long long prof_ab1 = 0, prof_b2 = 0;
+#endif
     while (processed < ntot && s_nk < cap) {
         const int want = min(chunk, ntot - processed);
         chunk = NMS_CH;
         const int wc = processed + want;  // cumulative rank this chunk must reach
         const u64 hi = wc <= nrows_sorted ? (rowkeys[wc - 1] | 0xFFFFFFFFull) : gmax;
-        {
-            // key high word = ~ord(score); for a non-negative score ord = bits | 0x80000000
-            const uint32_t best_bits = (~(uint32_t)(lo >> 32)) & 0x7FFFFFFFu, worst_bits = (~(uint32_t)(hi >> 32)) & 0x7FFFFFFFu;
-            if (!generic) {  // (arbitrary-sign scores keep the full window; the exact 64-bit test still applies)
-                msrc.lo = worst_bits;
-                msrc.span = best_bits - worst_bits;
-            }
-        }
         int got;
-        if (wc <= nrows_sorted) {
+        if (wc <= nrows_sorted && nonneg) {
             // only the wc best rows can hold one of the wc best candidates: scan just their matrix rows
             RowListSource rl;
             rl.m = mat;
@@ -1077,13 +1144,17 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
             rl.C = C;
             rl.nsub = (C + 127) / 128;
             rl.vec4 = ((C & 3) == 0);
-            rl.lo = msrc.lo;
-            rl.span = msrc.span;
+            rl.win.set(lo, hi);
             got = select_sorted_prefix(rl, lo, hi, want, keys, ktmp, NMS_KCAP, S);
         } else {
+            msrc.win.set(lo, hi);
             got = select_sorted_prefix(msrc, lo, hi, want, keys, ktmp, NMS_KCAP, S);
         }
         const int m = got < NMS_CH ? got : NMS_CH;  // boxes staged this round (a prefix of the sorted order)
+#ifdef YPP_PROFILE
+        if (prof_chunks == 0) YPP_PHASE(1, b, 3);
+        ++prof_chunks;
+#endif
         if (m == 0) break;
         for (int i = tid; i < m; i += NMS_THREADS) {
             const uint32_t flat = key_flat(keys[i]);
@@ -1106,9 +1177,16 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
             ccl[i] = c;
         }
         __syncthreads();
+#ifdef YPP_PROFILE
+        if (prof_chunks == 1) YPP_PHASE(1, b, 4);
+#endif
         for (int s0 = 0; s0 < m; s0 += NMS_G) {
             const int nk = s_nk;
             if (nk >= cap) break;
+#ifdef YPP_PROFILE
+            ++prof_groups;
+            long long pg_t0 = clock64();
+#endif
             // ---- phase A: the group's 64 candidates against the kept list
             if (per_class) {
                 // classes are independent: walk the chain of kept boxes of the candidate's own class (a handful)
@@ -1192,6 +1270,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
                 if (lane == 0) s_masks[i] = row;
             }
             __syncthreads();
+#ifdef YPP_PROFILE
+            long long pg_t1 = clock64();
+            prof_ab1 += pg_t1 - pg_t0;
+#endif
             // ---- phase B2: greedy scan over the group (warp 0): bit operations only
             if (warp == 0) {
                 const int gcount = min(NMS_G, m - s0);
@@ -1199,25 +1281,20 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
                 u64 alive = validm & ~s_sup;
                 const u64 ma = s_masks[lane], mb = s_masks[lane + 32];
                 const int room = cap - nk;
-                // the shuffle sources are compile-time constants, so all 128 shuffles are in flight at once and the
-                // serial chain is two bit operations per candidate
-                u64 keptm = 0ull;
-                const unsigned ma_lo = (unsigned)ma, ma_hi = (unsigned)(ma >> 32);
-                const unsigned mb_lo = (unsigned)mb, mb_hi = (unsigned)(mb >> 32);
-#pragma unroll 8
-                for (int i = 0; i < 32; ++i) {
-                    const unsigned lo32 = __shfl_sync(0xffffffffu, ma_lo, i), hi32 = __shfl_sync(0xffffffffu, ma_hi, i);
-                    const bool kp = (alive >> i) & 1ull;
-                    keptm |= kp ? (1ull << i) : 0ull;
-                    alive &= kp ? ~(((u64)hi32 << 32) | (u64)lo32) : ~0ull;
+                // Only a row that is alive and whose mask meets an alive candidate can change anything, and `alive`
+                // only shrinks: visit just those rows, in order. A candidate still alive at the end is kept.
+                u64 nz = ((u64)__ballot_sync(0xffffffffu, (mb & alive) != 0ull) << 32) |
+                         (u64)__ballot_sync(0xffffffffu, (ma & alive) != 0ull);
+                nz &= alive;
+                while (nz) {
+                    const int i = __ffsll((long long)nz) - 1;
+                    nz &= nz - 1ull;
+                    const u64 mrow = i < 32 ? ma : mb;
+                    const unsigned lo32 = __shfl_sync(0xffffffffu, (unsigned)mrow, i & 31);
+                    const unsigned hi32 = __shfl_sync(0xffffffffu, (unsigned)(mrow >> 32), i & 31);
+                    if ((alive >> i) & 1ull) alive &= ~(((u64)hi32 << 32) | (u64)lo32);
                 }
-#pragma unroll 8
-                for (int i = 0; i < 32; ++i) {
-                    const unsigned lo32 = __shfl_sync(0xffffffffu, mb_lo, i), hi32 = __shfl_sync(0xffffffffu, mb_hi, i);
-                    const bool kp = (alive >> (i + 32)) & 1ull;
-                    keptm |= kp ? (1ull << (i + 32)) : 0ull;
-                    alive &= kp ? ~(((u64)hi32 << 32) | (u64)lo32) : ~0ull;
-                }
+                u64 keptm = alive;
                 // only the first `room` kept boxes can enter the first `cap` kept (later ones never affect earlier)
                 for (int kc = __popcll(keptm); kc > room; --kc) keptm &= ~(1ull << (63 - __clzll((long long)keptm)));
 #pragma unroll
@@ -1243,11 +1320,24 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
                 }
             }
             __syncthreads();
+#ifdef YPP_PROFILE
+            prof_b2 += clock64() - pg_t1;
+#endif
         }
         processed += m;
         lo = keys[m - 1] + 1ull;
         __syncthreads();
     }
+    YPP_PHASE(1, b, 5);
+#ifdef YPP_PROFILE
+    if (tid == 0 && b < 256) {
+        g_phase[1][b][7] = prof_chunks;
+        g_phase[1][b][8] = prof_groups;
+        g_phase[1][b][9] = ntot;
+        g_phase[1][b][10] = prof_ab1;
+        g_phase[1][b][11] = prof_b2;
+    }
+#endif
     // outputs: dets = (boxes[keep], scores[keep]), labels[keep]  (bbox_nms.py:84-93)
     int nk = s_nk;
     // "keep all" (no max_num) but the kept list is full while candidates remain: report, do not truncate silently
@@ -1274,6 +1364,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         if (P.o_rows) P.o_rows[(size_t)b * P.out_cap + i] = r;
     }
     if (tid == 0) P.o_count[b] = nk;
+    YPP_PHASE(1, b, 6);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@ Ranks source lines by warp-stall samples and prints the dominant stall reasons p
 import csv, sys, subprocess, collections, re, os, tempfile, glob
 rep, kname = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+sort_key = sys.argv[4] if len(sys.argv) > 4 else 'samples'   # 'samples' or 'inst'
 lib = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..', 'mmdet-yolov4_b200', 'csrc', 'libyolopp.so')
 tmp = tempfile.mkdtemp()
 subprocess.run(['cuobjdump', '-xelf', 'all', os.path.abspath(lib)], cwd=tmp, capture_output=True)
@@ -48,7 +49,7 @@ def srcline(f, n):
         srcfiles[f] = open(p).read().splitlines() if os.path.isfile(p) else []
     L = srcfiles[f]
     return L[n - 1].strip()[:110] if 0 < n <= len(L) else ''
-print('total samples', tot)
-for (f, n), a in sorted(agg.items(), key=lambda kv: -kv[1]['samples'])[:top]:
+print('total samples', tot, ' total warp instructions', sum(a['inst'] for a in agg.values()))
+for (f, n), a in sorted(agg.items(), key=lambda kv: -kv[1][sort_key])[:top]:
     st = sorted(((a[s], s[6:]) for s in stall_cols if a[s] > 0), reverse=True)[:3]
     print(f"{a['samples']:8.0f} {100*a['samples']/max(tot,1):5.1f}% inst={a['inst']:10.0f} {f}:{n:<4d} {srcline(f,n)}   [{', '.join(f'{n2}:{v:.0f}' for v,n2 in st)}]")

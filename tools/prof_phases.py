@@ -1,0 +1,61 @@
+"""Phase timeline of the per-image kernels (profiling build tools/libyolopp_prof.so, -DYPP_PROFILE)."""
+import sys, ctypes
+sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import numpy as np, torch, cases
+from yolopp import _capi
+_capi.LIB_PATH = '/root/repo/tools/libyolopp_prof.so'
+import yolopp
+from yolopp.ops import Session
+lib = _capi.load_library()
+case = dict(cases.CASES['csp608_sparse'], batch=64)
+p = cases.build_params(case)
+levels = yolopp.synth.synth_levels(p, 11, 'sparse')
+s = Session(p)
+for _ in range(4): s.run(levels)
+torch.cuda.synchronize()
+buf = np.zeros((2, 256, 16), np.int64)
+lib.yolopp_phase_read.argtypes = [ctypes.c_void_p]
+lib.yolopp_phase_read(buf.ctypes.data_as(ctypes.c_void_p))
+B = 64
+sel = buf[0, :B]; nms = buf[1, :B]
+def stats(name, d):
+    print('  %-34s median %7.0f  p10 %7.0f  p90 %7.0f  max %7.0f' % (name, np.median(d), np.percentile(d, 10), np.percentile(d, 90), d.max()))
+print('select_kernel (cycles)')
+stats('pass0 keys + minmax', sel[:, 1] - sel[:, 0])
+stats('sample select', sel[:, 2] - sel[:, 1])
+stats('main select', sel[:, 3] - sel[:, 2])
+stats('retry + rank scatter', sel[:, 4] - sel[:, 3])
+stats('total', sel[:, 4] - sel[:, 0])
+print('  kernel span', sel[:, 4].max() - sel[:, 0].min())
+print('nms_image_kernel (cycles)')
+stats('row_stat reduction', nms[:, 1] - nms[:, 0])
+stats('row-best select', nms[:, 2] - nms[:, 1])
+stats('chunk 1 select', nms[:, 3] - nms[:, 2])
+stats('chunk 1 staging', nms[:, 4] - nms[:, 3])
+stats('groups (+ later chunks)', nms[:, 5] - nms[:, 4])
+stats('outputs', nms[:, 6] - nms[:, 5])
+stats('total', nms[:, 6] - nms[:, 0])
+print('  kernel span', nms[:, 6].max() - nms[:, 0].min())
+stats('chunks', nms[:, 7]); stats('groups', nms[:, 8]); stats('candidates', nms[:, 9])
+per_group = (nms[:, 5] - nms[:, 4]) / np.maximum(nms[:, 8], 1)
+stats('cycles per group', per_group)
+stats('  A + B1 per group', nms[:, 10] / np.maximum(nms[:, 8], 1)); stats('  B2 + append per group', nms[:, 11] / np.maximum(nms[:, 8], 1))
+ssp = np.zeros((2, 64, 4, 10), np.int64)
+lib.yolopp_ssp_read.argtypes = [ctypes.c_void_p]
+lib.yolopp_ssp_read(ssp.ctypes.data_as(ctypes.c_void_p))
+names = ['clear', 'pass1 (source scan -> stash)', 'histogram', 'scan + pivot', 'scatter', 'rank']
+for k, kn in ((0, 'select_kernel'), (1, 'nms_image_kernel')):
+    for call in range(2 if k == 0 else 2):
+        d = ssp[k, :, call]
+        if d[:, 6].max() == 0: continue
+        print('%s select_sorted_prefix call %d: groups %d stash %.0f cnt %.0f' % (kn, call, np.median(d[:, 9]), np.median(d[:, 7]), np.median(d[:, 8])))
+        for i, n in enumerate(names[:6]):
+            print('    %-30s %7.0f' % (n, np.median(d[:, i + 1] - d[:, i])))
+ssp2 = np.zeros((2, 64, 4, 4), np.int64)
+lib.yolopp_ssp2_read.argtypes = [ctypes.c_void_p]
+lib.yolopp_ssp2_read(ssp2.ctypes.data_as(ctypes.c_void_p))
+for k in (0, 1):
+    for call in (0, 1):
+        d = ssp2[k, :, call]
+        print('kernel %d call %d pass1 (thread 0 view): load+test %.0f  vote+slots %.0f  stash writes %.0f  | wait at barrier %.0f' % (
+            k, call, np.median(d[:, 0]), np.median(d[:, 1]), np.median(d[:, 2]), np.median(ssp[k, :, call, 2] - d[:, 3])))
