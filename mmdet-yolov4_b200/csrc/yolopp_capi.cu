@@ -130,6 +130,17 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     while (kcap < 2 * max_k) kcap <<= 1;
     d.sel_kcap = kcap;
     plan->sel_smem = (size_t)kcap * 8 * 2;  // sorted keys + scatter scratch
+    {
+        // staging buffer of the fast path: the largest top-k segment's objectness logits, when they fit
+        int max_m = 0;
+        for (int s = 0; s < d.nsegs; ++s)
+            if (d.seg[s].has_topk && d.seg[s].m_end - d.seg[s].m_begin > max_m) max_m = d.seg[s].m_end - d.seg[s].m_begin;
+        d.sel_stage = 0;
+        if (max_m > 0 && max_m <= 32768 && plan->sel_smem + (size_t)max_m * 4 <= 200 * 1024) {
+            d.sel_stage = max_m;
+            plan->sel_smem += (size_t)max_m * 4;
+        }
+    }
     plan->nms_smem = (size_t)NMS_KCAP * 8 * 2 + (size_t)d.keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)d.keep_cap * 28 +
                      (size_t)d.C * 4;
     plan->nms_smem = align_up(plan->nms_smem, 16);

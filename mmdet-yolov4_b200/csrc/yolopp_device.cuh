@@ -243,6 +243,7 @@ struct TopSelSmem {
     int wsum[32];
     int kb, above, bsize, count;
     u64 red[2][32];
+    unsigned long long bar;  // mbarrier of the staging copies (select kernel fast path, NMS row staging)
     SelectSmem rs;  // fallback radix select
 #ifdef YPP_PROFILE
     int prof_kernel, prof_call;
@@ -304,10 +305,11 @@ __device__ __forceinline__ void block_minmax(u64 vmin, u64 vmax, u64& omin, u64&
 // an exclusive scan, one scatter pass (keys land grouped by bucket), and a ranking step inside each bucket.
 // Falls back to the exact 8-bit radix select + bitonic sort when the pivot bucket does not fit in `cap`.
 // Requires unique keys, cap a power of two >= m, blockDim.x in {256, 512, 1024}; `tmp` is scratch of `cap`
-// keys; all threads call.
+// keys; all threads call. With `prefilled` >= 0 the caller has already placed the (<= cap) eligible keys in
+// out[0..prefilled) and the source is not touched (StashSource).
 template <class Source>
 __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl, u64 hi_incl, int m, u64* out, u64* tmp, int cap,
-                                    TopSelSmem& S) {
+                                    TopSelSmem& S, int prefilled = -1) {
     typedef typename Source::Raw Raw;
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
     const int n_groups = src.groups();
@@ -320,7 +322,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
     const u64 base = lo_incl >> shift;
     YPP_SSP(0);
     for (int i = tid; i < TS_BINS; i += nth) S.hist[i] = 0;
-    if (tid == 0) S.count = 0;
+    if (tid == 0) S.count = prefilled < 0 ? 0 : prefilled;  // prefilled: the caller already put the eligible keys in `out`
     __syncthreads();
     YPP_SSP(1);
     constexpr int U = Source::U, V = Source::V;  // U independent vector loads in flight per thread
@@ -335,7 +337,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
 #else
 #define YPP_ACC(i) do { } while (0)
 #endif
-    for (int b0 = 0; b0 < n_groups; b0 += nth * U) {
+    for (int b0 = 0; b0 < n_groups && prefilled < 0; b0 += nth * U) {
         Raw raw[U];
 #pragma unroll
         for (int q = 0; q < U; ++q) {
@@ -531,6 +533,16 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl,
     return cnt;
 }
 
+// placeholder source of a prefilled stash
+struct StashSource {
+    typedef uint32_t Raw;
+    static constexpr int V = 1, U = 1;
+    __device__ __forceinline__ Raw load(int) const { return 0u; }
+    __device__ __forceinline__ unsigned exact(const Raw&, int, u64, u64) const { return 0u; }
+    __device__ __forceinline__ u64 key_at(int, int) const { return 0ull; }
+    __device__ __forceinline__ int groups() const { return 0; }
+};
+
 // ------------------------------------------------------------------------------------------------
 // mbarrier + TMA
 // ------------------------------------------------------------------------------------------------
@@ -595,6 +607,13 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+// 4-byte asynchronous copy global -> shared (LDGSTS): many in flight per thread without holding registers
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");

@@ -80,6 +80,7 @@ struct DevParams {
     float score_thr, conf_thr, iou_thr, foff;
     int split_thr, nms_agnostic, m_eff, keep_cap, out_cap, rescale;
     int sel_kcap;  // key buffer (power of two) of the select kernel
+    int sel_stage; // 32-bit slots of the select kernel's logit staging buffer (0: exact path only)
     int nms_rowkeys_off;  // byte offset of the sorted row-best keys inside the NMS kernel's dynamic smem
     int tma_tiles, ldg_blocks;
     LevelDev lv[MAXL];
@@ -271,6 +272,234 @@ struct RowBestSource {
 // ------------------------------------------------------------------------------------------------
 // K0: objectness top-k
 // ------------------------------------------------------------------------------------------------
+// (level, anchor, position) of plane-major slot m of a segment; false for the alignment padding between levels
+__device__ __forceinline__ bool seg_slot(const DevParams& P, const SegDev& sg, int m, int& l, int& a, int& hw) {
+    for (int li = sg.num_levels - 1; li >= 0; --li) {
+        const LevelDev& lv = P.lv[sg.first_level + li];
+        if (m >= lv.m_off) {
+            int e = m - lv.m_off;
+            if (e >= P.A * lv.HW) return false;
+            int aa = 0;
+            while (e >= lv.HW) {
+                e -= lv.HW;
+                ++aa;
+            }
+            l = sg.first_level + li;
+            a = aa;
+            hw = e;
+            return true;
+        }
+    }
+    return false;
+}
+
+// rank map + row -> anchor table from the sorted top-k keys
+__device__ __forceinline__ void select_write(const DevParams& P, const SegDev& sg, int b, const u64* sel, int k) {
+    uint32_t* rank = P.rank + (size_t)b * P.M_pad;
+    const int first = sg.first_level, nl = sg.num_levels, A = P.A;
+    for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
+        const int n = (int)(uint32_t)sel[i];
+        int l = first;
+        for (int q = nl - 1; q >= 0; --q)
+            if (n >= P.lv[first + q].n_off) {
+                l = first + q;
+                break;
+            }
+        const LevelDev& lv = P.lv[l];
+        const int loc = n - lv.n_off;
+        const int hw = loc / A, a = loc - hw * A;
+        rank[lv.m_off + a * lv.HW + hw] = (uint32_t)(sg.row_off + i);
+        P.row_anchor[(size_t)b * P.R + sg.row_off + i] = n;
+    }
+}
+
+// Fast path of the objectness top-k: work on the RAW logits. sigmoid is monotone, so the k best confidences
+// belong to the k best logits — except for ties: distinct logits can round to the same confidence, and the
+// canonical order breaks confidence ties by anchor index. Hence:
+//   1. the segment's objectness logits are copied to shared memory (4-byte async copies: one DRAM round trip
+//      for the whole segment) and mapped to order-preserving integers;
+//   2. a histogram of a 1-in-8 sample picks a cut that keeps ~1.3 k logits (the "stash");
+//   3. only the stash goes through sigmoid and becomes (~ord(conf) << 32 | anchor) keys, which are sorted;
+//   4. the result is exact iff every logit outside the stash is strictly worse than the k-th key: checked with
+//      a 16-ulp guard band on the confidence of the cut itself (covers ties and any last-ulp non-monotonicity
+//      of the polynomial). Otherwise — saturated / mass-tied objectness — the caller runs the exact path over
+//      all confidences.
+// Returns true when the top-k has been written.
+__device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, int b, u64* sel, u64* tmp, uint32_t* ox, int kcap,
+                                         TopSelSmem& S) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    static_assert(SEL_THREADS * 2 == TS_BINS, "two histogram bins per thread in the pivot scan");
+    const int M = sg.m_end - sg.m_begin;
+    uint32_t* rank = P.rank + (size_t)b * P.M_pad + sg.m_begin;
+    for (int i = tid; i < TS_BINS; i += SEL_THREADS) S.hist[i] = 0;
+    if (tid == 0) S.count = 0;
+    // 1. stage the logits (slot order = plane-major order of the segment): one bulk copy per objectness plane
+    //    where planes are 16-byte aligned (issued by warp 0, one plane per lane), 4-byte async copies otherwise
+    uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        uint32_t bulk_bytes = 0;
+        for (int li = 0; li < sg.num_levels; ++li) {
+            const LevelDev& lv = P.lv[sg.first_level + li];
+            if (((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && (((lv.m_off - sg.m_begin) & 3) == 0))
+                bulk_bytes += (uint32_t)(P.A * lv.HW) * 4u;
+        }
+        mbar_arrive_expect_tx(bar, bulk_bytes);
+    }
+    __syncthreads();
+    for (int li = 0; li < sg.num_levels; ++li) {
+        const LevelDev& lv = P.lv[sg.first_level + li];
+        const float* lbase = lv.ptr + (size_t)b * P.A * P.NA * lv.HW;
+        const int AHW = P.A * lv.HW, s0 = lv.m_off - sg.m_begin;
+        const bool bulk = ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && ((s0 & 3) == 0);
+        if (bulk) {
+            if (warp == 0)
+                for (int a = lane; a < P.A; a += 32)
+                    bulk_load_1d(ox + s0 + a * lv.HW, lbase + ((size_t)a * P.NA + 4) * lv.HW, (uint32_t)lv.HW * 4u, bar);
+        } else {
+            for (int e = tid; e < AHW; e += SEL_THREADS) {
+                int a = 0, hw = e;
+                while (hw >= lv.HW) {
+                    hw -= lv.HW;
+                    ++a;
+                }
+                cp_async4(ox + s0 + e, lbase + ((size_t)a * P.NA + 4) * lv.HW + hw);
+            }
+        }
+        const int pad0 = s0 + AHW, pad1 = li + 1 < sg.num_levels ? P.lv[sg.first_level + li + 1].m_off - sg.m_begin : M;
+        if (tid < pad1 - pad0) ox[pad0 + tid] = 0xFFFFFFFFu;  // alignment padding: becomes ord 0, never eligible
+    }
+    YPP_PHASE(0, b, 5);
+    cp_async_wait_all();
+    mbar_wait(bar, 0u);
+    __syncthreads();
+    YPP_PHASE(0, b, 6);
+    uint32_t omin = 0xFFFFFFFFu, omax = 0u;
+    for (int m = tid; m < M; m += SEL_THREADS) {
+        const uint32_t raw = ox[m];
+        const uint32_t o = raw == 0xFFFFFFFFu ? 0u : f2ord(__uint_as_float(raw));
+        ox[m] = o;
+        rank[m] = RANK_INVALID;
+        omin = (o && o < omin) ? o : omin;
+        omax = o > omax ? o : omax;
+    }
+    omin = __reduce_min_sync(0xffffffffu, omin);
+    omax = __reduce_max_sync(0xffffffffu, omax);
+    YPP_PHASE(0, b, 7);
+    uint32_t* red = reinterpret_cast<uint32_t*>(&S.red[0][0]);
+    if (lane == 0) {
+        red[warp] = omin;
+        red[32 + warp] = omax;
+    }
+    __syncthreads();
+    omin = red[lane];
+    omax = red[32 + lane];
+    omin = __reduce_min_sync(0xffffffffu, omin);
+    omax = __reduce_max_sync(0xffffffffu, omax);
+    YPP_PHASE(0, b, 1);
+    const uint32_t range = omax - omin;
+    const int shift = range >= (uint32_t)TS_BINS ? (32 - __clz(range)) - 11 : 0;
+    // 2. sampled histogram of (omax - o): bin 0 holds the best logits
+    for (int m = tid * 8; m < M; m += SEL_THREADS * 8) {
+        const uint32_t o = ox[m];
+        if (o) atomicAdd(&S.hist[(omax - o) >> shift], 1);
+    }
+    __syncthreads();
+    const int ks = (sg.k * 13 + 79) / 80 + 24;  // 1.3 k / 8 + slack, in samples
+    {
+        const int h0 = S.hist[2 * tid], h1 = S.hist[2 * tid + 1], s = h0 + h1;
+        int incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) S.wsum[warp] = incl;
+        if (tid == 0) S.kb = TS_BINS - 1;
+        __syncthreads();
+        if (warp == 0) {
+            int w = S.wsum[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            S.wsum[lane] = wi - w;
+        }
+        __syncthreads();
+        const int excl = S.wsum[warp] + incl - s;
+        if (excl < ks && ks <= excl + h0) S.kb = 2 * tid;
+        else if (excl + h0 < ks && ks <= excl + s) S.kb = 2 * tid + 1;
+        __syncthreads();
+    }
+    const int pb = S.kb;
+    const uint32_t cut = (uint32_t)((((u64)pb + 1ull) << shift) - 1ull);  // keep omax - o <= cut
+    // 3. stash: slots of the surviving logits (unordered)
+    uint32_t* slots = reinterpret_cast<uint32_t*>(tmp);
+    {
+        static_assert(SEL_THREADS * 32 >= 32768, "one survivor bit per staged slot of a thread");
+        unsigned em = 0u;
+        for (int m = tid, j = 0; m < M; m += SEL_THREADS, ++j) {
+            const uint32_t o = ox[m];
+            em |= ((o && omax - o <= cut) ? 1u : 0u) << j;
+        }
+        const int c = __popc(em);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int sp = 0;
+        if (lane == 31 && incl) sp = atomicAdd(&S.count, incl);
+        sp = __shfl_sync(0xffffffffu, sp, 31) + incl - c;
+        while (em) {
+            const int j = __ffs(em) - 1;
+            em &= em - 1;
+            if (sp < 2 * kcap) slots[sp] = (uint32_t)(tid + j * SEL_THREADS);
+            ++sp;
+        }
+    }
+    __syncthreads();
+    const int n_stash = S.count;
+    YPP_PHASE(0, b, 2);
+    if (n_stash < sg.k || n_stash > kcap) return false;
+    // keys of the stash + their exact range
+    uint32_t hmin = 0xFFFFFFFFu, hmax = 0u;
+    for (int i = tid; i < n_stash; i += SEL_THREADS) {
+        const int m = (int)slots[i];
+        const float conf = c_sigmoid(ord2f(ox[m]));
+        int l = 0, a = 0, hw = 0;
+        seg_slot(P, sg, m + sg.m_begin, l, a, hw);
+        const uint32_t h = ~f2ord(conf);
+        sel[i] = ((u64)h << 32) | (u64)(uint32_t)(P.lv[l].n_off + hw * P.A + a);
+        hmin = h < hmin ? h : hmin;
+        hmax = h > hmax ? h : hmax;
+    }
+    hmin = __reduce_min_sync(0xffffffffu, hmin);
+    hmax = __reduce_max_sync(0xffffffffu, hmax);
+    if (lane == 0) {
+        red[warp] = hmin;
+        red[32 + warp] = hmax;
+    }
+    __syncthreads();
+    hmin = __reduce_min_sync(0xffffffffu, red[lane]);
+    hmax = __reduce_max_sync(0xffffffffu, red[32 + lane]);
+    __syncthreads();  // red[] and the slots in `tmp` are reused below
+    YPP_PHASE(0, b, 8);
+    StashSource none;
+    const int cnt = select_sorted_prefix(none, (u64)hmin << 32, ((u64)hmax << 32) | 0xFFFFFFFFull, sg.k, sel, tmp, kcap, S, n_stash);
+    YPP_PHASE(0, b, 3);
+    if (cnt < sg.k) return false;
+    // 4. every logit outside the stash is below the cut: its confidence is at most conf(cut) (+ rounding noise)
+    const uint32_t conf_cut = f2ord(c_sigmoid(ord2f(omax - cut)));
+    const uint32_t conf_k = ~(uint32_t)(sel[sg.k - 1] >> 32);
+    if (cut < range && !(conf_k >= conf_cut + 16u)) return false;
+    select_write(P, sg, b, sel, sg.k);
+    return true;
+}
+
 // One CTA per (top-k segment, image). Keys are (~ord(conf) << 32 | n): ascending = (conf desc, anchor asc) —
 // the canonical order of conf_pred.topk(nms_pre) (yolocsp_head.py:350-355 / yolo_head.py:281-302).
 __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_constant__ DevParams P) {
@@ -286,7 +515,16 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     YPP_PHASE(0, b, 0);
 #ifdef YPP_PROFILE
     if (threadIdx.x == 0) { S.prof_kernel = 0; S.prof_call = 0; }
+    __syncthreads();
 #endif
+    if (P.sel_stage >= sg.m_end - sg.m_begin) {
+        // fast path on the raw logits; falls through to the exact path when it cannot prove its result
+        if (select_fast(P, sg, b, sel, sel + P.sel_kcap, reinterpret_cast<uint32_t*>(sel + 2 * P.sel_kcap), P.sel_kcap, S)) {
+            YPP_PHASE(0, b, 4);
+            return;
+        }
+        __syncthreads();
+    }
     // pass 0: objectness of every anchor of the segment -> composite key; rank map cleared; key range.
     // Loads are issued in batches of 8 per thread so that one DRAM round trip covers 8 anchors.
     u64 kmin = ~0ull, kmax = 0ull;
@@ -353,22 +591,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
         __syncthreads();
         cnt = select_sorted_prefix(src, gmin, gmax, sg.k, sel, sel + P.sel_kcap, P.sel_kcap, S);
     }
-    const int k = cnt < sg.k ? cnt : sg.k;
-    const int first = sg.first_level, nl = sg.num_levels, A = P.A;
-    for (int i = tid; i < k; i += SEL_THREADS) {
-        const int n = (int)(uint32_t)sel[i];
-        int l = first;
-        for (int q = nl - 1; q >= 0; --q)
-            if (n >= P.lv[first + q].n_off) {
-                l = first + q;
-                break;
-            }
-        const LevelDev& lv = P.lv[l];
-        const int loc = n - lv.n_off;
-        const int hw = loc / A, a = loc - hw * A;
-        rank[lv.m_off + a * lv.HW + hw] = (uint32_t)(sg.row_off + i);
-        P.row_anchor[(size_t)b * P.R + sg.row_off + i] = n;
-    }
+    select_write(P, sg, b, sel, cnt < sg.k ? cnt : sg.k);
     YPP_PHASE(0, b, 4);
 }
 

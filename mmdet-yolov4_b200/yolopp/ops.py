@@ -212,3 +212,46 @@ class Session:
         """dict stage -> milliseconds of the last profiled run (call after torch.cuda.synchronize())."""
         ev = self._events
         return {n: ev[i].elapsed_time(ev[i + 1]) for i, n in enumerate(_capi.STAGE_NAMES)}
+
+
+class Pipeline:
+    """Software pipelining ACROSS batches for serving loops: `depth` Sessions (own workspace + output block each)
+    on `depth` CUDA streams, used round-robin. The per-image kernels of the path (objectness top-k, NMS: one CTA
+    per image) leave more than half of the SMs idle and are latency bound, the decode kernel is HBM bound; with
+    consecutive batches on different streams the top-k / NMS of one batch run beside the decode of another.
+
+        pipe = Pipeline(params, depth=3)
+        t = pipe.submit(pred_maps)        # asynchronous; pred_maps must stay alive until the ticket is done
+        out = pipe.result(t)              # waits (host) for that batch; dict of fixed-capacity device tensors
+
+    A slot's outputs are overwritten when the slot is reused, i.e. `depth` submits later.
+    """
+
+    def __init__(self, params, depth=3, device='cuda'):
+        self.depth = int(depth)
+        self.dev = torch.device(device)
+        self.sessions = [Session(params, device) for _ in range(self.depth)]
+        with torch.cuda.device(self.dev):
+            self.streams = [torch.cuda.Stream(self.dev) for _ in range(self.depth)]
+            self.done = [torch.cuda.Event() for _ in range(self.depth)]
+        self.n = 0
+
+    def submit(self, pred_maps, scale_factors=None):
+        slot = self.n % self.depth
+        self.n += 1
+        st = self.streams[slot]
+        st.wait_stream(torch.cuda.current_stream(self.dev))  # the inputs were produced on the caller's stream
+        with torch.cuda.stream(st):
+            self.sessions[slot].run(pred_maps, scale_factors)
+            self.done[slot].record(st)
+        return slot
+
+    def result(self, ticket):
+        self.done[ticket].synchronize()
+        return self.sessions[ticket].out
+
+    def join(self):
+        """Makes the caller's current stream wait for everything submitted so far (no host sync)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for st in self.streams:
+            cur.wait_stream(st)

@@ -298,3 +298,50 @@ def test_get_results_host_and_bbox2result():
         assert len(per_class) == 80 and sum(len(x) for x in per_class) == len(labels)
         for c in range(80):
             np.testing.assert_array_equal(per_class[c], orc['dets'][b][orc['labels'][b] == c])
+
+
+def test_pipeline_matches_single_stream():
+    """Batches in flight on several streams (yolopp.ops.Pipeline) give the results of one batch at a time."""
+    import yolopp
+    from yolopp.ops import Pipeline
+    case = dict(cases.CASES['csp608_sparse'], batch=8)
+    p = cases.build_params(case)
+    inputs = [yolopp.synth.synth_levels(p, 100 + j, case['dist']) for j in range(5)]
+    want = []
+    for lv in inputs:
+        out = yolopp.get_bboxes_raw(p, lv)
+        torch.cuda.synchronize()
+        want.append({k: v.cpu().numpy().copy() for k, v in out.items()})
+    pipe = Pipeline(p, depth=3)
+    for rnd in range(2):  # second round reuses the slots
+        tickets = []
+        for j in (0, 1, 2):
+            tickets.append((j, pipe.submit(inputs[j])))
+        for j, t in tickets:
+            out = pipe.result(t)
+            for k in ('count', 'num_candidates', 'labels', 'anchors', 'rows'):
+                np.testing.assert_array_equal(out[k].cpu().numpy(), want[j][k], err_msg=f'{k} batch {j}')
+            np.testing.assert_array_equal(_u32(out['dets'].cpu().numpy()), _u32(want[j]['dets']))
+        # keep all three slots busy with other batches before the next round
+        for j in (3, 4, 3):
+            pipe.submit(inputs[j])
+    torch.cuda.synchronize()
+
+
+def test_select_exact_path_on_tied_objectness():
+    """Objectness logits quantised to a handful of values (mass ties at the top-k cut): the raw-logit fast path
+    of the select kernel must decline and the exact path must reproduce the canonical (conf desc, index asc) order."""
+    import yolopp
+    for name, q in (('csp_tiny', 2.0), ('csp608_sparse', 2.0), ('csp608_sparse', 64.0)):
+        case = dict(cases.CASES[name])
+        p = cases.build_params(case)
+        levels = yolopp.synth.synth_levels(p, 5, case['dist'])
+        A, NA = p.num_anchors, 5 + p.num_classes
+        for x in levels:
+            B, _, H, W = x.shape
+            v = x.view(B, A, NA, H, W)
+            v[:, :, 4] = torch.round(v[:, :, 4] * q) / q  # multiples of 1/q
+        host = [x.cpu().numpy() for x in levels]
+        orc = oracle.get_bboxes(p, host)
+        _, _, res = run_cuda(case, p, levels)
+        compare(p, res, orc, f'tied objectness {name} 1/{q}')

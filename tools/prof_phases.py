@@ -21,10 +21,11 @@ sel = buf[0, :B]; nms = buf[1, :B]
 def stats(name, d):
     print('  %-34s median %7.0f  p10 %7.0f  p90 %7.0f  max %7.0f' % (name, np.median(d), np.percentile(d, 10), np.percentile(d, 90), d.max()))
 print('select_kernel (cycles)')
-stats('pass0 keys + minmax', sel[:, 1] - sel[:, 0])
-stats('sample select', sel[:, 2] - sel[:, 1])
-stats('main select', sel[:, 3] - sel[:, 2])
-stats('retry + rank scatter', sel[:, 4] - sel[:, 3])
+stats('stage logits + ord + minmax', sel[:, 1] - sel[:, 0])
+stats('   issue async copies', sel[:, 5] - sel[:, 0]); stats('   wait copies', sel[:, 6] - sel[:, 5]); stats('   ord + rank clear', sel[:, 7] - sel[:, 6]); stats('   keys of the stash', sel[:, 8] - sel[:, 2])
+stats('sampled pivot + stash', sel[:, 2] - sel[:, 1])
+stats('keys + sort', sel[:, 3] - sel[:, 2])
+stats('guard + rank scatter', sel[:, 4] - sel[:, 3])
 stats('total', sel[:, 4] - sel[:, 0])
 print('  kernel span', sel[:, 4].max() - sel[:, 0].min())
 print('nms_image_kernel (cycles)')
