@@ -14,6 +14,26 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Staging ring of the NMS kernel's candidate scan: NMS_STAGES buffers of whole score-matrix rows (rows must be
+// 16-byte multiples for the asynchronous copies; classes <= 128 so that one lane owns one 16-byte chunk of a row).
+// Kept to ~60 KB: the kernel also lives off the L1 that shared memory is carved from.
+static size_t nms_add_stage(ypp::DevParams& d, size_t smem) {
+    d.nms_stage_off = 0;
+    d.nms_stage_rows = 0;
+#ifdef YPP_NO_STAGE
+    return smem;
+#endif
+    if (d.C % 4 != 0 || d.C > 128 || d.generic) return smem;
+    smem = (smem + 127) & ~(size_t)127;
+    int rows = (int)((60 * 1024) / ypp::NMS_STAGES / ((size_t)d.C * 4));
+    rows &= ~15;  // whole rounds of the 16 warps
+    if (rows > 256) rows = 256;
+    if (rows < 16 || smem + (size_t)ypp::NMS_STAGES * rows * d.C * 4 > 200 * 1024) return smem;
+    d.nms_stage_off = (int)smem;
+    d.nms_stage_rows = rows;
+    return smem + (size_t)ypp::NMS_STAGES * rows * d.C * 4;
+}
+
 struct Plan {
     DevParams d;
     size_t off_counters, counters_bytes;
@@ -146,6 +166,7 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     plan->nms_smem = align_up(plan->nms_smem, 16);
     d.nms_rowkeys_off = (int)plan->nms_smem;
     plan->nms_smem += (size_t)NMS_KCAP * 8;
+    plan->nms_smem = nms_add_stage(d, plan->nms_smem);
 
     // which kernel decodes which level
     const StageGeom geom = stage_geom(NA);
@@ -477,8 +498,9 @@ static size_t nms_only_smem(int keep_cap, int nlab, int* rowkeys_off) {
 
 static int launch_nms_only(DevParams& d, int nlab, cudaStream_t stream) {
     int off = 0;
-    const size_t smem = nms_only_smem(d.keep_cap, nlab, &off);
+    size_t smem = nms_only_smem(d.keep_cap, nlab, &off);
     d.nms_rowkeys_off = off;
+    smem = nms_add_stage(d, smem);
     if (smem > 220 * 1024) return YOLOPP_E_INVALID;
     cudaError_t e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_rc(e);

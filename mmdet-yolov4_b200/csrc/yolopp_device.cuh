@@ -308,9 +308,10 @@ __device__ __forceinline__ void block_minmax(u64 vmin, u64 vmax, u64& omin, u64&
 // keys; all threads call. With `prefilled` >= 0 the caller has already placed the (<= cap) eligible keys in
 // out[0..prefilled) and the source is not touched (StashSource).
 template <class Source>
-__device__ __noinline__ int select_sorted_prefix(const Source& src, u64 lo_incl, u64 hi_incl, int m, u64* out, u64* tmp, int cap,
-                                    TopSelSmem& S, int prefilled = -1) {
+__device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_incl, u64 hi_incl, int m, u64* __restrict__ out,
+                                                 u64* __restrict__ tmp, int cap, TopSelSmem& S, int prefilled = -1) {
     typedef typename Source::Raw Raw;
+    const Source src = src_ref;  // fields in registers: the caller's object lives in local memory
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nth >> 5;
     const int n_groups = src.groups();
     const u64 x = lo_incl ^ hi_incl;
@@ -611,6 +612,15 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
 // 4-byte asynchronous copy global -> shared (LDGSTS): many in flight per thread without holding registers
 __device__ __forceinline__ void cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// 16-byte variant (both addresses 16-byte aligned), bypassing L1
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");

@@ -82,6 +82,7 @@ struct DevParams {
     int sel_kcap;  // key buffer (power of two) of the select kernel
     int sel_stage; // 32-bit slots of the select kernel's logit staging buffer (0: exact path only)
     int nms_rowkeys_off;  // byte offset of the sorted row-best keys inside the NMS kernel's dynamic smem
+    int nms_stage_off, nms_stage_rows;  // staging ring of the candidate scan: NMS_STAGES x nms_stage_rows matrix rows
     int tma_tiles, ldg_blocks;
     LevelDev lv[MAXL];
     SegDev seg[MAXL];
@@ -1207,6 +1208,100 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
     P.row_stat[(size_t)b * P.R + r] = make_uint4(best, worst, (uint32_t)npass, 0u);
 }
 
+// Candidate scan of the NMS kernel through shared memory: the score-matrix rows of the `nrows` best rows
+// (rows[i], low word = row index) are streamed through a ring of NMS_STAGES staging buffers with 16-byte
+// asynchronous copies (no registers held, all stages in flight: the DRAM latency is paid about once instead of
+// once per load batch), and every entry inside the key window [lo, hi] lands in the stash `out` as a 64-bit key.
+// Warp w owns rows w, w + 16, ... of a stage, one lane per 16-byte chunk of a row (C <= 128, C % 4 == 0).
+// Returns the number of stashed keys (may exceed cap: the caller then falls back to the generic source scan);
+// all threads call.
+constexpr int NMS_STAGES = 3;
+__device__ __noinline__ int nms_stage_scan(const DevParams& P, const uint32_t* mat, const u64* rows, int nrows, u64 lo, u64 hi,
+                                           u64* out, int cap, unsigned char* stage, int* count) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = NMS_THREADS / 32;
+    const int C = P.C, C4 = C >> 2, H = P.nms_stage_rows;
+    const uint32_t row_bytes = (uint32_t)C * 4u;
+    ScoreWindow win;
+    win.set(lo, hi);
+    const int npass = (nrows + H - 1) / H;
+    if (tid == 0) *count = 0;
+    auto issue = [&](int pass) {  // every thread copies the chunks it will later test (plus commit)
+        if (pass < npass) {
+            const int r0 = pass * H, n = min(H, nrows - r0);
+            unsigned char* dst = stage + (size_t)(pass % NMS_STAGES) * H * row_bytes;
+            if (lane < C4)
+                for (int i = warp; i < n; i += NW)
+                    cp_async16(dst + (size_t)i * row_bytes + lane * 16, mat + (size_t)(uint32_t)rows[r0 + i] * C + 4 * lane);
+        }
+        cp_async_commit();
+    };
+#ifdef YPP_PROFILE
+    long long pt[3] = {0, 0, 0}, pt_t = clock64();
+#define YPP_ACC2(i) do { long long t2 = clock64(); pt[i] += t2 - pt_t; pt_t = t2; } while (0)
+#else
+#define YPP_ACC2(i) do { } while (0)
+#endif
+#pragma unroll
+    for (int s = 0; s < NMS_STAGES; ++s) issue(s);
+    YPP_ACC2(0);
+    for (int pass = 0; pass < npass; ++pass) {
+        const int r0 = pass * H, n = min(H, nrows - r0);
+        const unsigned char* src = stage + (size_t)(pass % NMS_STAGES) * H * row_bytes;
+        cp_async_wait_group<NMS_STAGES - 1>();  // this thread's copies of `pass` have landed; it reads only those
+        if (pass == 0) __syncthreads();         // (*count = 0 above)
+        YPP_ACC2(1);
+        // survivors of up to 8 rows are flushed together
+        for (int i0 = warp; i0 < n; i0 += NW * 8) {
+            unsigned em = 0u;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = i0 + q * NW;
+                if (i < n && lane < C4) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(src + (size_t)i * row_bytes + lane * 16);
+                    const uint32_t f0 = win.ends ? (uint32_t)rows[r0 + i] * (uint32_t)C + 4u * lane : 0u;
+                    em |= win.test4(w, f0) << (q * 4);
+                }
+            }
+            if (__any_sync(0xffffffffu, em != 0u)) {
+                const int c = __popc(em);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                int sp = 0;
+                if (lane == 31) sp = atomicAdd(count, incl);
+                sp = __shfl_sync(0xffffffffu, sp, 31) + incl - c;
+                while (em) {
+                    const int pos = __ffs(em) - 1;
+                    em &= em - 1;
+                    const int i = i0 + (pos >> 2) * NW, v = pos & 3;
+                    const uint32_t word = *reinterpret_cast<const uint32_t*>(src + (size_t)i * row_bytes + lane * 16 + v * 4);
+                    const uint32_t flat = (uint32_t)rows[r0 + i] * (uint32_t)C + 4u * lane + v;
+                    if (sp < cap) out[sp] = score_key(word, flat);
+                    ++sp;
+                }
+            }
+        }
+        YPP_ACC2(2);
+        issue(pass + NMS_STAGES);  // the same thread re-fills exactly the chunks it has just consumed
+        YPP_ACC2(0);
+    }
+#ifdef YPP_PROFILE
+    if (tid == 0 && blockIdx.x < 256) {
+        g_phase[1][blockIdx.x][12] = pt[0];
+        g_phase[1][blockIdx.x][13] = pt[1];
+        g_phase[1][blockIdx.x][14] = pt[2];
+        g_phase[1][blockIdx.x][15] = npass;
+    }
+#endif
+    cp_async_wait_group<0>();
+    __syncthreads();
+    return *count;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: per-image NMS over the merged, score-ordered candidate stream
 // ------------------------------------------------------------------------------------------------
@@ -1222,7 +1317,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     extern __shared__ __align__(16) unsigned char nms_smem[];
     __shared__ TopSelSmem S;
     __shared__ u64 s_sup, s_masks[NMS_G];
-    __shared__ int s_nk;
+    __shared__ int s_nk, s_stash;
     __shared__ uint32_t s_red[4];
     const int cap = P.keep_cap;
     u64* keys = reinterpret_cast<u64*>(nms_smem);                 // [NMS_KCAP] sorted chunk
@@ -1368,7 +1463,16 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
             rl.nsub = (C + 127) / 128;
             rl.vec4 = ((C & 3) == 0);
             rl.win.set(lo, hi);
-            got = select_sorted_prefix(rl, lo, hi, want, keys, ktmp, NMS_KCAP, S);
+            int staged = -1;
+            if (P.nms_stage_rows > 0)
+                staged = nms_stage_scan(P, mat, rowkeys, wc, lo, hi, keys, NMS_KCAP, nms_smem + P.nms_stage_off, &s_stash);
+            if (staged >= 0 && staged <= NMS_KCAP) {
+                StashSource none;
+                got = select_sorted_prefix(none, lo, hi, want, keys, ktmp, NMS_KCAP, S, staged);
+            } else {
+                __syncthreads();
+                got = select_sorted_prefix(rl, lo, hi, want, keys, ktmp, NMS_KCAP, S);
+            }
         } else {
             msrc.win.set(lo, hi);
             got = select_sorted_prefix(msrc, lo, hi, want, keys, ktmp, NMS_KCAP, S);

@@ -32,6 +32,7 @@ print('nms_image_kernel (cycles)')
 stats('row_stat reduction', nms[:, 1] - nms[:, 0])
 stats('row-best select', nms[:, 2] - nms[:, 1])
 stats('chunk 1 select', nms[:, 3] - nms[:, 2])
+stats('   staged scan: issue copies', nms[:, 12]); stats('   staged scan: wait', nms[:, 13]); stats('   staged scan: test + stash', nms[:, 14]); stats('   staged scan: passes', nms[:, 15])
 stats('chunk 1 staging', nms[:, 4] - nms[:, 3])
 stats('groups (+ later chunks)', nms[:, 5] - nms[:, 4])
 stats('outputs', nms[:, 6] - nms[:, 5])
