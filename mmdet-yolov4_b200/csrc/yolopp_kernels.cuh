@@ -770,14 +770,18 @@ __device__ __forceinline__ void process_batch(const DevParams& P, const LevelDev
         P.row_box[(size_t)b * P.R + rg] = bx;
         if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + rg] = lv.n_off + hw * P.A + a;
     }
-    // class activations of all four slots in one straight-line block: 12 independent dependency chains keep the
-    // FMA pipe busy (a single sigmoid is ~35 dependent instructions). Empty slots compute on zeros.
+    // class activations of all four slots, four at a time behind one call (c_sigmoid4): four independent
+    // dependency chains keep the FMA pipe busy and the consumer loop stays small. Empty slots compute on zeros.
     float sgm[4][DEC_ROUNDS];
     if (!P.agnostic) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int u = 0; u < DEC_ROUNDS; ++u) sgm[q][u] = c_sigmoid(tv_all[OFF + q][u]);
+        for (int u = 0; u < DEC_ROUNDS; ++u) {
+            const float4 r = c_sigmoid4(make_float4(tv_all[OFF][u], tv_all[OFF + 1][u], tv_all[OFF + 2][u], tv_all[OFF + 3][u]));
+            sgm[0][u] = r.x;
+            sgm[1][u] = r.y;
+            sgm[2][u] = r.z;
+            sgm[3][u] = r.w;
+        }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {

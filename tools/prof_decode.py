@@ -25,6 +25,7 @@ gather = np.arange(nt) < 64 * 3 * 6
 for name, sel in (('gather', gather), ('tma', ~gather)):
     print(name, 'n=%d' % sel.sum(), ' producer wait-empty %.0f | issue->landed %.0f | landed->released %.0f | released->done %.0f  (medians)' % (
         np.median((iss1 - iss0)[sel]), np.median((land - iss1)[sel]), np.median((rel - land)[sel]), np.median((done - rel)[sel])))
+    print('      means: wait-empty %.0f | issue->landed %.0f | landed->released %.0f | released->done %.0f' % ((iss1 - iss0)[sel].mean(), (land - iss1)[sel].mean(), (rel - land)[sel].mean(), (done - rel)[sel].mean()))
     print('      p90: wait-empty %.0f | issue->landed %.0f | landed->released %.0f | released->done %.0f' % (
         np.percentile((iss1 - iss0)[sel], 90), np.percentile((land - iss1)[sel], 90), np.percentile((rel - land)[sel], 90), np.percentile((done - rel)[sel], 90)))
 m6, m7 = buf[:, 6], buf[:, 7]; ok = (~gather) & (m7 > 0)
