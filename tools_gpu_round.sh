@@ -6,11 +6,16 @@ nvidia-smi -L > gpurun_out/gpu_$TAG.txt
 timeout 900 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu_$TAG.log 2>&1
 echo "pytest exit=$?" >> gpurun_out/pytest_gpu_$TAG.log
 tail -3 gpurun_out/pytest_gpu_$TAG.log
-timeout 600 python bench.py --steps 50 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
-tail -c 3000 gpurun_out/bench_$TAG.json
+timeout 600 python bench.py --steps 200 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+tail -c 600 gpurun_out/bench_$TAG.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
 timeout 300 python bench.py --workload yolov4_608_b64_dense --steps 20 --no-cpu-baseline --no-e2e > gpurun_out/bench_dense_$TAG.json 2>> gpurun_out/bench_$TAG.err
+timeout 300 python bench.py --pipeline-depth 1 --steps 100 --no-cpu-baseline --no-e2e > gpurun_out/bench_depth1_$TAG.json 2>> gpurun_out/bench_$TAG.err
+# launch list of the bench command (per-launch durations, serialised)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>> gpurun_out/bench_$TAG.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:decode_tma -s 3 -c 1 -f -o gpurun_out/prof_decode_$TAG python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>> gpurun_out/bench_$TAG.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:nms_image -s 3 -c 1 -f -o gpurun_out/prof_nms_$TAG python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>> gpurun_out/bench_$TAG.err
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:select_kernel -s 3 -c 1 -f -o gpurun_out/prof_select_$TAG python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>> gpurun_out/bench_$TAG.err
-ls -la gpurun_out | tail -20
+# DRAM traffic of the three kernels in their natural cache state (single pass, no replay)
+timeout 300 ncu --clock-control none --cache-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum -k regex:"select_kernel|decode_tma|nms_image" -s 6 -c 6 --csv --log-file gpurun_out/pipe_traffic_$TAG.csv python bench.py --pipeline-depth 1 --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>> gpurun_out/bench_$TAG.err
+for k in decode_tma nms_image select_kernel; do
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o gpurun_out/prof_${k}_$TAG python bench.py --pipeline-depth 1 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>> gpurun_out/bench_$TAG.err
+done
+ls -la gpurun_out | grep $TAG
