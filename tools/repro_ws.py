@@ -1,0 +1,57 @@
+"""Which intermediate differs between two runs? Diffs the workspace buffers (rank, row_anchor, row_box, row_stat, mat)."""
+import sys
+sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import numpy as np, torch, cases, yolopp
+from yolopp.ops import Session
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+case = dict(cases.CASES['csp608_sparse'], batch=B)
+p = cases.build_params(case)
+levels = yolopp.synth.synth_levels(p, 12, case['dist'])
+s = Session(p)
+info = s.info
+R, C = 1000, 80
+M_pad = None
+def au(x, a=256): return (x + a - 1) // a * a
+# recover M_pad from the workspace size: total = au(B*M*8)+au(B*M*4)+au(B*R*4)+2*au(B*R*16)+au(B*R*C*4)
+rest = au(B * R * 4) + 2 * au(B * R * 16) + au(B * R * C * 4)
+for M in range(22743, 23000):
+    if au(B * M * 8) + au(B * M * 4) + rest == s.ws_bytes: M_pad = M
+print('M_pad', M_pad, 'ws', s.ws_bytes)
+offs = {}; off = 0
+for name, sz in (('ckey', B * M_pad * 8), ('rank', B * M_pad * 4), ('row_anchor', B * R * 4), ('row_box', B * R * 16), ('row_stat', B * R * 16), ('mat', B * R * C * 4)):
+    offs[name] = (off, sz); off += au(sz)
+def snap():
+    s.ws.zero_(); s.run(levels); torch.cuda.synchronize()
+    return s.ws.cpu().numpy().copy(), {k: v.cpu().numpy().copy() for k, v in s.out.items()}
+a, oa = snap()
+for r in range(12):
+    b, ob = snap()
+    if np.array_equal(oa['dets'], ob['dets']) and np.array_equal(oa['num_candidates'], ob['num_candidates']): continue
+    print('run', r, 'differs; images', [i for i in range(B) if not np.array_equal(oa['dets'][i], ob['dets'][i])])
+    for name, (o, sz) in offs.items():
+        if name == 'ckey': continue
+        x, y = a[o:o + sz], b[o:o + sz]
+        if not np.array_equal(x, y):
+            idx = np.nonzero(x != y)[0]
+            per = sz // B
+            print('  ', name, 'bytes differing', len(idx), 'images', sorted(set((idx // per).tolist()))[:10])
+            if name == 'row_stat':
+                rows = sorted(set(((idx % per) // 16).tolist())); print('     rows', rows[:20])
+                xs = x.view(np.uint32).reshape(B, R, 4); ys = y.view(np.uint32).reshape(B, R, 4)
+                im = int(idx[0] // per)
+                for rr in rows[:6]: print('     img', im, 'row', rr, xs[im, rr], ys[im, rr], 'anchor', a[offs['row_anchor'][0]:][:B*R*4].view(np.int32).reshape(B, R)[im, rr])
+            if name == 'row_box':
+                xb = x.view(np.float32).reshape(B, R, 4); yb = y.view(np.float32).reshape(B, R, 4)
+                im = int(idx[0] // per); rws = sorted(set(((idx % per) // 16).tolist()))
+                anc = a[offs['row_anchor'][0]:][:B*R*4].view(np.int32).reshape(B, R)
+                for rr in rws[:6]: print('     box img', im, 'row', rr, 'anchor', anc[im, rr], xb[im, rr], yb[im, rr])
+                # what SHOULD it be: decode the same anchors with the coder op from the raw logits
+                lv0 = levels[0][im].view(3, 85, -1)
+                for rr in rws[:6]:
+                    n = int(anc[im, rr]); hw, aa = n // 3, n % 3
+                    print('       logits t0..t4 of anchor', n, lv0[aa, :5, hw].cpu().numpy(), ' neighbours hw+-64:', lv0[aa, 0, hw - 64].item(), lv0[aa, 0, hw + 64].item())
+            if name == 'mat':
+                rows = sorted(set(((idx % per) // (C * 4)).tolist())); print('     rows', rows[:20])
+    break
+else:
+    print('no difference in 12 runs')
