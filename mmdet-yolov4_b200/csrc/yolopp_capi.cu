@@ -175,7 +175,7 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     plan->dec_ctas_per_sm = plan->dec_smem <= 110 * 1024 ? 2 : 1;
     int tma_tiles = 0, ldg_blocks = 0;
     // persistent decode kernel: sparse-admission levels — TMA tiles where the plane stride is 16-byte aligned,
-    // gather tiles (enumerated first; the consumer warps take them directly, outside the TMA ring) where it is not
+    // gather tiles (enumerated first, their latency hides under the streaming) where it is not
     for (int l = 0; l < d.L; ++l) {
         LevelDev& lv = d.lv[l];
         const SegDev& sg = d.seg[lv.seg];
@@ -202,9 +202,6 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
         }
     }
     d.tma_tiles = tma_tiles;
-    d.gather_tiles = 0;
-    for (int l = 0; l < d.L; ++l)
-        if (d.lv[l].use_tma == 2) d.gather_tiles += d.lv[l].tpp * d.B * d.A;
     d.ldg_blocks = ldg_blocks;
 
     // workspace layout

@@ -18,17 +18,8 @@ constexpr uint32_t RANK_INVALID = 0xFFFFFFFFu;
 
 constexpr int TILE_T = 64;       // positions per TMA tile = two 32-wide boxes with 128-byte rows (SWIZZLE_128B)
 constexpr int TILE_SUB = 32;     // positions per box
-#ifndef YPP_STAGES
-#define YPP_STAGES 4
-#endif
-#ifndef YPP_PWARPS
-#define YPP_PWARPS 2
-#endif
-#ifndef YPP_MINB
-#define YPP_MINB 2
-#endif
-constexpr int DEC_STAGES = YPP_STAGES;    // TMA pipeline depth
-constexpr int DEC_PWARPS = YPP_PWARPS;    // producer warps per CTA: warp p issues the tiles of iterations it == p (mod 2)
+constexpr int DEC_STAGES = 4;    // TMA pipeline depth
+constexpr int DEC_PWARPS = 2;    // producer warps per CTA: warp p issues the tiles of iterations it == p (mod 2)
 #ifndef YPP_CWARPS
 #define YPP_CWARPS 8
 #endif
@@ -92,8 +83,7 @@ struct DevParams {
     int sel_stage; // 32-bit slots of the select kernel's logit staging buffer (0: exact path only)
     int nms_rowkeys_off;  // byte offset of the sorted row-best keys inside the NMS kernel's dynamic smem
     int nms_stage_off, nms_stage_rows;  // staging ring of the candidate scan: NMS_STAGES x nms_stage_rows matrix rows
-    int tma_tiles, ldg_blocks;  // tma_tiles = gather tiles (ids 0 .. gather_tiles-1) + streamed tiles
-    int gather_tiles;
+    int tma_tiles, ldg_blocks;
     LevelDev lv[MAXL];
     SegDev seg[MAXL];
     // workspace
@@ -886,17 +876,16 @@ __device__ long long g_prof[(1 << 16) * 8];
 // Handing a stage back is a write-after-read hazard ACROSS PROXIES: the consumer read the stage through the generic
 // proxy (ld.shared), the refill writes it through the async proxy (TMA). The mbarrier orders the two threads but
 // not the two proxies, so every consumer lane issues a proxy fence before the warp's arrive, and the producer
-// issues one after it has acquired the stage. Without them the shipped ring gave run-to-run differences in the
-// first tiles of a launch (3 % of the runs at batch 64, 35 % at batch 128; tools/race_probe.py); with either
-// fence 0 of 400 runs differed, at no measurable cost (111 us either way).
+// issues one after it has acquired the stage. Without them the ring gave run-to-run differences in the first
+// tiles of a launch (3 % of the runs at batch 64, 35 % at batch 128; tools/race_probe.py); with either fence 0 of
+// 400 runs differed, at no measurable cost.
 __device__ __forceinline__ void stage_release_fence() { fence_proxy_async(); }
 
-// Streamed tile of a CTA's ring iteration `it` (round-robin over the CTAs: neighbouring tiles are in flight at the
-// same time). Tile ids below `first` are gather tiles: those never enter the ring.
-__device__ __forceinline__ long long dec_tile_of(int it, int first) { return first + blockIdx.x + (long long)it * gridDim.x; }
+// Tile of a CTA's iteration `it` (round-robin over the CTAs: neighbouring tiles are in flight at the same time).
+__device__ __forceinline__ long long dec_tile_of(int it) { return blockIdx.x + (long long)it * gridDim.x; }
 
 template <int MODE>
-__global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const __grid_constant__ DevParams P,
+__global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid_constant__ DevParams P,
                                                                   const __grid_constant__ TmapPack maps) {
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned base (swizzle) — the launch reserves 1 KB of slack
@@ -925,15 +914,15 @@ __global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const
     if (warp < DEC_PWARPS) {
         // ---------------- producers: warp p owns the iterations it == p (mod DEC_PWARPS), i.e. stages p, p+2 ----------------
         static_assert(DEC_STAGES % DEC_PWARPS == 0, "a stage must belong to one producer warp");
-        for (int k0 = 0; dec_tile_of(k0 * DEC_PWARPS + warp, P.gather_tiles) < total; k0 += 32) {
+        for (int k0 = 0; dec_tile_of(k0 * DEC_PWARPS + warp) < total; k0 += 32) {
             // lane j: coordinates of this warp's iteration number k0 + j
-            const long long tl = dec_tile_of((k0 + lane) * DEC_PWARPS + warp, P.gather_tiles);
+            const long long tl = dec_tile_of((k0 + lane) * DEC_PWARPS + warp);
             int d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0, d_hw = 0, d_rbase = 0, d_topk = 0;
             if (tl < total) {
                 const int t = (int)tl;
-                int best0 = -1;  // the streamed level with the largest first-tile id <= t
+                int best0 = -1;  // the level with the largest first-tile id <= t (gather levels are enumerated first)
                 for (int q = 0; q < P.L; ++q)
-                    if (P.lv[q].use_tma == 1 && t >= P.lv[q].tile0 && P.lv[q].tile0 > best0) {
+                    if (P.lv[q].use_tma && t >= P.lv[q].tile0 && P.lv[q].tile0 > best0) {
                         best0 = P.lv[q].tile0;
                         d_l = q;
                     }
@@ -950,7 +939,7 @@ __global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const
             }
             for (int j = 0; j < 32; ++j) {
                 const int it = (k0 + j) * DEC_PWARPS + warp;
-                if (dec_tile_of(it, P.gather_tiles) >= total) break;
+                if (dec_tile_of(it) >= total) break;
                 const int l = __shfl_sync(0xffffffffu, d_l, j), plane = __shfl_sync(0xffffffffu, d_plane, j);
                 const int hw0 = __shfl_sync(0xffffffffu, d_hw0, j), bb = __shfl_sync(0xffffffffu, d_b, j);
                 const int a = __shfl_sync(0xffffffffu, d_a, j);
@@ -959,10 +948,10 @@ __global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const
                 if (lane == 0) {
                     const int s = it % DEC_STAGES;
                     const uint32_t ph = (uint32_t)(it / DEC_STAGES) & 1u;
-                    YPP_STAMP(dec_tile_of(it, P.gather_tiles), 0);
+                    YPP_STAMP(dec_tile_of(it), 0);
                     mbar_wait(&empty[s], ph ^ 1u);
                     fence_proxy_async();  // see stage_release_fence(): generic reads of the stage -> TMA writes
-                    YPP_STAMP(dec_tile_of(it, P.gather_tiles), 1);
+                    YPP_STAMP(dec_tile_of(it), 1);
                     const LevelDev& lv = P.lv[l];
                     unsigned char* dst = stages + (size_t)s * g.stage_bytes;
                     // descriptor first (it carries the iteration number the consumer matches and everything the
@@ -970,7 +959,9 @@ __global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const
                     *reinterpret_cast<int4*>(dst + g.desc_off + 16) = make_int4(hwn, rbase, tk, lv.use_tma);
                     *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l | (a << 8), bb, hw0, it);
                     uint64_t* fb = &full[s];
-                    {
+                    if (lv.use_tma == 2) {
+                        mbar_arrive(fb);  // gather tile: nothing to stream, the consumer reads global memory itself
+                    } else {
                         const bool topk = tk != 0;
                         const bool two = hw0 + TILE_SUB < hwn;  // the second box is not entirely out of bounds
                         mbar_arrive_expect_tx(fb, box_bytes * (two ? 2u : 1u) + (topk ? TILE_T * 4u : 0u));
@@ -996,50 +987,12 @@ __global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const
     // header before arming the barrier, which it can only do after the previous fill of that stage was consumed;
     // a consumer first waits until the header shows ITS iteration (the barrier is then in that fill's phase or
     // later), and only then does the parity wait.
-    // Gather tiles first (levels whose plane stride is not 16-byte aligned, e.g. 19x19: no tensor map): they never
-    // enter the ring — every consumer warp of the grid takes its share directly and gathers the admitted anchors'
-    // logits from global memory while the producers already stream the first tiles.
-    for (long long gt = (long long)blockIdx.x * DEC_CWARPS + (warp - DEC_PWARPS); gt < P.gather_tiles;
-         gt += (long long)gridDim.x * DEC_CWARPS) {
-        const int t = (int)gt;
-        int lvl = 0, best0 = -1;
-        for (int q = 0; q < P.L; ++q)
-            if (P.lv[q].use_tma == 2 && t >= P.lv[q].tile0 && P.lv[q].tile0 > best0) {
-                best0 = P.lv[q].tile0;
-                lvl = q;
-            }
-        const LevelDev& lv = P.lv[lvl];
-        const SegDev& sg = P.seg[lv.seg];
-        const int loc = t - lv.tile0;
-        const int plane = loc / lv.tpp;
-        const int hw0 = (loc - plane * lv.tpp) * TILE_T;
-        const int b = plane / P.A, a = plane - b * P.A;
-        const float* slab = lv.ptr + (size_t)plane * NA * lv.HW;
-        const size_t HW = (size_t)lv.HW;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int hw = hw0 + h * 32 + lane;
-            uint32_t r = RANK_INVALID;
-            if (hw < lv.HW) r = row_of(P, lv, b, a, hw);
-            unsigned adm = __ballot_sync(0xffffffffu, r != RANK_INVALID);
-            while (adm) {
-                const int src = __ffs(adm) - 1;
-                adm &= adm - 1;
-                const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
-                const int hwp = hw0 + h * 32 + src;
-                const float av = lane < 5 ? __ldg(slab + (size_t)lane * HW + hwp) : 0.f;
-                process_anchor<MODE>(P, lv, sg, b, a, hwp, rr, lane, av, [&](int u) -> float {
-                    return __ldg(slab + (size_t)(5 + u * 32 + lane) * HW + hwp);
-                });
-            }
-        }
-    }
     const bool in_regs = P.C <= 32 * DEC_ROUNDS;
     while (true) {
         int it = 0;
         if (lane == 0) it = atomicAdd(next_it, 1);
         it = __shfl_sync(0xffffffffu, it, 0);
-        if (dec_tile_of(it, P.gather_tiles) >= total) break;
+        if (dec_tile_of(it) >= total) break;
         const int s = it % DEC_STAGES;
         const unsigned char* stage = stages + (size_t)s * g.stage_bytes;
         {
@@ -1047,12 +1000,40 @@ __global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const
             while (*dit != it) __nanosleep(YPP_SLEEP);
         }
         mbar_wait(&full[s], (uint32_t)(it / DEC_STAGES) & 1u);
-        YPP_STAMP(dec_tile_of(it, P.gather_tiles), 2);
+        YPP_STAMP(dec_tile_of(it), 2);
         const int4 desc = *reinterpret_cast<const int4*>(stage + g.desc_off);
         const int4 desc2 = *reinterpret_cast<const int4*>(stage + g.desc_off + 16);
         const int b = desc.y, a = desc.x >> 8, hw0 = desc.z;
         const int lvl = desc.x & 0xFF, HWn = desc2.x, rbase = desc2.y;
         const bool topk = desc2.z != 0;
+        if (desc2.w == 2) {
+            // gather tile (plane stride not 16-byte aligned, e.g. 19x19): the stage is not used
+            stage_release_fence();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            const LevelDev& lv = P.lv[lvl];
+            const SegDev& sg = P.seg[lv.seg];
+            const float* slab = lv.ptr + (size_t)(b * P.A + a) * NA * lv.HW;
+            const size_t HW = (size_t)lv.HW;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int hw = hw0 + h * 32 + lane;
+                uint32_t r = RANK_INVALID;
+                if (hw < lv.HW) r = row_of(P, lv, b, a, hw);
+                unsigned adm = __ballot_sync(0xffffffffu, r != RANK_INVALID);
+                while (adm) {
+                    const int src = __ffs(adm) - 1;
+                    adm &= adm - 1;
+                    const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+                    const int hwp = hw0 + h * 32 + src;
+                    const float av = lane < 5 ? __ldg(slab + (size_t)lane * HW + hwp) : 0.f;
+                    process_anchor<MODE>(P, lv, sg, b, a, hwp, rr, lane, av, [&](int u) -> float {
+                        return __ldg(slab + (size_t)(5 + u * 32 + lane) * HW + hwp);
+                    });
+                }
+            }
+            continue;
+        }
         const uint32_t* rk = reinterpret_cast<const uint32_t*>(stage + g.rank_off);
 
         // admitted positions of the tile as a 64-bit mask (everything needed comes from the stage header: no
@@ -1065,14 +1046,14 @@ __global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const
         }
         uint32_t m_lo = __ballot_sync(0xffffffffu, r_lo != RANK_INVALID);
         uint32_t m_hi = __ballot_sync(0xffffffffu, r_hi != RANK_INVALID);
-        YPP_STAMP(dec_tile_of(it, P.gather_tiles), 6);
+        YPP_STAMP(dec_tile_of(it), 6);
         bool released = false;
         if (!(m_lo | m_hi)) {
             stage_release_fence();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             released = true;
-            YPP_STAMP(dec_tile_of(it, P.gather_tiles), 3);
+            YPP_STAMP(dec_tile_of(it), 3);
         }
         while (m_lo | m_hi) {
             // pick up to DEC_BATCH admitted positions (uniform scalar work) ...
@@ -1109,14 +1090,14 @@ __global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const
                 const int gq = lane >> 3, kq = lane & 7;
                 const int pg0 = gq == 0 ? pos[0] : (gq == 1 ? pos[1] : (gq == 2 ? pos[2] : pos[3]));
                 const float av0 = (kq < 5 && gq < nb) ? tile_at(stage, g.sub_bytes, kq, pg0) : 0.f;
-                YPP_STAMP(dec_tile_of(it, P.gather_tiles), 7);
+                YPP_STAMP(dec_tile_of(it), 7);
                 // last batch and everything is in registers: give the stage back before the math
                 if (!(m_lo | m_hi)) {
                     stage_release_fence();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
                     released = true;
-                    YPP_STAMP(dec_tile_of(it, P.gather_tiles), 3);
+                    YPP_STAMP(dec_tile_of(it), 3);
                 }
                 process_batch<MODE, 0>(P, lv, sg, b, a, hw0, nb, pos, rr, av0, tv, lane);
             } else {
@@ -1137,14 +1118,14 @@ __global__ void __launch_bounds__(DEC_THREADS, YPP_MINB) decode_tma_kernel(const
             stage_release_fence();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
-            YPP_STAMP(dec_tile_of(it, P.gather_tiles), 3);
+            YPP_STAMP(dec_tile_of(it), 3);
         }
-        YPP_STAMP(dec_tile_of(it, P.gather_tiles), 4);
+        YPP_STAMP(dec_tile_of(it), 4);
 #ifdef YPP_PROFILE
-        if (lane == 0 && dec_tile_of(it, P.gather_tiles) < (1 << 16)) {
+        if (lane == 0 && dec_tile_of(it) < (1 << 16)) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            g_prof[(size_t)dec_tile_of(it, P.gather_tiles) * 8 + 5] = smid;
+            g_prof[(size_t)dec_tile_of(it) * 8 + 5] = smid;
         }
 #endif
     }
