@@ -33,6 +33,7 @@ WORKLOADS = {
     'yolov4_608_b64_dense': ('csp608_dense', 64),
     'yolov5_640_b128_sparse': ('csp640_sparse', 128),
     'yolov3_640_b128_sparse': ('v3_640_sparse', 128),
+    'yolov4_1280_b128_sparse': ('csp1280_sparse', 128),  # configs[4]: 1024 images sharded over 8 GPUs
 }
 
 
@@ -130,10 +131,7 @@ def get_case(workload):
     import cases
     from yolopp import _capi as capi
     key, batch = WORKLOADS[workload]
-    if key == 'v3_640_sparse':
-        case = cases._v3(640, batch, 'sparse', 47)
-    else:
-        case = dict(cases.CASES[key])
+    case = dict(cases.CASES[key])
     case['batch'] = batch
     return case
 

@@ -157,6 +157,11 @@ typedef struct yolopp_plan_info {
 } yolopp_plan_info;
 int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info);
 
+/* Host-only self-test (no GPU): runs the decode kernel's tile scheduler map (sequence position -> tile id, the same
+ * function the kernel compiles) over [0, total) with `gather` gather tiles and checks that it is a bijection, that
+ * gather tiles are evenly spread and that both kinds stay in ascending order. YOLOPP_OK or YOLOPP_E_INVALID. */
+int yolopp_selftest_tile_sequence(int32_t total, int32_t gather);
+
 /*
  * bbox_coder.decode as a standalone elementwise op (YOLOV4BBoxCoder.decode yolov4_bbox_coder.py:39-67 when
  * mode == YOLOPP_MODE_CSP, YOLOBBoxCoder.decode yolo_bbox_coder.py:60-89 when mode == YOLOPP_MODE_V3).

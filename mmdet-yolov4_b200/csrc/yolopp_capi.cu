@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/yolopp.h"
 #include "yolopp_kernels.cuh"
 
@@ -202,13 +204,17 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
         }
     }
     d.tma_tiles = tma_tiles;
+    d.gather_tiles = 0;  // enumerated first (pass 2 above)
+    for (int l = 0; l < d.L; ++l)
+        if (d.lv[l].use_tma == 2) d.gather_tiles += d.lv[l].tpp * d.B * d.A;
     d.ldg_blocks = ldg_blocks;
 
     // workspace layout
     size_t off = 0;
     const size_t B = (size_t)d.B, Cc = (size_t)d.C, R = (size_t)d.R;
     plan->off_counters = off;
-    plan->counters_bytes = 0;
+    plan->counters_bytes = 256;  // tile counter of the decode kernel's scheduler
+    off += plan->counters_bytes;
     plan->off_ckey = off;
     off += align_up(B * d.M_pad * 8, 256);
     plan->off_rank = off;
@@ -228,6 +234,7 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
 void bind_workspace(Plan* plan, void* ws) {
     unsigned char* w = (unsigned char*)ws;
     DevParams& d = plan->d;
+    d.tile_ctr = (unsigned*)(w + plan->off_counters);
     d.ckey = (u64*)(w + plan->off_ckey);
     d.rank = (uint32_t*)(w + plan->off_rank);
     d.row_anchor = (int*)(w + plan->off_row_anchor);
@@ -356,6 +363,10 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return YOLOPP_E_CUDA + 999;
         }
+        if (d.ntopk == 0) {  // select_kernel (which zeroes the tile counter) did not run
+            e = cudaMemsetAsync(d.tile_ctr, 0, sizeof(unsigned), stream);
+            if (e != cudaSuccess) return cuda_rc(e);
+        }
         int grid = sm_count() * plan.dec_ctas_per_sm;
         if (grid > d.tma_tiles) grid = d.tma_tiles;
         if (d.mode == YOLOPP_MODE_CSP) {
@@ -397,6 +408,30 @@ int yolopp_get_bboxes_profiled(const yolopp_params* p, const float* const* level
                                void* const* events, int num_events) {
     if (!events || num_events < YOLOPP_NUM_STAGE_EVENTS) return YOLOPP_E_INVALID;
     return run_get_bboxes(p, level_ptrs, scale_factors, out, workspace, workspace_bytes, stream, events, num_events);
+}
+
+int yolopp_selftest_tile_sequence(int32_t total, int32_t gather) {
+    // host-side run of the decode kernel's own sequence -> tile map: must be a bijection on [0, total) whose
+    // gather tiles (ids < gather) come in ascending order, evenly spread, and whose streamed tiles stay in order
+    if (total <= 0 || gather < 0 || gather > total) return YOLOPP_E_INVALID;
+    std::vector<unsigned char> seen((size_t)total, 0);
+    int last_gather = -1, last_stream = gather - 1;
+    long long last_gather_q = -1;
+    const long long period = gather ? total / gather : 0;
+    for (unsigned q = 0; q < (unsigned)total; ++q) {
+        const int t = ypp::dec_tile_of_seq(q, total, gather);
+        if (t < 0 || t >= total || seen[(size_t)t]) return YOLOPP_E_INVALID;
+        seen[(size_t)t] = 1;
+        if (t < gather) {
+            if (t != last_gather + 1 || (last_gather_q >= 0 && (long long)q - last_gather_q != period)) return YOLOPP_E_INVALID;
+            last_gather = t;
+            last_gather_q = q;
+        } else {
+            if (t != last_stream + 1) return YOLOPP_E_INVALID;
+            last_stream = t;
+        }
+    }
+    return (last_gather == gather - 1 && last_stream == total - 1) ? YOLOPP_OK : YOLOPP_E_INVALID;
 }
 
 int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info) {
@@ -481,6 +516,7 @@ int yolopp_synth_level(float* out, int32_t batch, int32_t num_anchors, int32_t n
 int yolopp_prof_read(long long* host, int n) {
     return (int)cudaMemcpyFromSymbol(host, ypp::g_prof, sizeof(long long) * (size_t)n);
 }
+int yolopp_prof_cta_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_prof_cta, sizeof(long long) * 1024 * 8); }
 int yolopp_ssp_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_ssp, sizeof(long long) * 2 * 64 * 4 * 10); }
 int yolopp_ssp2_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_ssp2, sizeof(long long) * 2 * 64 * 4 * 4); }
 int yolopp_phase_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_phase, sizeof(long long) * 2 * 256 * 16); }

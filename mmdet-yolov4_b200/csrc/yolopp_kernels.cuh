@@ -84,6 +84,8 @@ struct DevParams {
     int nms_rowkeys_off;  // byte offset of the sorted row-best keys inside the NMS kernel's dynamic smem
     int nms_stage_off, nms_stage_rows;  // staging ring of the candidate scan: NMS_STAGES x nms_stage_rows matrix rows
     int tma_tiles, ldg_blocks;
+    int gather_tiles;        // tiles 0 .. gather_tiles-1 of the decode kernel's enumeration are gather tiles
+    unsigned* tile_ctr;      // workspace: next position of the decode kernel's tile sequence (zeroed by select_kernel)
     LevelDev lv[MAXL];
     SegDev seg[MAXL];
     // workspace
@@ -510,6 +512,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     const int b = blockIdx.y;
     const SegDev& sg = P.seg[P.topk_segs[blockIdx.x]];
     const int tid = threadIdx.x;
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *P.tile_ctr = 0u;  // the decode kernel's tile scheduler
     u64* ckey = P.ckey + (size_t)b * P.M_pad;
     uint32_t* rank = P.rank + (size_t)b * P.M_pad;
 
@@ -868,6 +871,14 @@ __device__ __forceinline__ float tile_at(const unsigned char* stage, uint32_t su
 #ifdef YPP_PROFILE
 // per-tile timestamps (profiling build only): [tile][0..5] = issue start, issued, landed, released, done, smid
 __device__ long long g_prof[(1 << 16) * 8];
+// per CTA: [0] clock64 and [1] globaltimer (ns) at kernel entry, [2]/[3] the same when the CTA's last consumer warp
+// leaves, [4] smid — lets the per-SM clock64 stamps be placed on one time axis
+__device__ long long g_prof_cta[1024 * 8];
+__device__ __forceinline__ long long ypp_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 #define YPP_STAMP(t, i) do { if (lane == 0 && (t) < (1 << 16)) g_prof[(size_t)(t) * 8 + (i)] = clock64(); } while (0)
 #else
 #define YPP_STAMP(t, i) do { } while (0)
@@ -881,8 +892,19 @@ __device__ long long g_prof[(1 << 16) * 8];
 // 400 runs differed, at no measurable cost.
 __device__ __forceinline__ void stage_release_fence() { fence_proxy_async(); }
 
-// Tile of a CTA's iteration `it` (round-robin over the CTAs: neighbouring tiles are in flight at the same time).
-__device__ __forceinline__ long long dec_tile_of(int it) { return blockIdx.x + (long long)it * gridDim.x; }
+// Position q of the kernel's tile sequence -> tile id. Gather tiles (ids 0 .. G-1) are latency-bound: one warp
+// gathers ~3 anchors x 85 scattered words while the others keep streaming, so they are spread evenly through the
+// sequence (every (total / G)-th position) instead of sitting at its head, where every CTA started with four of
+// them and the stream had a 4 us hole. Bijective on [0, total).
+__host__ __device__ __forceinline__ int dec_tile_of_seq(unsigned q, int total, int G) {
+    if (G == 0) return (int)q;
+    const unsigned period = (unsigned)total / (unsigned)G;  // >= 1
+    const unsigned slot = q / period;
+    if (slot < (unsigned)G && slot * period == q) return (int)slot;  // the slot-th gather tile
+    const unsigned before = slot + 1u < (unsigned)G ? slot + 1u : (unsigned)G;  // gather positions below q
+    return G + (int)(q - before);
+}
+constexpr int DEC_KIND_STOP = 3;  // stage header: the producer has run out of tiles
 
 template <int MODE>
 __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid_constant__ DevParams P,
@@ -895,12 +917,23 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
     const uint32_t box_bytes = (uint32_t)NA * 128u;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [DEC_STAGES]: the tile streamed into stage s has landed
     uint64_t* empty = full + DEC_STAGES;                      // [DEC_STAGES]: stage s may be refilled
-    int* next_it = reinterpret_cast<int*>(empty + DEC_STAGES);  // next tile (iteration) a consumer may claim
+    int* next_it = reinterpret_cast<int*>(empty + DEC_STAGES);  // next ring iteration a consumer may claim
+    volatile int* done = next_it + 1;                           // [DEC_PWARPS]: producer p has posted its STOP
     unsigned char* stages = smem_raw + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef YPP_PROFILE
+    if (threadIdx.x == 0 && blockIdx.x < 1024) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_prof_cta[blockIdx.x * 8 + 0] = clock64();
+        g_prof_cta[blockIdx.x * 8 + 1] = ypp_globaltimer();
+        g_prof_cta[blockIdx.x * 8 + 4] = smid;
+    }
+#endif
     if (threadIdx.x == 0) {
         *next_it = 0;
+        for (int pw = 0; pw < DEC_PWARPS; ++pw) done[pw] = 0;
         for (int s = 0; s < DEC_STAGES; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
@@ -912,101 +945,163 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
 
     const int total = P.tma_tiles;
     if (warp < DEC_PWARPS) {
-        // ---------------- producers: warp p owns the iterations it == p (mod DEC_PWARPS), i.e. stages p, p+2 ----------------
+        // ---------------- producers: warp p fills the ring iterations it == p (mod DEC_PWARPS), i.e. stages p, p+2 ----
+        // Tiles are claimed from ONE device-wide counter: SMs do not all stream at the same rate, and with a static
+        // round-robin the CTAs finished between 78 and 102 us (tools/prof_timeline.py). Claims are batched and
+        // guided: a warp takes n = remaining / (4 x producer warps) tiles at a time (at most 32, at least 1), its
+        // lanes work out the n tiles' coordinates in parallel (the level lookup and the integer divisions are a
+        // ~200-instruction dependent chain: done per tile by one lane they cost 11 % of the bandwidth), lane 0
+        // issues them, and the next batch is claimed before the current one is issued so that the atomic's
+        // latency hides behind the waits for empty stages. Towards the end the batches shrink to single tiles and
+        // all CTAs run dry within a tile or two of each other.
         static_assert(DEC_STAGES % DEC_PWARPS == 0, "a stage must belong to one producer warp");
-        for (int k0 = 0; dec_tile_of(k0 * DEC_PWARPS + warp) < total; k0 += 32) {
-            // lane j: coordinates of this warp's iteration number k0 + j
-            const long long tl = dec_tile_of((k0 + lane) * DEC_PWARPS + warp);
-            int d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0, d_hw = 0, d_rbase = 0, d_topk = 0;
-            if (tl < total) {
-                const int t = (int)tl;
+        const unsigned nprod = gridDim.x * DEC_PWARPS;
+        auto batch_size = [&](unsigned seen) -> unsigned {
+            const unsigned rem = seen < (unsigned)total ? (unsigned)total - seen : 0u;
+            const unsigned n = rem / (4u * nprod);
+            return n < 1u ? 1u : (n > 32u ? 32u : n);
+        };
+        unsigned n = batch_size(0u), base = 0u;
+        if (lane == 0) base = atomicAdd(P.tile_ctr, n);
+        int k = 0;  // tiles this warp has put into the ring
+        while (true) {
+            base = __shfl_sync(0xffffffffu, base, 0);
+            // the following batch, claimed now (lane 0 keeps the result to itself until the next round)
+            const unsigned n_next = batch_size(base + n);
+            unsigned base_next = 0u;
+            if (lane == 0) base_next = atomicAdd(P.tile_ctr, n_next);
+            // lane j < n: coordinates of sequence position base + j
+            int d_t = -1, d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0, d_hw = 0, d_rbase = 0, d_topk = 0, d_kind = 0;
+            if ((unsigned)lane < n && base + (unsigned)lane < (unsigned)total) {
+                const int t = dec_tile_of_seq(base + (unsigned)lane, total, P.gather_tiles);
                 int best0 = -1;  // the level with the largest first-tile id <= t (gather levels are enumerated first)
-                for (int q = 0; q < P.L; ++q)
-                    if (P.lv[q].use_tma && t >= P.lv[q].tile0 && P.lv[q].tile0 > best0) {
-                        best0 = P.lv[q].tile0;
-                        d_l = q;
+                for (int i = 0; i < P.L; ++i)
+                    if (P.lv[i].use_tma && t >= P.lv[i].tile0 && P.lv[i].tile0 > best0) {
+                        best0 = P.lv[i].tile0;
+                        d_l = i;
                     }
                 const LevelDev& lv = P.lv[d_l];
+                const SegDev& sg = P.seg[lv.seg];
                 const int loc = t - lv.tile0;
+                d_t = t;
                 d_plane = loc / lv.tpp;  // b*A + a
                 d_hw0 = (loc - d_plane * lv.tpp) * TILE_T;
                 d_b = d_plane / P.A;
                 d_a = d_plane - d_b * P.A;
-                const SegDev& sg = P.seg[lv.seg];
                 d_hw = lv.HW;
                 d_topk = sg.has_topk;
+                d_kind = lv.use_tma;
                 d_rbase = sg.row_off + (lv.n_off - P.lv[sg.first_level].n_off) + d_a;  // row of position 0 (no top-k)
             }
-            for (int j = 0; j < 32; ++j) {
-                const int it = (k0 + j) * DEC_PWARPS + warp;
-                if (dec_tile_of(it) >= total) break;
+            for (unsigned j = 0; j < n; ++j, ++k) {
+                const int t = __shfl_sync(0xffffffffu, d_t, j);
                 const int l = __shfl_sync(0xffffffffu, d_l, j), plane = __shfl_sync(0xffffffffu, d_plane, j);
                 const int hw0 = __shfl_sync(0xffffffffu, d_hw0, j), bb = __shfl_sync(0xffffffffu, d_b, j);
                 const int a = __shfl_sync(0xffffffffu, d_a, j);
                 const int hwn = __shfl_sync(0xffffffffu, d_hw, j), rbase = __shfl_sync(0xffffffffu, d_rbase, j);
-                const int tk = __shfl_sync(0xffffffffu, d_topk, j);
+                const int tk = __shfl_sync(0xffffffffu, d_topk, j), kind = __shfl_sync(0xffffffffu, d_kind, j);
                 if (lane == 0) {
+                    const int it = k * DEC_PWARPS + warp;
                     const int s = it % DEC_STAGES;
                     const uint32_t ph = (uint32_t)(it / DEC_STAGES) & 1u;
-                    YPP_STAMP(dec_tile_of(it), 0);
-                    mbar_wait(&empty[s], ph ^ 1u);
-                    fence_proxy_async();  // see stage_release_fence(): generic reads of the stage -> TMA writes
-                    YPP_STAMP(dec_tile_of(it), 1);
-                    const LevelDev& lv = P.lv[l];
                     unsigned char* dst = stages + (size_t)s * g.stage_bytes;
-                    // descriptor first (it carries the iteration number the consumer matches and everything the
-                    // consumer needs before it can release the stage), then arm the barrier
-                    *reinterpret_cast<int4*>(dst + g.desc_off + 16) = make_int4(hwn, rbase, tk, lv.use_tma);
-                    *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l | (a << 8), bb, hw0, it);
                     uint64_t* fb = &full[s];
-                    if (lv.use_tma == 2) {
-                        mbar_arrive(fb);  // gather tile: nothing to stream, the consumer reads global memory itself
+                    YPP_STAMP(t < 0 ? (1 << 16) : t, 0);
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    if (t < 0) {
+                        // out of tiles: tell the consumers (the header lives in the stage, so the stage must be free)
+                        *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(DEC_KIND_STOP << 16, 0, 0, it);
+                        mbar_arrive(fb);
                     } else {
-                        const bool topk = tk != 0;
-                        const bool two = hw0 + TILE_SUB < hwn;  // the second box is not entirely out of bounds
-                        mbar_arrive_expect_tx(fb, box_bytes * (two ? 2u : 1u) + (topk ? TILE_T * 4u : 0u));
-                        // No L2 eviction hint on purpose: plane rows are in general not 128-byte aligned, so
-                        // neighbouring tiles share the lines at their common edge; with evict_first the second
-                        // tile re-fetched them from DRAM (measured: 635 MB read per launch instead of 512 MB).
-                        tma_load_2d(dst, &maps.m[l], hw0, plane * NA, fb);
-                        if (two) tma_load_2d(dst + g.sub_bytes, &maps.m[l], hw0 + TILE_SUB, plane * NA, fb);
-                        if (topk)
-                            bulk_load_1d(dst + g.rank_off, P.rank + (size_t)bb * P.M_pad + lv.m_off + a * lv.HW + hw0,
-                                         TILE_T * 4u, fb);
+                        fence_proxy_async();  // see stage_release_fence(): generic reads of the stage -> TMA writes
+                        YPP_STAMP(t, 1);
+                        // descriptor first (it carries the iteration number the consumer matches and everything the
+                        // consumer needs before it can release the stage), then arm the barrier
+                        *reinterpret_cast<int4*>(dst + g.desc_off + 16) = make_int4(hwn, rbase, tk, t);
+                        *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l | (a << 8) | (kind << 16), bb, hw0, it);
+                        if (kind == 2) {
+                            mbar_arrive(fb);  // gather tile: nothing to stream, the consumer reads global memory itself
+                        } else {
+                            const bool topk = tk != 0;
+                            const bool two = hw0 + TILE_SUB < hwn;  // the second box is not entirely out of bounds
+                            mbar_arrive_expect_tx(fb, box_bytes * (two ? 2u : 1u) + (topk ? TILE_T * 4u : 0u));
+                            // No L2 eviction hint on purpose: plane rows are in general not 128-byte aligned, so
+                            // neighbouring tiles share the lines at their common edge; with evict_first the second
+                            // tile re-fetched them from DRAM (measured: 635 MB read per launch instead of 512 MB).
+                            tma_load_2d(dst, &maps.m[l], hw0, plane * NA, fb);
+                            if (two) tma_load_2d(dst + g.sub_bytes, &maps.m[l], hw0 + TILE_SUB, plane * NA, fb);
+                            if (topk)
+                                bulk_load_1d(dst + g.rank_off,
+                                             P.rank + (size_t)bb * P.M_pad + P.lv[l].m_off + a * hwn + hw0, TILE_T * 4u, fb);
+                        }
                     }
                 }
+                if (t < 0) return;  // STOP posted (uniform: t comes from a shuffle)
             }
+            n = n_next;
+            base = base_next;
         }
-        return;
     }
-    // ---------------- consumers: whichever warp is free claims the CTA's next tile, in order ----------------
+    // ---------------- consumers: whichever warp is free claims the CTA's next ring iteration, in order ------------
     // Tiles carry 0..8 admitted anchors, so a static round-robin would let one heavy tile block its stage (and
     // with it the in-order producers) while the other warps idle. Several warps therefore wait on the same
     // stage barrier for DIFFERENT fills, and a parity wait can only tell a barrier's current phase from the one
     // before it. The tile descriptor disambiguates: the producer writes the iteration number into the stage
     // header before arming the barrier, which it can only do after the previous fill of that stage was consumed;
     // a consumer first waits until the header shows ITS iteration (the barrier is then in that fill's phase or
-    // later), and only then does the parity wait.
+    // later), and only then does the parity wait. A producer that has run out of tiles posts a STOP header; the
+    // consumer that meets it raises the producer's `done` flag, which also frees the consumers already waiting
+    // for later iterations of that producer.
     const bool in_regs = P.C <= 32 * DEC_ROUNDS;
     while (true) {
         int it = 0;
         if (lane == 0) it = atomicAdd(next_it, 1);
         it = __shfl_sync(0xffffffffu, it, 0);
-        if (dec_tile_of(it) >= total) break;
         const int s = it % DEC_STAGES;
         const unsigned char* stage = stages + (size_t)s * g.stage_bytes;
         {
             const volatile int* dit = reinterpret_cast<const volatile int*>(stage + g.desc_off) + 3;
-            while (*dit != it) __nanosleep(YPP_SLEEP);
+            bool gone = false;
+            while (*dit != it) {
+                if (done[it % DEC_PWARPS]) {
+                    // the STOP was posted after every real fill of this producer was armed: look once more
+                    __threadfence_block();
+                    gone = *dit != it;
+                    break;
+                }
+                __nanosleep(YPP_SLEEP);
+            }
+            if (gone) {
+                bool all = true;
+#pragma unroll
+                for (int pw = 0; pw < DEC_PWARPS; ++pw) all = all && done[pw] != 0;
+                if (all) break;
+                continue;
+            }
         }
         mbar_wait(&full[s], (uint32_t)(it / DEC_STAGES) & 1u);
-        YPP_STAMP(dec_tile_of(it), 2);
         const int4 desc = *reinterpret_cast<const int4*>(stage + g.desc_off);
+        const int kind = desc.x >> 16;
+        if (kind == DEC_KIND_STOP) {
+            if (lane == 0) {
+                __threadfence_block();
+                done[it % DEC_PWARPS] = 1;
+            }
+            __syncwarp();
+            bool all = true;
+#pragma unroll
+            for (int pw = 0; pw < DEC_PWARPS; ++pw) all = all && done[pw] != 0;
+            if (all) break;
+            continue;
+        }
         const int4 desc2 = *reinterpret_cast<const int4*>(stage + g.desc_off + 16);
-        const int b = desc.y, a = desc.x >> 8, hw0 = desc.z;
+        const int b = desc.y, a = (desc.x >> 8) & 0xFF, hw0 = desc.z;
         const int lvl = desc.x & 0xFF, HWn = desc2.x, rbase = desc2.y;
         const bool topk = desc2.z != 0;
-        if (desc2.w == 2) {
+        const int tile_id = desc2.w;
+        (void)tile_id;
+        YPP_STAMP(tile_id, 2);
+        if (kind == 2) {
             // gather tile (plane stride not 16-byte aligned, e.g. 19x19): the stage is not used
             stage_release_fence();
             __syncwarp();
@@ -1046,14 +1141,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         }
         uint32_t m_lo = __ballot_sync(0xffffffffu, r_lo != RANK_INVALID);
         uint32_t m_hi = __ballot_sync(0xffffffffu, r_hi != RANK_INVALID);
-        YPP_STAMP(dec_tile_of(it), 6);
+        YPP_STAMP(tile_id, 6);
         bool released = false;
         if (!(m_lo | m_hi)) {
             stage_release_fence();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
             released = true;
-            YPP_STAMP(dec_tile_of(it), 3);
+            YPP_STAMP(tile_id, 3);
         }
         while (m_lo | m_hi) {
             // pick up to DEC_BATCH admitted positions (uniform scalar work) ...
@@ -1090,14 +1185,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                 const int gq = lane >> 3, kq = lane & 7;
                 const int pg0 = gq == 0 ? pos[0] : (gq == 1 ? pos[1] : (gq == 2 ? pos[2] : pos[3]));
                 const float av0 = (kq < 5 && gq < nb) ? tile_at(stage, g.sub_bytes, kq, pg0) : 0.f;
-                YPP_STAMP(dec_tile_of(it), 7);
+                YPP_STAMP(tile_id, 7);
                 // last batch and everything is in registers: give the stage back before the math
                 if (!(m_lo | m_hi)) {
                     stage_release_fence();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[s]);
                     released = true;
-                    YPP_STAMP(dec_tile_of(it), 3);
+                    YPP_STAMP(tile_id, 3);
                 }
                 process_batch<MODE, 0>(P, lv, sg, b, a, hw0, nb, pos, rr, av0, tv, lane);
             } else {
@@ -1118,17 +1213,23 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             stage_release_fence();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
-            YPP_STAMP(dec_tile_of(it), 3);
+            YPP_STAMP(tile_id, 3);
         }
-        YPP_STAMP(dec_tile_of(it), 4);
+        YPP_STAMP(tile_id, 4);
 #ifdef YPP_PROFILE
-        if (lane == 0 && dec_tile_of(it) < (1 << 16)) {
+        if (lane == 0 && tile_id < (1 << 16)) {
             unsigned smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-            g_prof[(size_t)dec_tile_of(it) * 8 + 5] = smid;
+            g_prof[(size_t)tile_id * 8 + 5] = (long long)smid | ((long long)blockIdx.x << 16);
         }
 #endif
     }
+#ifdef YPP_PROFILE
+    if (lane == 0 && blockIdx.x < 1024) {  // every consumer warp stamps; the last one to leave wins
+        g_prof_cta[blockIdx.x * 8 + 2] = clock64();
+        g_prof_cta[blockIdx.x * 8 + 3] = ypp_globaltimer();
+    }
+#endif
 }
 
 // Generic path for levels the TMA kernel cannot take (plane stride not 16-byte aligned, e.g. 19x19) and for

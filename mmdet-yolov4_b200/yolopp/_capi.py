@@ -233,7 +233,7 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = ('yolopp_abi_version', 'yolopp_strerror', 'yolopp_workspace_bytes', 'yolopp_get_bboxes',
-                    'yolopp_get_bboxes_profiled', 'yolopp_describe',
+                    'yolopp_get_bboxes_profiled', 'yolopp_describe', 'yolopp_selftest_tile_sequence',
                     'yolopp_coder_decode', 'yolopp_nms_workspace_bytes', 'yolopp_batched_nms', 'yolopp_multiclass_nms',
                     'yolopp_synth_level',
                     'yolopp_sigmoid', 'yolopp_exp')

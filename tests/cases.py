@@ -91,13 +91,17 @@ CASES = {
                       scale_factors=[[1.5, 1.5, 1.5, 1.5], [0.4, 0.6, 0.4, 0.6]]),
     # BASELINE.json config 4 (i): the yolov5 configs build the same YOLOCSPHead at 640^2
     'csp640_sparse': _csp(640, 2, 'sparse', 46),
+    # BASELINE.json config 4 (ii): YOLOv3 convention at 640^2 (per-level top-k, conf_thr, score_factors)
+    'v3_640_sparse': _v3(640, 2, 'sparse', 47),
+    # BASELINE.json config 5: 1280^2 (100 800 anchors per image: the objectness top-k runs its exact path)
+    'csp1280_sparse': _csp(1280, 2, 'sparse', 48),
 }
 
 # subset that is also frozen as golden vectors produced by the reference's own source (tests/golden)
 GOLDEN_CASES = ['csp608_sparse', 'csp608_dense', 'csp608_dense_thr07', 'csp608_sparse_thr002', 'csp320_nopre_sparse', 'csp_odd', 'csp416_rescale',
                 'csp_saturated', 'tencent_agnostic', 'csp_nms_agnostic', 'csp_nms_offset1', 'csp_nms_maxnum',
                 'csp_force_global', 'v3_416_sparse', 'v3_416_dense', 'v3_320_mid', 'v3_rescale', 'csp640_sparse',
-                'csp_empty']
+                'csp_empty', 'v3_640_sparse', 'csp1280_sparse']
 
 
 def build_params(case, batch=None):
@@ -140,3 +144,21 @@ def host_levels(case, params=None):
         x = oracle.synth_level(p.batch, p.num_anchors, na, hw, m, s, ysynth.level_seed(case['seed'], l))
         out.append(x.reshape(p.level_shape(l)))
     return out
+
+
+def asis_rel_err(ref_dets, got_dets):
+    """Largest relative deviation between reference-as-it-runs detections and ours, (n,5) each. north_star's bar
+    is 1e-5 relative (fp32). A box corner is `centre -/+ half-size` (yolov4_bbox_coder.py:62-65), so a corner near 0
+    is a difference of two large numbers: a 1-ulp sigmoid difference (torch's SIMD sigmoid vs the canonical
+    polynomial) is an ABSOLUTE error of ~1 ulp of the operands, not of the corner. Coordinates are therefore
+    measured against the magnitude of the box they belong to (max |coordinate| of that detection); the score column
+    is measured against itself."""
+    import numpy as np
+    a = np.asarray(ref_dets, np.float64).reshape(-1, 5)
+    o = np.asarray(got_dets, np.float64).reshape(-1, 5)
+    if a.shape[0] == 0:
+        return 0.0
+    scale = np.maximum(np.abs(a[:, :4]).max(axis=1, keepdims=True), 1e-3)
+    box = (np.abs(a[:, :4] - o[:, :4]) / np.maximum(np.abs(a[:, :4]), scale)).max()
+    score = (np.abs(a[:, 4] - o[:, 4]) / np.maximum(np.abs(a[:, 4]), 1e-3)).max()
+    return float(max(box, score))

@@ -50,9 +50,8 @@ def test_oracle_vs_reference_as_is(name):
         if bool(g['has_anchors']):
             np.testing.assert_array_equal(out['anchors'][b], g['asis_anchors'][b, :n])
         if n:
-            a, o = g['asis_dets'][b, :n].astype(np.float64), out['dets'][b].astype(np.float64)
-            rel = np.abs(a - o) / np.maximum(np.abs(a), 1e-3)
-            assert rel.max() <= 1e-5, rel.max()
+            rel = cases.asis_rel_err(g['asis_dets'][b, :n], out['dets'][b])  # coordinates vs their box's magnitude
+            assert rel <= 1e-5, rel
 
 
 def test_reference_kat_yolo_bbox_coder():

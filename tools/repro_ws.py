@@ -13,11 +13,11 @@ R, C = 1000, 80
 M_pad = None
 def au(x, a=256): return (x + a - 1) // a * a
 # recover M_pad from the workspace size: total = au(B*M*8)+au(B*M*4)+au(B*R*4)+2*au(B*R*16)+au(B*R*C*4)
-rest = au(B * R * 4) + 2 * au(B * R * 16) + au(B * R * C * 4)
+rest = 256 + au(B * R * 4) + 2 * au(B * R * 16) + au(B * R * C * 4)  # 256: scheduler counters at the front
 for M in range(22743, 23000):
     if au(B * M * 8) + au(B * M * 4) + rest == s.ws_bytes: M_pad = M
 print('M_pad', M_pad, 'ws', s.ws_bytes)
-offs = {}; off = 0
+offs = {}; off = 256
 for name, sz in (('ckey', B * M_pad * 8), ('rank', B * M_pad * 4), ('row_anchor', B * R * 4), ('row_box', B * R * 16), ('row_stat', B * R * 16), ('mat', B * R * C * 4)):
     offs[name] = (off, sz); off += au(sz)
 def snap():
