@@ -181,8 +181,11 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     for (int l = 0; l < d.L; ++l) {
         LevelDev& lv = d.lv[l];
         const SegDev& sg = d.seg[lv.seg];
-        const bool sparse = sg.has_topk && (long long)sg.k * 4 <= sg.N;
-        lv.use_tma = (tma_fits && sparse) ? ((lv.HW % 4 == 0) ? 1 : 2) : 0;
+        // every level whose segment ran a top-k goes through the persistent kernel, however dense the admission:
+        // a densely admitted level (YOLOv3's 20x20 level keeps 1000 of 1200 anchors) costs its consumers a dozen
+        // register batches per tile there, but the generic kernel would gather the same anchors one by one with
+        // uncoalesced loads (87 us for that level at 640^2 batch 128)
+        lv.use_tma = (tma_fits && sg.has_topk) ? ((lv.HW % 4 == 0) ? 1 : 2) : 0;
     }
     for (int pass = 2; pass >= 0; --pass) {
         for (int l = 0; l < d.L; ++l) {
@@ -339,6 +342,18 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
     e = cudaMemsetAsync(out->status, 0, sizeof(int32_t), stream);
     if (e != cudaSuccess) return cuda_rc(e);
 
+    // decode kernel's grid and the statically assigned head of its tile sequence (select_kernel initialises the
+    // scheduler counter with it; must match batch_size(0) in decode_tma_kernel)
+    int dec_grid = sm_count() * plan.dec_ctas_per_sm;
+    if (dec_grid > d.tma_tiles) dec_grid = d.tma_tiles;
+    if (d.tma_tiles > 0) {
+        const unsigned nprod = (unsigned)dec_grid * DEC_PWARPS;
+        unsigned n0 = (unsigned)d.tma_tiles / (4u * nprod);
+        n0 = n0 < 1u ? 1u : (n0 > 32u ? 32u : n0);
+        d.dec_first = nprod * n0;
+    } else {
+        d.dec_first = 0;
+    }
     YPP_MARK();  // 0: start of select
     if (d.ntopk > 0) {
         e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.sel_smem);
@@ -363,12 +378,10 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return YOLOPP_E_CUDA + 999;
         }
-        if (d.ntopk == 0) {  // select_kernel (which zeroes the tile counter) did not run
-            e = cudaMemsetAsync(d.tile_ctr, 0, sizeof(unsigned), stream);
-            if (e != cudaSuccess) return cuda_rc(e);
-        }
-        int grid = sm_count() * plan.dec_ctas_per_sm;
-        if (grid > d.tma_tiles) grid = d.tma_tiles;
+        // the persistent kernel only takes levels whose segment ran a top-k, so select_kernel (which initialises
+        // the scheduler counter) has run
+        if (d.ntopk == 0) return YOLOPP_E_INVALID;
+        const int grid = dec_grid;
         if (d.mode == YOLOPP_MODE_CSP) {
             e = cudaFuncSetAttribute(decode_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.dec_smem);
             if (e != cudaSuccess) return cuda_rc(e);

@@ -85,7 +85,8 @@ struct DevParams {
     int nms_stage_off, nms_stage_rows;  // staging ring of the candidate scan: NMS_STAGES x nms_stage_rows matrix rows
     int tma_tiles, ldg_blocks;
     int gather_tiles;        // tiles 0 .. gather_tiles-1 of the decode kernel's enumeration are gather tiles
-    unsigned* tile_ctr;      // workspace: next position of the decode kernel's tile sequence (zeroed by select_kernel)
+    unsigned* tile_ctr;      // workspace: next unclaimed position of the decode kernel's tile sequence (set by select_kernel)
+    unsigned dec_first;      // positions handed out statically: every producer warp's first batch needs no atomic
     LevelDev lv[MAXL];
     SegDev seg[MAXL];
     // workspace
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     const int b = blockIdx.y;
     const SegDev& sg = P.seg[P.topk_segs[blockIdx.x]];
     const int tid = threadIdx.x;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *P.tile_ctr = 0u;  // the decode kernel's tile scheduler
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *P.tile_ctr = P.dec_first;  // the decode kernel's tile scheduler
     u64* ckey = P.ckey + (size_t)b * P.M_pad;
     uint32_t* rank = P.rank + (size_t)b * P.M_pad;
 
@@ -961,8 +962,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             const unsigned n = rem / (4u * nprod);
             return n < 1u ? 1u : (n > 32u ? 32u : n);
         };
-        unsigned n = batch_size(0u), base = 0u;
-        if (lane == 0) base = atomicAdd(P.tile_ctr, n);
+        // first batch: static (the counter starts at nprod * n), so the first tiles are issued without waiting for an atomic
+        unsigned n = batch_size(0u), base = (blockIdx.x * DEC_PWARPS + (unsigned)warp) * n;
         int k = 0;  // tiles this warp has put into the ring
         while (true) {
             base = __shfl_sync(0xffffffffu, base, 0);

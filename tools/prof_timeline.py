@@ -31,7 +31,10 @@ rate = (cta[:, 3] - cta[:, 1]) / np.maximum(cta[:, 2] - cta[:, 0], 1)
 print('SM clock (cycles/ns) median %.3f' % np.median(1 / rate))
 T0 = cta[:, 1].min()
 print('CTA start spread: %.2f us; CTA end: first %.2f last %.2f us after kernel start' % ((cta[:, 1].max() - T0) / 1e3, (cta[:, 3].min() - T0) / 1e3, (cta[:, 3].max() - T0) / 1e3))
-tile_cta = (buf[:, 5] >> 16).astype(np.int64)  # tiles are claimed dynamically: the consumer records its CTA
+valid = (buf[:, 1] > 0) & (buf[:, 2] > 0) & (buf[:, 4] > 0)  # gather tiles leave before the last stamps
+print('tiles', nt, 'with complete stamps', int(valid.sum()))
+buf = buf[valid]
+tile_cta = np.minimum((buf[:, 5] >> 16).astype(np.int64), G - 1)  # tiles are claimed dynamically: the consumer records its CTA
 def ns(col):
     return cta[tile_cta, 1] + (buf[:, col] - cta[tile_cta, 0]) * rate[tile_cta] - T0
 iss, land, rel, done = ns(1), ns(2), ns(3), ns(4)

@@ -11,6 +11,12 @@ tail -c 600 gpurun_out/bench_$TAG.json
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_$TAG.json 2>> gpurun_out/bench_$TAG.err
 timeout 300 python bench.py --workload yolov4_608_b64_dense --steps 20 --no-cpu-baseline --no-e2e > gpurun_out/bench_dense_$TAG.json 2>> gpurun_out/bench_$TAG.err
 timeout 300 python bench.py --pipeline-depth 1 --steps 100 --no-cpu-baseline --no-e2e > gpurun_out/bench_depth1_$TAG.json 2>> gpurun_out/bench_$TAG.err
+for w in yolov5_640_b128_sparse yolov3_640_b128_sparse yolov4_1280_b128_sparse; do
+  timeout 200 python bench.py --workload $w --steps 30 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_${w}_$TAG.json 2>> gpurun_out/bench_$TAG.err
+done
+timeout 200 python tools/stock_gpu.py 64 5 > gpurun_out/stock_gpu_$TAG.txt 2>> gpurun_out/bench_$TAG.err
+timeout 100 python tools/prof_timeline.py csp608_sparse 64 > gpurun_out/timeline_608_$TAG.txt 2>> gpurun_out/bench_$TAG.err
+timeout 100 python tools/prof_timeline.py csp640_sparse 128 > gpurun_out/timeline_640_$TAG.txt 2>> gpurun_out/bench_$TAG.err
 # launch list of the bench command (per-launch durations, serialised)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>> gpurun_out/bench_$TAG.err
 # DRAM traffic of the three kernels in their natural cache state (single pass, no replay)
