@@ -228,7 +228,7 @@ def run_yolopp(args):
     levels = inputs[0]
     depth = max(1, args.pipeline_depth)
     pipe = Pipeline(p, depth, dev)
-    sess = pipe.sessions[0]
+    sess = yolopp.ops.Session(p, dev)  # a batch that runs alone (batches_in_flight = 0): latency / per-kernel timing
     info = sess.info
     sf = None
 

@@ -92,7 +92,10 @@ typedef struct yolopp_params {
     int32_t rescale;       /* divide boxes by scale_factor[b][0..3] before NMS */
     /* capacity knobs (0 = worst case) */
     int32_t out_capacity;  /* rows of the per-image output block; 0 -> max_per_img (must be > 0 then) */
-    int32_t reserved[7];
+    /* scheduling hint (no effect on results): how many batches the caller keeps in flight on different streams.
+       <= 1: the batch runs alone -> lowest latency schedule; > 1: schedule that lets neighbouring batches overlap */
+    int32_t batches_in_flight;
+    int32_t reserved[6];
 } yolopp_params;
 
 /* Per-detection outputs. All arrays are device memory, [batch][out_capacity] row-major, caller-owned.
@@ -157,10 +160,6 @@ typedef struct yolopp_plan_info {
 } yolopp_plan_info;
 int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info);
 
-/* Host-only self-test (no GPU): runs the decode kernel's tile scheduler map (sequence position -> tile id, the same
- * function the kernel compiles) over [0, total) with `gather` gather tiles and checks that it is a bijection, that
- * gather tiles are evenly spread and that both kinds stay in ascending order. YOLOPP_OK or YOLOPP_E_INVALID. */
-int yolopp_selftest_tile_sequence(int32_t total, int32_t gather);
 
 /*
  * bbox_coder.decode as a standalone elementwise op (YOLOV4BBoxCoder.decode yolov4_bbox_coder.py:39-67 when

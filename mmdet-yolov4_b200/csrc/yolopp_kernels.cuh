@@ -86,7 +86,7 @@ struct DevParams {
     int tma_tiles, ldg_blocks;
     int gather_tiles;        // tiles 0 .. gather_tiles-1 of the decode kernel's enumeration are gather tiles
     unsigned* tile_ctr;      // workspace: next unclaimed position of the decode kernel's tile sequence (set by select_kernel)
-    unsigned dec_first;      // positions handed out statically: every producer warp's first batch needs no atomic
+    unsigned dec_first;      // positions [0, dec_first) of the tile sequence are dealt round-robin, the rest is claimed
     LevelDev lv[MAXL];
     SegDev seg[MAXL];
     // workspace
@@ -855,11 +855,13 @@ __host__ __device__ inline StageGeom stage_geom(int NA) {
     return g;
 }
 // logit of attribute k at position p of the tile (SWIZZLE_128B: 16-byte chunk index XOR (row mod 8))
-__device__ __forceinline__ float tile_at(const unsigned char* stage, uint32_t sub_bytes, int k, int p) {
+__device__ __forceinline__ uint32_t tile_off(uint32_t sub_bytes, int k, int p) {
     const int col = p & 31;
-    const uint32_t off = (uint32_t)(p >> 5) * sub_bytes + (uint32_t)k * 128u +
-                         ((uint32_t)(((col >> 2) ^ (k & 7)) << 4) | (uint32_t)((col & 3) << 2));
-    return *reinterpret_cast<const float*>(stage + off);
+    return (uint32_t)(p >> 5) * sub_bytes + (uint32_t)k * 128u +
+           ((uint32_t)(((col >> 2) ^ (k & 7)) << 4) | (uint32_t)((col & 3) << 2));
+}
+__device__ __forceinline__ float tile_at(const unsigned char* stage, uint32_t sub_bytes, int k, int p) {
+    return *reinterpret_cast<const float*>(stage + tile_off(sub_bytes, k, p));
 }
 
 // Persistent, warp-specialised. Warp 0 is the producer: its 32 lanes work out the coordinates of the CTA's next
@@ -893,18 +895,6 @@ __device__ __forceinline__ long long ypp_globaltimer() {
 // 400 runs differed, at no measurable cost.
 __device__ __forceinline__ void stage_release_fence() { fence_proxy_async(); }
 
-// Position q of the kernel's tile sequence -> tile id. Gather tiles (ids 0 .. G-1) are latency-bound: one warp
-// gathers ~3 anchors x 85 scattered words while the others keep streaming, so they are spread evenly through the
-// sequence (every (total / G)-th position) instead of sitting at its head, where every CTA started with four of
-// them and the stream had a 4 us hole. Bijective on [0, total).
-__host__ __device__ __forceinline__ int dec_tile_of_seq(unsigned q, int total, int G) {
-    if (G == 0) return (int)q;
-    const unsigned period = (unsigned)total / (unsigned)G;  // >= 1
-    const unsigned slot = q / period;
-    if (slot < (unsigned)G && slot * period == q) return (int)slot;  // the slot-th gather tile
-    const unsigned before = slot + 1u < (unsigned)G ? slot + 1u : (unsigned)G;  // gather positions below q
-    return G + (int)(q - before);
-}
 constexpr int DEC_KIND_STOP = 3;  // stage header: the producer has run out of tiles
 
 template <int MODE>
@@ -947,34 +937,62 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
     const int total = P.tma_tiles;
     if (warp < DEC_PWARPS) {
         // ---------------- producers: warp p fills the ring iterations it == p (mod DEC_PWARPS), i.e. stages p, p+2 ----
-        // Tiles are claimed from ONE device-wide counter: SMs do not all stream at the same rate, and with a static
-        // round-robin the CTAs finished between 78 and 102 us (tools/prof_timeline.py). Claims are batched and
-        // guided: a warp takes n = remaining / (4 x producer warps) tiles at a time (at most 32, at least 1), its
-        // lanes work out the n tiles' coordinates in parallel (the level lookup and the integer divisions are a
-        // ~200-instruction dependent chain: done per tile by one lane they cost 11 % of the bandwidth), lane 0
-        // issues them, and the next batch is claimed before the current one is issued so that the atomic's
-        // latency hides behind the waits for empty stages. Towards the end the batches shrink to single tiles and
+        // SMs do not all stream at the same rate: with a purely static round-robin of the tiles the CTAs finished
+        // between 78 and 102 us (tools/prof_timeline.py) and the last 20 us ran far below the HBM rate. Hybrid
+        // schedule: the first 3/4 of the tile sequence is dealt round-robin exactly as before (descriptors of 32
+        // tiles computed across the lanes, no atomics, neighbouring tiles in flight at the same time), the last
+        // quarter is claimed from ONE device-wide counter in small guided batches (remaining / (4 x producer warps),
+        // at most 8, at least 1; the next batch is claimed before the current one is issued so that the atomic's
+        // latency hides behind the waits for empty stages), so fast CTAs keep going until the sequence is empty and
         // all CTAs run dry within a tile or two of each other.
         static_assert(DEC_STAGES % DEC_PWARPS == 0, "a stage must belong to one producer warp");
         const unsigned nprod = gridDim.x * DEC_PWARPS;
+        const unsigned S = P.dec_first;  // positions [0, S) are dealt round-robin, [S, total) come from the counter
         auto batch_size = [&](unsigned seen) -> unsigned {
             const unsigned rem = seen < (unsigned)total ? (unsigned)total - seen : 0u;
             const unsigned n = rem / (4u * nprod);
-            return n < 1u ? 1u : (n > 32u ? 32u : n);
+            return n < 1u ? 1u : (n > 8u ? 8u : n);
         };
-        // first batch: static (the counter starts at nprod * n), so the first tiles are issued without waiting for an atomic
-        unsigned n = batch_size(0u), base = (blockIdx.x * DEC_PWARPS + (unsigned)warp) * n;
+        unsigned ks = 0;      // static phase: tiles of this warp dealt so far
+        bool dyn = false;     // dynamic phase entered
+        unsigned n = 0, base = 0;
         int k = 0;  // tiles this warp has put into the ring
         while (true) {
-            base = __shfl_sync(0xffffffffu, base, 0);
-            // the following batch, claimed now (lane 0 keeps the result to itself until the next round)
-            const unsigned n_next = batch_size(base + n);
-            unsigned base_next = 0u;
-            if (lane == 0) base_next = atomicAdd(P.tile_ctr, n_next);
-            // lane j < n: coordinates of sequence position base + j
+            unsigned q_lane = 0xFFFFFFFFu, n_next = 0u, base_next = 0u;
+            bool to_dyn = dyn;
+            if (!dyn) {
+                // round-robin over the CTAs (neighbouring tiles are in flight at the same time in different CTAs):
+                // this warp's ks-th tile is position blockIdx.x + (ks * DEC_PWARPS + warp) * gridDim.x
+                const unsigned q0 = blockIdx.x + (ks * DEC_PWARPS + (unsigned)warp) * gridDim.x;
+                if (q0 < S) {
+                    const unsigned left = (S - q0 + nprod - 1u) / nprod;
+                    n = left < 32u ? left : 32u;
+                    q_lane = q0 + (unsigned)lane * nprod;
+                    ks += n;
+                    if (n == left) {  // last static batch: claim the first dynamic one now
+                        n_next = batch_size(S);
+                        // (everything dealt statically: nothing to claim, the STOP follows without an atomic's latency)
+                        base_next = (unsigned)total;
+                        if (lane == 0 && S < (unsigned)total) base_next = atomicAdd(P.tile_ctr, n_next);
+                        to_dyn = true;
+                    }
+                } else {
+                    dyn = to_dyn = true;
+                    n = batch_size(S);
+                    if (lane == 0) base = atomicAdd(P.tile_ctr, n);
+                }
+            }
+            if (dyn) {
+                base = __shfl_sync(0xffffffffu, base, 0);
+                // the following batch, claimed now (lane 0 keeps the result to itself until the next round)
+                n_next = batch_size(base + n);
+                if (lane == 0 && base < (unsigned)total) base_next = atomicAdd(P.tile_ctr, n_next);
+                q_lane = base + (unsigned)lane;
+            }
+            // lane j < n: coordinates of its sequence position
             int d_t = -1, d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0, d_hw = 0, d_rbase = 0, d_topk = 0, d_kind = 0;
-            if ((unsigned)lane < n && base + (unsigned)lane < (unsigned)total) {
-                const int t = dec_tile_of_seq(base + (unsigned)lane, total, P.gather_tiles);
+            if ((unsigned)lane < n && q_lane < (unsigned)total) {
+                const int t = (int)q_lane;  // gather tiles (ids below P.gather_tiles) sit at the head of the sequence
                 int best0 = -1;  // the level with the largest first-tile id <= t (gather levels are enumerated first)
                 for (int i = 0; i < P.L; ++i)
                     if (P.lv[i].use_tma && t >= P.lv[i].tile0 && P.lv[i].tile0 > best0) {
@@ -1039,8 +1057,11 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                 }
                 if (t < 0) return;  // STOP posted (uniform: t comes from a shuffle)
             }
-            n = n_next;
-            base = base_next;
+            if (to_dyn) {
+                dyn = true;
+                n = n_next;
+                base = base_next;
+            }
         }
     }
     // ---------------- consumers: whichever warp is free claims the CTA's next ring iteration, in order ------------

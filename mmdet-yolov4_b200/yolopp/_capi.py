@@ -51,7 +51,8 @@ class YoloppParams(ctypes.Structure):
         ('max_per_img', c_int32),
         ('rescale', c_int32),
         ('out_capacity', c_int32),
-        ('reserved', c_int32 * 7),
+        ('batches_in_flight', c_int32),
+        ('reserved', c_int32 * 6),
     ]
 
     # convenience -----------------------------------------------------------------------------
@@ -233,7 +234,7 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = ('yolopp_abi_version', 'yolopp_strerror', 'yolopp_workspace_bytes', 'yolopp_get_bboxes',
-                    'yolopp_get_bboxes_profiled', 'yolopp_describe', 'yolopp_selftest_tile_sequence',
+                    'yolopp_get_bboxes_profiled', 'yolopp_describe',
                     'yolopp_coder_decode', 'yolopp_nms_workspace_bytes', 'yolopp_batched_nms', 'yolopp_multiclass_nms',
                     'yolopp_synth_level',
                     'yolopp_sigmoid', 'yolopp_exp')

@@ -230,7 +230,9 @@ class Pipeline:
     def __init__(self, params, depth=3, device='cuda'):
         self.depth = int(depth)
         self.dev = torch.device(device)
-        self.sessions = [Session(params, device) for _ in range(self.depth)]
+        p = type(params).from_buffer_copy(params)
+        p.batches_in_flight = self.depth  # scheduling hint: decode CTAs retire progressively, neighbours overlap
+        self.sessions = [Session(p, device) for _ in range(self.depth)]
         with torch.cuda.device(self.dev):
             self.streams = [torch.cuda.Stream(self.dev) for _ in range(self.depth)]
             self.done = [torch.cuda.Event() for _ in range(self.depth)]

@@ -30,24 +30,6 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(capi.YoloppParams) == 4 * (7 + 5 * 8 + 8 * 8 * 4 + 11 + 7)
 
 
-def test_decode_tile_scheduler_map_is_a_bijection():
-    """The persistent decode kernel claims positions of a tile SEQUENCE from a device-wide counter; the map
-    position -> tile (gather tiles spread evenly, streamed tiles in order) is compiled for host and device from
-    one source. Every tile must be visited exactly once for any (tiles, gather tiles) split."""
-    lib = capi.load_library()
-    lib.yolopp_selftest_tile_sequence.argtypes = [ctypes.c_int32, ctypes.c_int32]
-    for total, gather in [(1, 0), (1, 1), (2, 1), (7, 7), (23040, 1152), (46080, 2304), (23040, 0), (1000, 999), (1000, 1),
-                          (1000, 501), (1000, 499), (97, 13), (65536, 4097), (201600, 0), (120, 6), (5, 2), (3, 2)]:
-        assert lib.yolopp_selftest_tile_sequence(total, gather) == capi.OK, (total, gather)
-    rng = np.random.RandomState(5)
-    for _ in range(200):
-        total = int(rng.randint(1, 5000))
-        gather = int(rng.randint(0, total + 1))
-        assert lib.yolopp_selftest_tile_sequence(total, gather) == capi.OK, (total, gather)
-    assert lib.yolopp_selftest_tile_sequence(0, 0) == capi.E_INVALID
-    assert lib.yolopp_selftest_tile_sequence(5, 6) == capi.E_INVALID
-
-
 def test_planning_calls_need_no_device():
     lib = capi.load_library()
     p = cases.build_params(dict(cases.CASES['csp608_sparse'], batch=64))

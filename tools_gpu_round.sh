@@ -17,6 +17,10 @@ done
 timeout 200 python tools/stock_gpu.py 64 5 > gpurun_out/stock_gpu_$TAG.txt 2>> gpurun_out/bench_$TAG.err
 timeout 100 python tools/prof_timeline.py csp608_sparse 64 > gpurun_out/timeline_608_$TAG.txt 2>> gpurun_out/bench_$TAG.err
 timeout 100 python tools/prof_timeline.py csp640_sparse 128 > gpurun_out/timeline_640_$TAG.txt 2>> gpurun_out/bench_$TAG.err
+# compute-sanitizer on small end-to-end runs (every kernel, both decode paths)
+for tool in memcheck synccheck; do
+  timeout 300 compute-sanitizer --tool $tool python tools/sanitize.py csp_tiny csp_odd csp608_sparse v3_tiny_nopre 2>&1 | grep -E "ERROR SUMMARY|count|Error" | sort | uniq -c | head -20 > gpurun_out/sanitizer_${tool}_$TAG.txt
+done
 # launch list of the bench command (per-launch durations, serialised)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>> gpurun_out/bench_$TAG.err
 # DRAM traffic of the three kernels in their natural cache state (single pass, no replay)
