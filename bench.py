@@ -256,9 +256,11 @@ def run_yolopp(args):
     barrier()
     sampler.start()
     ev0.record()
+    t_host0 = time.perf_counter()
     for i in range(K):
         slot = pipe.submit(inputs[i % 2], sf)
         ev_done[i].record(pipe.streams[slot])
+    host_submit_ms = (time.perf_counter() - t_host0) * 1e3 / K  # host time to issue one step (not a GPU time)
     pipe.join()
     ev1.record()
     torch.cuda.synchronize(dev)
@@ -376,7 +378,7 @@ def run_yolopp(args):
                             ms_per_batch=statistics.mean(ms))
 
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=max(3, args.warmup),
-                ms_per_step=total_ms_max / K, latency_ms=latency_ms, p50_ms=statistics.median(lat_each),
+                ms_per_step=total_ms_max / K, host_submit_ms_per_step=host_submit_ms, latency_ms=latency_ms, p50_ms=statistics.median(lat_each),
                 p90_ms=lat_each[int(0.9 * (n_lat - 1))], p99_ms=lat_each[int(0.99 * (n_lat - 1))], higher_is_better=True, scaling='weak', vs_baseline=None,
                 dtype='f32', data='synthetic', config=config_dict(args, case, dict(pipeline_depth=depth, pipeline='steps issued round-robin on '
                                                                   f'{depth} CUDA streams, one workspace per stream; latency_ms / p50_ms / p90_ms / p99_ms = one batch alone on one stream')), clocks=clocks, e2e=e2e,
