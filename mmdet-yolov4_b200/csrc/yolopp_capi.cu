@@ -8,6 +8,11 @@
 #include "../../include/yolopp.h"
 #include "yolopp_kernels.cuh"
 
+#ifndef YPP_STATIC_NUM
+#define YPP_STATIC_NUM 3  // statically dealt share of the decode kernel's tile sequence (batch alone)
+#define YPP_STATIC_DEN 4
+#endif
+
 using namespace ypp;
 
 namespace {
@@ -348,7 +353,7 @@ static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs
     d.dec_first = 0;
     if (d.tma_tiles > 0) {
         d.dec_first = p->batches_in_flight > 1 ? (unsigned)d.tma_tiles
-                                               : (unsigned)(((long long)d.tma_tiles * 3 / 4) / dec_grid) * (unsigned)dec_grid;
+                                               : (unsigned)(((long long)d.tma_tiles * YPP_STATIC_NUM / YPP_STATIC_DEN) / dec_grid) * (unsigned)dec_grid;
     }
     YPP_MARK();  // 0: start of select
     if (d.ntopk > 0) {
