@@ -242,6 +242,13 @@ def test_run_to_run_reproducible(batch, runs):
         _, _, again = run_cuda(case, p, levels)
         for k in res:
             np.testing.assert_array_equal(again[k], res[k], err_msg=f'run {r}: run-to-run difference in {k}')
+    # the schedule for overlapped batches (everything dealt statically) gives the same bits as the hybrid one
+    p_static = type(p).from_buffer_copy(p)
+    p_static.batches_in_flight = 3
+    for r in range(5):
+        _, _, other = run_cuda(case, p_static, levels)
+        for k in res:
+            np.testing.assert_array_equal(other[k], res[k], err_msg=f'static schedule, run {r}: difference in {k}')
     p2 = cases.build_params(case, batch=2)
     orc = oracle.get_bboxes(p2, [x[:2].cpu().numpy() for x in levels])
     for b in range(2):
