@@ -10,6 +10,10 @@
  *   AnchorGenerator.grid_anchors (YOLO)           mmdet/core/anchor/anchor_generator.py:207-270,639-665
  *   multiclass_nms                                mmdet/core/post_processing/bbox_nms.py:7-93
  *   mmcv.ops.nms.batched_nms / nms / nms_cpu      third party, mmcv-full 1.3.2..1.4.0 (call site bbox_nms.py:2,84)
+ * and, around the path:
+ *   bbox2result (per-class split of the detections)  mmdet/core/bbox/transforms.py:99-116
+ *   Mish activation forward / backward               mmdet/ops/mish_cuda/src/mish.h:17-29, kernel/mish_cuda.cu:26-71
+ *   channels-last (NHWC) head outputs                mmdet/models/dense_heads/yolocsp_head.py:216-222 (convs_pred output)
  *
  * Conventions
  *   - plain C, no torch types; every pointer marked "device" is a CUDA device pointer on the
@@ -37,7 +41,7 @@
 extern "C" {
 #endif
 
-#define YOLOPP_ABI_VERSION 1
+#define YOLOPP_ABI_VERSION 2
 
 #define YOLOPP_MAX_LEVELS 8
 #define YOLOPP_MAX_ANCHORS 8      /* base anchors per level (mmdet asserts the same count on every level) */
@@ -95,8 +99,16 @@ typedef struct yolopp_params {
     /* scheduling hint (no effect on results): how many batches the caller keeps in flight on different streams.
        <= 1: the batch runs alone -> lowest latency schedule; > 1: schedule that lets neighbouring batches overlap */
     int32_t batches_in_flight;
-    int32_t reserved[6];
+    /* memory layout of the level tensors: YOLOPP_LAYOUT_NCHW = contiguous (B, A*(5+C), H, W) as the reference's
+       convs_pred return them (yolocsp_head.py:216-222); YOLOPP_LAYOUT_NHWC = the channels-last memory of the same
+       logical tensor, (B, H, W, A*(5+C)) — what a cuDNN NHWC convolution writes. With NHWC the 5+C logits of an
+       anchor are contiguous and only the admitted anchors are read (no pass over the whole tensor). */
+    int32_t layout;
+    int32_t reserved[5];
 } yolopp_params;
+
+#define YOLOPP_LAYOUT_NCHW 0
+#define YOLOPP_LAYOUT_NHWC 1
 
 /* Per-detection outputs. All arrays are device memory, [batch][out_capacity] row-major, caller-owned.
    Rows >= count[b] are left untouched. */
@@ -108,6 +120,11 @@ typedef struct yolopp_outputs {
     int32_t* count;     /* [B]          number of detections */
     int32_t* num_candidates; /* [B]     candidates that entered batched_nms (bbox_nms.py:66); may be NULL */
     int32_t* status;    /* [1]          0 or YOLOPP_E_OVERFLOW, data dependent; written every call */
+    /* bbox2result on the device (mmdet/core/bbox/transforms.py:99-116): the same detections grouped by label, each
+       group in score order (== bboxes[labels == c]); group c = rows cls_offsets[b][c] .. cls_offsets[b][c+1]-1.
+       Both NULL or both set. */
+    float* cls_dets;       /* [B][cap][5] */
+    int32_t* cls_offsets;  /* [B][C+1]   (C = 1 when class agnostic) */
 } yolopp_outputs;
 
 /* ABI version of the loaded library. */
@@ -141,21 +158,58 @@ int yolopp_get_bboxes_profiled(const yolopp_params* p, const float* const* level
                                const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream,
                                void* const* events, int num_events);
 
+/*
+ * Plan handle for serving loops: everything yolopp_get_bboxes derives per call (validation, workspace layout, TMA
+ * tensor maps, grid sizes) is computed once for a fixed set of buffers; yolopp_plan_run is then three kernel
+ * launches and nothing else on the host. The handle is ordinary host memory owned by the caller (create / destroy),
+ * holds no device memory and no global state; the buffers it was created for must stay alive while it is used.
+ * One plan may be run on any stream, but not concurrently with itself (it owns its workspace).
+ */
+typedef struct yolopp_plan yolopp_plan;
+int yolopp_plan_create(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
+                       const yolopp_outputs* out, void* workspace, size_t workspace_bytes, yolopp_plan** plan);
+int yolopp_plan_run(const yolopp_plan* plan, void* stream);
+/* as yolopp_get_bboxes_profiled */
+int yolopp_plan_run_profiled(const yolopp_plan* plan, void* stream, void* const* events, int num_events);
+void yolopp_plan_destroy(yolopp_plan* plan);
+
+/*
+ * Stage entries = the parity taps of SURVEY.md A.3. Same params / level tensors / workspace as yolopp_get_bboxes.
+ *
+ * yolopp_topk_conf: the objectness top-k alone (yolocsp_head.py:348-355: `_, topk_inds = conf_pred.topk(nms_pre)`;
+ *   yolo_head.py:281-302 per level). topk_inds DEVICE [B][R] int32, R = yolopp_plan_info.rows_per_image: row r of
+ *   image b = concatenated anchor index (level-major, (y*W+x)*A+a) of the r-th row that enters multiclass_nms, in
+ *   canonical (conf desc, anchor asc) order per top-k segment; segments without a top-k list their anchors in
+ *   order.
+ *
+ * yolopp_decode: top-k + fused decode, i.e. the tensors that enter multiclass_nms / batched_nms (bbox_nms.py:34-67):
+ *   boxes  DEVICE [B][R][4]  decoded (and rescaled) box of every row
+ *   scores DEVICE [B][R][C]  score of candidate (row, class) — cls*conf (CSP) / cls*score_factor (V3) — as fp32, and
+ *          the bit pattern 0xFFFFFFFF (a NaN) where the pair is NOT a candidate (failed score_thr / conf_thr); the
+ *          reference's candidate list `inds = valid_mask.nonzero()` is the row-major order of the non-NaN entries.
+ *   topk_inds as above (may be NULL).
+ */
+int yolopp_topk_conf(const yolopp_params* p, const float* const* level_ptrs, int32_t* topk_inds, void* workspace,
+                     size_t workspace_bytes, void* stream);
+int yolopp_decode(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors, float* boxes,
+                  float* scores, int32_t* topk_inds, void* workspace, size_t workspace_bytes, void* stream);
+
 /* How a configuration is executed (for DESIGN.md / bench.py roofline arithmetic). */
 typedef struct yolopp_plan_info {
     int32_t anchors_per_image;   /* N */
     int32_t rows_per_image;      /* R: rows entering multiclass_nms */
     int32_t num_attrib;          /* 5 + C (5 when class agnostic) */
-    int32_t tma_level_mask;      /* bit l set: level l is streamed by the TMA decode kernel */
+    int32_t tma_level_mask;      /* bit l set: level l is streamed by the TMA decode kernel (plain or quad-row tiles) */
     int32_t tma_tiles;           /* tiles of the TMA decode kernel */
     int32_t ldg_blocks;          /* blocks of the generic decode kernel */
     int32_t decode_smem_bytes;   /* dynamic shared memory of the TMA decode kernel */
     int32_t decode_ctas_per_sm;
     int32_t kernel_launches;     /* kernels launched per yolopp_get_bboxes call */
-    int32_t reserved0;
+    int32_t dense_tiles;         /* 32-position tiles of the dense-admission decode kernel */
     int64_t tma_bytes_per_image; /* algorithmic bytes read per image by the persistent decode kernel (TMA tiles +
                                     gather tiles of unaligned levels): 4*A*(5+C)*sum(HW) over its levels */
-    int64_t ldg_bytes_per_image; /* ... by the generic decode kernel (dense admission) */
+    int64_t ldg_bytes_per_image; /* ... by the other decode kernels (dense admission, > 256 attributes; NHWC: the
+                                    admitted rows, 4*(5+C)*R) */
     int64_t workspace_bytes;
 } yolopp_plan_info;
 int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info);
@@ -202,6 +256,18 @@ int yolopp_multiclass_nms(const float* multi_bboxes, int boxes_per_class, const 
                           int nms_offset, int split_thr, int class_agnostic, int nms_max_num, int max_num, float* dets,
                           int64_t* labels, int64_t* flat_inds, int32_t* num_keep, int32_t* num_candidates,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Mish activation (mmdet/ops/mish_cuda): y = x * tanh(softplus(x)), softplus threshold 20 (mish.h:15-19);
+ * backward dx = dy * (x * (1 - tanh(sp)^2) * (1 - exp(-sp)) + tanh(sp)) (mish.h:22-29). Half / bfloat16 compute in
+ * fp32 (mish.h:33-50). Elementwise over n contiguous elements, 16-byte aligned pointers, on `stream` (the
+ * reference launches on the default stream: mish_cuda.cu:53,70).
+ */
+#define YOLOPP_DTYPE_F32 0
+#define YOLOPP_DTYPE_F16 1
+#define YOLOPP_DTYPE_BF16 2
+int yolopp_mish_forward(const void* in, void* out, int64_t n, int dtype, void* stream);
+int yolopp_mish_backward(const void* grad_out, const void* in, void* grad_in, int64_t n, int dtype, void* stream);
 
 /*
  * Bit-reproducible synthetic head tensors (bench / tests): element i of a level tensor gets

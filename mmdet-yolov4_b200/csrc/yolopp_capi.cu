@@ -1,12 +1,16 @@
 // yolopp_capi.cu — the C ABI of include/yolopp.h: validation, workspace plan, TMA descriptors, launches.
 // Pure CUDA runtime + one driver entry point (cuTensorMapEncodeTiled, resolved through the runtime so the
-// library does not link libcuda). No torch, no allocation, no host synchronisation.
+// library does not link libcuda). No torch, no device allocation, no host synchronisation.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
 
 #include "../../include/yolopp.h"
 #include "yolopp_kernels.cuh"
+#include "yolopp_mish.cuh"
 
 #ifndef YPP_STATIC_NUM
 #define YPP_STATIC_NUM 3  // statically dealt share of the decode kernel's tile sequence (batch alone)
@@ -46,6 +50,7 @@ struct Plan {
     size_t total;
     size_t dec_smem, sel_smem, nms_smem;
     int dec_ctas_per_sm;
+    int rows_blocks;  // NHWC: blocks of the row-driven decode kernel
 };
 
 #define CHECK_ARG(cond) \
@@ -53,11 +58,14 @@ struct Plan {
         if (!(cond)) return false; \
     } while (0)
 
+constexpr size_t SMEM_LIMIT = 227 * 1024;  // dynamic shared memory a CTA may opt into on sm_100
+
 // Validates the params and lays the workspace out. Level pointers are filled in by the caller.
 bool make_plan(const yolopp_params* p, Plan* plan) {
     CHECK_ARG(p != nullptr);
     CHECK_ARG(p->abi_version == YOLOPP_ABI_VERSION);
     CHECK_ARG(p->mode == YOLOPP_MODE_CSP || p->mode == YOLOPP_MODE_V3);
+    CHECK_ARG(p->layout == YOLOPP_LAYOUT_NCHW || p->layout == YOLOPP_LAYOUT_NHWC);
     CHECK_ARG(p->batch >= 1 && p->batch <= 65535);
     CHECK_ARG(p->num_levels >= 1 && p->num_levels <= YOLOPP_MAX_LEVELS);
     CHECK_ARG(p->num_anchors >= 1 && p->num_anchors <= YOLOPP_MAX_ANCHORS);
@@ -77,6 +85,7 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     d.C = C;
     d.NA = NA;
     d.agnostic = agn ? 1 : 0;
+    d.nhwc = p->layout == YOLOPP_LAYOUT_NHWC ? 1 : 0;
     d.score_thr = p->score_thr;
     d.conf_thr = p->conf_thr;
     d.iou_thr = p->iou_thr;
@@ -108,7 +117,7 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
         CHECK_ARG(n_off < (1 << 24));
     }
     d.N = (int)n_off;
-    d.M_pad = (int)m_off + 64;  // slack: the rank row of a partial last tile is fetched whole
+    d.M_pad = (int)m_off + 72;  // slack: the rank row of a partial last tile is fetched whole (+ aligned superset)
 
     // top-k segments: CSP = one over all levels (yolocsp_head.py:350-355); V3 = one per level (yolo_head.py:281-302)
     d.nsegs = (p->mode == YOLOPP_MODE_CSP) ? 1 : d.L;
@@ -126,12 +135,9 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
         sg.N = (int)n;
         sg.m_begin = d.lv[sg.first_level].m_off;
         sg.m_end = d.lv[sg.first_level + sg.num_levels - 1].m_off + d.lv[sg.first_level + sg.num_levels - 1].HW * d.A;
-        sg.has_topk = (p->nms_pre > 0 && p->nms_pre < n) ? 1 : 0;
+        sg.has_topk = (p->nms_pre > 0 && p->nms_pre < n) ? 1 : 0;  // any k: beyond SEL_MAX_K the sort runs in chunks
         sg.k = sg.has_topk ? p->nms_pre : (int)n;
-        if (sg.has_topk) {
-            CHECK_ARG(sg.k <= SEL_MAX_K);  // smem sort capacity of the select kernel
-            d.topk_segs[d.ntopk++] = s;
-        }
+        if (sg.has_topk) d.topk_segs[d.ntopk++] = s;
         sg.row_off = (int)row_off;
         row_off += sg.k;
     }
@@ -152,51 +158,90 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     for (int s = 0; s < d.nsegs; ++s)
         if (d.seg[s].has_topk && d.seg[s].k > max_k) max_k = d.seg[s].k;
     int kcap = 4096;  // >= 2k: room for the survivors of the sampled pivot (~1.5k expected)
-    while (kcap < 2 * max_k) kcap <<= 1;
-    d.sel_kcap = kcap;
+    while (kcap < 2 * max_k && kcap < 2 * SEL_MAX_K) kcap <<= 1;
+    d.sel_kcap = kcap;  // (nms_pre > SEL_MAX_K: chunks of kcap / 2 sorted keys)
     plan->sel_smem = (size_t)kcap * 8 * 2;  // sorted keys + scatter scratch
-    {
-        // staging buffer of the fast path: the largest top-k segment's objectness logits, when they fit
+    d.sel_stage = 0;
+    d.sel_stride = 1;
+    if (max_k <= SEL_MAX_K) {
+        // staging buffer of the fast path: the largest top-k segment's objectness logits when they fit (<= 32768
+        // slots), else a 1-in-2^j sample of them (<= 16384 slots) and a streamed pass over the segment
         int max_m = 0;
         for (int s = 0; s < d.nsegs; ++s)
             if (d.seg[s].has_topk && d.seg[s].m_end - d.seg[s].m_begin > max_m) max_m = d.seg[s].m_end - d.seg[s].m_begin;
-        d.sel_stage = 0;
-        if (max_m > 0 && max_m <= 32768 && plan->sel_smem + (size_t)max_m * 4 <= 200 * 1024) {
-            d.sel_stage = max_m;
-            plan->sel_smem += (size_t)max_m * 4;
+        if (max_m > 0) {
+            int slots = max_m;
+            if (!(max_m <= 32768 && plan->sel_smem + (size_t)max_m * 4 <= 200 * 1024)) {
+                int stride = 2;
+                while ((max_m + stride - 1) / stride > 16384) stride <<= 1;
+                d.sel_stride = stride;
+                slots = (max_m + stride - 1) / stride;
+            }
+            d.sel_stage = slots;
+            plan->sel_smem += (size_t)slots * 4;
         }
     }
+    CHECK_ARG(plan->sel_smem <= SMEM_LIMIT);
     plan->nms_smem = (size_t)NMS_KCAP * 8 * 2 + (size_t)d.keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)d.keep_cap * 28 +
                      (size_t)d.C * 4;
     plan->nms_smem = align_up(plan->nms_smem, 16);
     d.nms_rowkeys_off = (int)plan->nms_smem;
     plan->nms_smem += (size_t)NMS_KCAP * 8;
     plan->nms_smem = nms_add_stage(d, plan->nms_smem);
+    CHECK_ARG(plan->nms_smem <= SMEM_LIMIT);
 
     // which kernel decodes which level
-    const StageGeom geom = stage_geom(NA);
-    plan->dec_smem = 1024 /*alignment slack*/ + 1024 /*barriers*/ + (size_t)DEC_STAGES * geom.stage_bytes;
-    const bool tma_fits = plan->dec_smem <= 200 * 1024 && NA <= 256;
-    plan->dec_ctas_per_sm = plan->dec_smem <= 110 * 1024 ? 2 : 1;
-    int tma_tiles = 0, ldg_blocks = 0;
-    // persistent decode kernel: sparse-admission levels — TMA tiles where the plane stride is 16-byte aligned,
-    // gather tiles (enumerated first, their latency hides under the streaming) where it is not
-    for (int l = 0; l < d.L; ++l) {
-        LevelDev& lv = d.lv[l];
-        const SegDev& sg = d.seg[lv.seg];
-        const bool sparse = sg.has_topk && (long long)sg.k * 4 <= sg.N;
-        lv.use_tma = (tma_fits && sparse) ? ((lv.HW % 4 == 0) ? 1 : 2) : 0;
-    }
-    for (int pass = 2; pass >= 0; --pass) {
+    d.dec_quad = 0;
+    int tma_tiles = 0, ldg_blocks = 0, dense_tiles = 0;
+    if (d.nhwc) {
+        // channels-last: the row-driven kernel serves every level
+        for (int l = 0; l < d.L; ++l) d.lv[l].use_tma = 0;
+        plan->rows_blocks = (int)(((long long)d.B * d.R + ROWS_WARPS - 1) / ROWS_WARPS);
+    } else {
+        bool tma_fits = NA <= 256;
+        for (int l = 0; l < d.L && tma_fits; ++l) {
+            const SegDev& sg = d.seg[d.lv[l].seg];
+            if (sg.has_topk && (long long)sg.k * 4 <= sg.N && d.lv[l].HW % 4 != 0) d.dec_quad = 1;
+        }
+        StageGeom geom = stage_geom(NA, d.dec_quad);
+        plan->dec_smem = 1024 /*alignment slack*/ + 1024 /*barriers*/ + (size_t)DEC_STAGES * geom.stage_bytes;
+        tma_fits = tma_fits && plan->dec_smem <= 200 * 1024;
+        plan->dec_ctas_per_sm = plan->dec_smem <= 110 * 1024 ? 2 : 1;
+        // persistent decode kernel: sparse-admission levels — TMA tiles where the plane stride is 16-byte aligned,
+        // quad-row TMA tiles where it is not
         for (int l = 0; l < d.L; ++l) {
             LevelDev& lv = d.lv[l];
-            if (lv.use_tma != pass) continue;
-            if (lv.use_tma) {
+            const SegDev& sg = d.seg[lv.seg];
+            const bool sparse = sg.has_topk && (long long)sg.k * 4 <= sg.N;
+            lv.use_tma = (tma_fits && sparse) ? ((lv.HW % 4 == 0) ? 1 : 3) : 0;
+            lv.dense = (!lv.use_tma && !sparse) ? 1 : 0;
+            lv.qrows = (int)(((long long)d.B * d.A * NA) / 4);
+        }
+#ifdef YPP_QUAD_LAST
+        const int order[3] = {1, 3, -1};
+#else
+        const int order[3] = {3, 1, -1};  // unaligned levels first (they are the small, coarse levels)
+#endif
+        for (int pi = 0; pi < 2; ++pi) {
+            for (int l = 0; l < d.L; ++l) {
+                LevelDev& lv = d.lv[l];
+                if (lv.use_tma != order[pi]) continue;
                 lv.tpp = (lv.HW + TILE_T - 1) / TILE_T;
                 lv.tile0 = tma_tiles;
                 long long t = (long long)lv.tpp * d.B * d.A;
                 CHECK_ARG(tma_tiles + t < (1ll << 30));
                 tma_tiles += (int)t;
+            }
+        }
+        for (int l = 0; l < d.L; ++l) {
+            LevelDev& lv = d.lv[l];
+            if (lv.use_tma) continue;
+            if (lv.dense) {
+                lv.tpp = (lv.HW + 31) / 32;
+                lv.tile0 = dense_tiles;
+                long long t = (long long)lv.tpp * d.B * d.A;
+                CHECK_ARG(dense_tiles + t < (1ll << 30));
+                dense_tiles += (int)t;
             } else {
                 lv.tpp = (lv.HW + 127) / 128;
                 lv.tile0 = ldg_blocks;
@@ -207,10 +252,8 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
         }
     }
     d.tma_tiles = tma_tiles;
-    d.gather_tiles = 0;  // enumerated first (pass 2 above)
-    for (int l = 0; l < d.L; ++l)
-        if (d.lv[l].use_tma == 2) d.gather_tiles += d.lv[l].tpp * d.B * d.A;
     d.ldg_blocks = ldg_blocks;
+    d.dense_tiles = dense_tiles;
 
     // workspace layout
     size_t off = 0;
@@ -251,32 +294,226 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;  // resolved once; the driver symbol never changes
-    if (fn) return fn;
+    static std::atomic<EncodeTiledFn> fn{nullptr};  // resolved once; the driver symbol never changes
+    EncodeTiledFn f = fn.load(std::memory_order_acquire);
+    if (f) return f;
     void* sym = nullptr;
     cudaDriverEntryPointQueryResult qres;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess) return nullptr;
     if (qres != cudaDriverEntryPointSuccess) return nullptr;
-    fn = (EncodeTiledFn)sym;
-    return fn;
+    fn.store((EncodeTiledFn)sym, std::memory_order_release);
+    return (EncodeTiledFn)sym;
 }
 
 inline int cuda_rc(cudaError_t e) { return e == cudaSuccess ? YOLOPP_OK : YOLOPP_E_CUDA + (int)e; }
 
-int device_check() {
+// Per-device, once per process: sm_100 check, SM count, and the opt-in to large dynamic shared memory for the
+// kernels that need it. The attribute is set to the DEVICE MAXIMUM (not a call's own size), so concurrent callers
+// with different configurations can never lower it under each other; the only process-wide state of the library
+// is this idempotent initialisation.
+struct DeviceInfo {
+    int rc;
+    int sms;
+};
+DeviceInfo device_info() {
+    static std::atomic<int> state[64];  // 0: unknown, else (sms << 8) | 1
+    DeviceInfo di = {YOLOPP_E_NO_DEVICE, 148};
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return YOLOPP_E_NO_DEVICE;
-    int major = 0;
-    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return YOLOPP_E_NO_DEVICE;
-    if (major != 10) return YOLOPP_E_NO_DEVICE;  // sm_100a only: no other code path exists
+    if (cudaGetDevice(&dev) != cudaSuccess) return di;
+    if (dev >= 0 && dev < 64) {
+        const int st = state[dev].load(std::memory_order_acquire);
+        if (st) {
+            di.rc = YOLOPP_OK;
+            di.sms = st >> 8;
+            return di;
+        }
+    }
+    int major = 0, sms = 148, optin = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return di;
+    if (major != 10) return di;  // sm_100a only: no other code path exists
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    if (e != cudaSuccess) {
+        di.rc = cuda_rc(e);
+        return di;
+    }
+    if (dev >= 0 && dev < 64) state[dev].store((sms << 8) | 1, std::memory_order_release);
+    di.rc = YOLOPP_OK;
+    di.sms = sms;
+    return di;
+}
+
+}  // namespace
+
+// Everything a call needs, derived once: the caller-visible handle of yolopp_plan_create and the stack object of
+// the one-shot entry points.
+struct yolopp_plan {
+    Plan plan;
+    TmapPack maps;
+    int dec_grid;
+    int stop_after;  // 0: whole path, 1: after the top-k, 2: after the decode (stage entries)
+};
+
+namespace {
+
+int prepare(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors, const yolopp_outputs* out,
+            void* workspace, size_t workspace_bytes, int stop_after, yolopp_plan* pl) {
+    Plan& plan = pl->plan;
+    if (!make_plan(p, &plan)) return YOLOPP_E_INVALID;
+    if (!level_ptrs) return YOLOPP_E_INVALID;
+    if (stop_after == 0 && (!out || !out->dets || !out->labels || !out->count || !out->status)) return YOLOPP_E_INVALID;
+    if (out && ((out->cls_dets == nullptr) != (out->cls_offsets == nullptr))) return YOLOPP_E_INVALID;
+    if (p->rescale && !scale_factors && stop_after != 1) return YOLOPP_E_INVALID;
+    if (!workspace || workspace_bytes < plan.total) return YOLOPP_E_WORKSPACE;
+    if (((uintptr_t)workspace & 255) != 0) return YOLOPP_E_INVALID;
+    const DeviceInfo di = device_info();
+    if (di.rc != YOLOPP_OK) return di.rc;
+    pl->stop_after = stop_after;
+    DevParams& d = plan.d;
+    for (int l = 0; l < d.L; ++l) {
+        if (!level_ptrs[l] || ((uintptr_t)level_ptrs[l] & 3) != 0) return YOLOPP_E_INVALID;
+        d.lv[l].ptr = level_ptrs[l];
+        // a tensor map needs a 16-byte aligned base: otherwise the level's tiles are gathered
+        if (d.lv[l].use_tma && ((uintptr_t)level_ptrs[l] & 15) != 0) d.lv[l].use_tma = 2;
+    }
+    bind_workspace(&plan, workspace);
+    d.scale = scale_factors;
+    if (out) {
+        d.o_dets = out->dets;
+        d.o_labels = (long long*)out->labels;
+        d.o_anchors = out->anchors;
+        d.o_rows = out->rows;
+        d.o_count = out->count;
+        d.o_ncand = out->num_candidates;
+        d.o_status = out->status;
+        d.o_cls_dets = out->cls_dets;
+        d.o_cls_offsets = out->cls_offsets;
+    }
+    // decode kernel's grid and the statically dealt head of its tile sequence (select_kernel initialises the
+    // scheduler counter with it). A batch that runs alone: 3/4 of the tiles, a whole number of rounds over the
+    // CTAs, the rest is claimed dynamically so that all CTAs run dry together. Batches in flight on several
+    // streams (params.batches_in_flight > 1): everything is dealt statically — CTAs then retire progressively
+    // and the per-image kernels of the neighbouring batches move onto the freed SMs while the rest of the decode
+    // kernel still streams.
+    int dec_grid = di.sms * plan.dec_ctas_per_sm;
+    if (dec_grid > d.tma_tiles) dec_grid = d.tma_tiles;
+    pl->dec_grid = dec_grid;
+    d.dec_first = 0;
+    if (d.tma_tiles > 0) {
+        d.dec_first = p->batches_in_flight > 1 ? (unsigned)d.tma_tiles
+                                               : (unsigned)(((long long)d.tma_tiles * YPP_STATIC_NUM / YPP_STATIC_DEN) / dec_grid) * (unsigned)dec_grid;
+        // the persistent kernel only takes levels whose segment ran a top-k, so select_kernel (which initialises
+        // the scheduler counter) runs
+        if (d.ntopk == 0) return YOLOPP_E_INVALID;
+        EncodeTiledFn enc = get_encode_fn();
+        if (!enc) return YOLOPP_E_NO_DEVICE;
+        memset(&pl->maps, 0, sizeof(pl->maps));
+        const StageGeom geom = stage_geom(d.NA, d.dec_quad);
+        for (int l = 0; l < d.L; ++l) {
+            const LevelDev& lv = d.lv[l];
+            CUresult r = CUDA_SUCCESS;
+            if (lv.use_tma == 1) {
+                // rows = planes, one (NA x 32) box = all attributes of 32 positions
+                cuuint64_t gdim[2] = {(cuuint64_t)lv.HW, (cuuint64_t)d.B * d.A * d.NA};
+                cuuint64_t gstr[1] = {(cuuint64_t)lv.HW * 4};
+                cuuint32_t box[2] = {(cuuint32_t)TILE_SUB, (cuuint32_t)d.NA};
+                cuuint32_t estr[2] = {1, 1};
+                r = enc(&pl->maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)lv.ptr, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            } else if (lv.use_tma == 3) {
+                // plane stride 4 * HW bytes is not a multiple of 16: view the tensor as rows of FOUR planes (stride
+                // 16 * HW bytes); a box = 32 positions of one plane-in-row x the rows a slab spans
+                if (lv.qrows < 1) {
+                    d.lv[l].use_tma = 2;
+                    continue;
+                }
+                cuuint64_t gdim[2] = {(cuuint64_t)lv.HW * 4, (cuuint64_t)lv.qrows};
+                cuuint64_t gstr[1] = {(cuuint64_t)lv.HW * 16};
+                cuuint32_t box[2] = {(cuuint32_t)TILE_SUB, (cuuint32_t)geom.quad_rows};
+                cuuint32_t estr[2] = {1, 1};
+                r = enc(&pl->maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)lv.ptr, gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            }
+            if (r != CUDA_SUCCESS) return YOLOPP_E_CUDA + 999;
+        }
+    }
     return YOLOPP_OK;
 }
 
-int sm_count() {
-    int dev = 0, n = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    return n;
+int launch(const yolopp_plan* pl, cudaStream_t stream, void* const* events, int num_events) {
+    const Plan& plan = pl->plan;
+    const DevParams& d = plan.d;
+    cudaError_t e;
+    int ev_i = 0;
+#define YPP_MARK()                                                                          \
+    do {                                                                                    \
+        if (events && ev_i < num_events) {                                                  \
+            e = cudaEventRecord((cudaEvent_t)events[ev_i++], stream);                       \
+            if (e != cudaSuccess) return cuda_rc(e);                                        \
+        }                                                                                   \
+    } while (0)
+    YPP_MARK();  // 0: start of select
+    if (d.ntopk > 0) {
+        // (block (0, 0) also clears the status word and initialises the decode kernel's tile counter)
+        select_kernel<<<dim3(d.ntopk, d.B), SEL_THREADS, plan.sel_smem, stream>>>(d);
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    } else if (d.o_status) {
+        e = cudaMemsetAsync(d.o_status, 0, sizeof(int32_t), stream);
+        if (e != cudaSuccess) return cuda_rc(e);
+    }
+    if (pl->stop_after == 1) {
+        // rows of the segments that keep every anchor (decode would write them): the anchors in order
+        if (d.ntopk < d.nsegs) {
+            const long long n = (long long)d.B * d.R;
+            fill_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d);
+            if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+        }
+        return YOLOPP_OK;
+    }
+    YPP_MARK();  // 1: start of decode (persistent TMA kernel / NHWC rows kernel)
+    if (d.tma_tiles > 0) {
+        if (d.mode == YOLOPP_MODE_CSP)
+            decode_tma_kernel<0><<<pl->dec_grid, DEC_THREADS, plan.dec_smem, stream>>>(d, pl->maps);
+        else
+            decode_tma_kernel<1><<<pl->dec_grid, DEC_THREADS, plan.dec_smem, stream>>>(d, pl->maps);
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    }
+    if (d.nhwc) {
+        if (d.mode == YOLOPP_MODE_CSP)
+            decode_rows_kernel<0><<<plan.rows_blocks, 32 * ROWS_WARPS, 0, stream>>>(d);
+        else
+            decode_rows_kernel<1><<<plan.rows_blocks, 32 * ROWS_WARPS, 0, stream>>>(d);
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    }
+    YPP_MARK();  // 2: start of decode (other levels)
+    if (d.dense_tiles > 0) {
+        const int blocks = (d.dense_tiles + DENSE_WARPS - 1) / DENSE_WARPS;
+        if (d.mode == YOLOPP_MODE_CSP)
+            decode_dense_kernel<0><<<blocks, 32 * DENSE_WARPS, 0, stream>>>(d);
+        else
+            decode_dense_kernel<1><<<blocks, 32 * DENSE_WARPS, 0, stream>>>(d);
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    }
+    if (d.ldg_blocks > 0) {
+        if (d.mode == YOLOPP_MODE_CSP)
+            decode_ldg_kernel<0><<<d.ldg_blocks, 128, 0, stream>>>(d);
+        else
+            decode_ldg_kernel<1><<<d.ldg_blocks, 128, 0, stream>>>(d);
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    }
+    if (pl->stop_after == 2) return YOLOPP_OK;
+    YPP_MARK();  // 3: start of the per-image NMS
+    nms_image_kernel<<<d.B, NMS_THREADS, plan.nms_smem, stream>>>(d);
+    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    YPP_MARK();  // 4: end
+#undef YPP_MARK
+    return YOLOPP_OK;
 }
 
 }  // namespace
@@ -302,126 +539,80 @@ size_t yolopp_workspace_bytes(const yolopp_params* p) {
     return plan.total;
 }
 
-static int run_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
-                          const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream_,
-                          void* const* events, int num_events) {
-    Plan plan;
-    if (!make_plan(p, &plan)) return YOLOPP_E_INVALID;
-    if (!level_ptrs || !out || !out->dets || !out->labels || !out->count || !out->status) return YOLOPP_E_INVALID;
-    if (p->rescale && !scale_factors) return YOLOPP_E_INVALID;
-    if (!workspace || workspace_bytes < plan.total) return YOLOPP_E_WORKSPACE;
-    if (((uintptr_t)workspace & 255) != 0) return YOLOPP_E_INVALID;
-    int rc = device_check();
-    if (rc != YOLOPP_OK) return rc;
-    cudaStream_t stream = (cudaStream_t)stream_;
-    DevParams& d = plan.d;
-    for (int l = 0; l < d.L; ++l) {
-        if (!level_ptrs[l]) return YOLOPP_E_INVALID;
-        d.lv[l].ptr = level_ptrs[l];
-        if (d.lv[l].use_tma == 1 && ((uintptr_t)level_ptrs[l] & 15) != 0) return YOLOPP_E_INVALID;
-    }
-    bind_workspace(&plan, workspace);
-    d.scale = scale_factors;
-    d.o_dets = out->dets;
-    d.o_labels = (long long*)out->labels;
-    d.o_anchors = out->anchors;
-    d.o_rows = out->rows;
-    d.o_count = out->count;
-    d.o_ncand = out->num_candidates;
-    d.o_status = out->status;
-
-    cudaError_t e;
-    int ev_i = 0;
-#define YPP_MARK()                                                                          \
-    do {                                                                                    \
-        if (events && ev_i < num_events) {                                                  \
-            e = cudaEventRecord((cudaEvent_t)events[ev_i++], stream);                       \
-            if (e != cudaSuccess) return cuda_rc(e);                                        \
-        }                                                                                   \
-    } while (0)
-    e = cudaMemsetAsync(out->status, 0, sizeof(int32_t), stream);
-    if (e != cudaSuccess) return cuda_rc(e);
-
-    // decode kernel's grid and the statically dealt head of its tile sequence (select_kernel initialises the
-    // scheduler counter with it). A batch that runs alone: 3/4 of the tiles, a whole number of rounds over the
-    // CTAs, the rest is claimed dynamically so that all CTAs run dry together. Batches in flight on several
-    // streams (params.batches_in_flight > 1): everything is dealt statically — CTAs then retire progressively
-    // (78 .. 102 us at 608^2 b64) and the per-image kernels of the neighbouring batches move onto the freed SMs
-    // while the rest of the decode kernel still streams; measured 550 k img/s against 530 k with the dynamic tail.
-    int dec_grid = sm_count() * plan.dec_ctas_per_sm;
-    if (dec_grid > d.tma_tiles) dec_grid = d.tma_tiles;
-    d.dec_first = 0;
-    if (d.tma_tiles > 0) {
-        d.dec_first = p->batches_in_flight > 1 ? (unsigned)d.tma_tiles
-                                               : (unsigned)(((long long)d.tma_tiles * YPP_STATIC_NUM / YPP_STATIC_DEN) / dec_grid) * (unsigned)dec_grid;
-    }
-    YPP_MARK();  // 0: start of select
-    if (d.ntopk > 0) {
-        e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.sel_smem);
-        if (e != cudaSuccess) return cuda_rc(e);
-        select_kernel<<<dim3(d.ntopk, d.B), SEL_THREADS, plan.sel_smem, stream>>>(d);
-        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
-    }
-    YPP_MARK();  // 1: start of decode (TMA)
-    if (d.tma_tiles > 0) {
-        EncodeTiledFn enc = get_encode_fn();
-        if (!enc) return YOLOPP_E_NO_DEVICE;
-        TmapPack maps;
-        memset(&maps, 0, sizeof(maps));
-        for (int l = 0; l < d.L; ++l) {
-            if (d.lv[l].use_tma != 1) continue;
-            cuuint64_t gdim[2] = {(cuuint64_t)d.lv[l].HW, (cuuint64_t)d.B * d.A * d.NA};
-            cuuint64_t gstr[1] = {(cuuint64_t)d.lv[l].HW * 4};
-            cuuint32_t box[2] = {(cuuint32_t)TILE_SUB, (cuuint32_t)d.NA};
-            cuuint32_t estr[2] = {1, 1};
-            CUresult r = enc(&maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)d.lv[l].ptr, gdim, gstr, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return YOLOPP_E_CUDA + 999;
-        }
-        // the persistent kernel only takes levels whose segment ran a top-k, so select_kernel (which initialises
-        // the scheduler counter) has run
-        if (d.ntopk == 0) return YOLOPP_E_INVALID;
-        const int grid = dec_grid;
-        if (d.mode == YOLOPP_MODE_CSP) {
-            e = cudaFuncSetAttribute(decode_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.dec_smem);
-            if (e != cudaSuccess) return cuda_rc(e);
-            decode_tma_kernel<0><<<grid, DEC_THREADS, plan.dec_smem, stream>>>(d, maps);
-        } else {
-            e = cudaFuncSetAttribute(decode_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.dec_smem);
-            if (e != cudaSuccess) return cuda_rc(e);
-            decode_tma_kernel<1><<<grid, DEC_THREADS, plan.dec_smem, stream>>>(d, maps);
-        }
-        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
-    }
-    YPP_MARK();  // 2: start of decode (LDG)
-    if (d.ldg_blocks > 0) {
-        if (d.mode == YOLOPP_MODE_CSP)
-            decode_ldg_kernel<0><<<d.ldg_blocks, 128, 0, stream>>>(d);
-        else
-            decode_ldg_kernel<1><<<d.ldg_blocks, 128, 0, stream>>>(d);
-        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
-    }
-    YPP_MARK();  // 3: start of the per-image NMS
-    e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.nms_smem);
-    if (e != cudaSuccess) return cuda_rc(e);
-    nms_image_kernel<<<d.B, NMS_THREADS, plan.nms_smem, stream>>>(d);
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
-    YPP_MARK();  // 4: end
-#undef YPP_MARK
-    return YOLOPP_OK;
-}
-
 int yolopp_get_bboxes(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
                       const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream) {
-    return run_get_bboxes(p, level_ptrs, scale_factors, out, workspace, workspace_bytes, stream, nullptr, 0);
+    yolopp_plan pl;
+    const int rc = prepare(p, level_ptrs, scale_factors, out, workspace, workspace_bytes, 0, &pl);
+    if (rc != YOLOPP_OK) return rc;
+    return launch(&pl, (cudaStream_t)stream, nullptr, 0);
 }
 
 int yolopp_get_bboxes_profiled(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
                                const yolopp_outputs* out, void* workspace, size_t workspace_bytes, void* stream,
                                void* const* events, int num_events) {
     if (!events || num_events < YOLOPP_NUM_STAGE_EVENTS) return YOLOPP_E_INVALID;
-    return run_get_bboxes(p, level_ptrs, scale_factors, out, workspace, workspace_bytes, stream, events, num_events);
+    yolopp_plan pl;
+    const int rc = prepare(p, level_ptrs, scale_factors, out, workspace, workspace_bytes, 0, &pl);
+    if (rc != YOLOPP_OK) return rc;
+    return launch(&pl, (cudaStream_t)stream, events, num_events);
+}
+
+int yolopp_plan_create(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors,
+                       const yolopp_outputs* out, void* workspace, size_t workspace_bytes, yolopp_plan** plan) {
+    if (!plan) return YOLOPP_E_INVALID;
+    *plan = nullptr;
+    yolopp_plan* pl = (yolopp_plan*)malloc(sizeof(yolopp_plan));
+    if (!pl) return YOLOPP_E_INVALID;
+    const int rc = prepare(p, level_ptrs, scale_factors, out, workspace, workspace_bytes, 0, pl);
+    if (rc != YOLOPP_OK) {
+        free(pl);
+        return rc;
+    }
+    *plan = pl;
+    return YOLOPP_OK;
+}
+
+int yolopp_plan_run(const yolopp_plan* plan, void* stream) {
+    if (!plan) return YOLOPP_E_INVALID;
+    return launch(plan, (cudaStream_t)stream, nullptr, 0);
+}
+
+int yolopp_plan_run_profiled(const yolopp_plan* plan, void* stream, void* const* events, int num_events) {
+    if (!plan || !events || num_events < YOLOPP_NUM_STAGE_EVENTS) return YOLOPP_E_INVALID;
+    return launch(plan, (cudaStream_t)stream, events, num_events);
+}
+
+void yolopp_plan_destroy(yolopp_plan* plan) { free(plan); }
+
+int yolopp_topk_conf(const yolopp_params* p, const float* const* level_ptrs, int32_t* topk_inds, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    if (!topk_inds) return YOLOPP_E_INVALID;
+    yolopp_plan pl;
+    int rc = prepare(p, level_ptrs, nullptr, nullptr, workspace, workspace_bytes, 1, &pl);
+    if (rc != YOLOPP_OK) return rc;
+    rc = launch(&pl, (cudaStream_t)stream, nullptr, 0);
+    if (rc != YOLOPP_OK) return rc;
+    const DevParams& d = pl.plan.d;
+    return cuda_rc(cudaMemcpyAsync(topk_inds, d.row_anchor, (size_t)d.B * d.R * sizeof(int32_t), cudaMemcpyDeviceToDevice,
+                                   (cudaStream_t)stream));
+}
+
+int yolopp_decode(const yolopp_params* p, const float* const* level_ptrs, const float* scale_factors, float* boxes,
+                  float* scores, int32_t* topk_inds, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (!boxes || !scores) return YOLOPP_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    yolopp_plan pl;
+    int rc = prepare(p, level_ptrs, scale_factors, nullptr, workspace, workspace_bytes, 2, &pl);
+    if (rc != YOLOPP_OK) return rc;
+    rc = launch(&pl, stream, nullptr, 0);
+    if (rc != YOLOPP_OK) return rc;
+    const DevParams& d = pl.plan.d;
+    const size_t rows = (size_t)d.B * d.R;
+    cudaError_t e = cudaMemcpyAsync(boxes, d.row_box, rows * 16, cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scores, d.mat, rows * d.C * 4, cudaMemcpyDeviceToDevice, stream);
+    if (e == cudaSuccess && topk_inds)
+        e = cudaMemcpyAsync(topk_inds, d.row_anchor, rows * sizeof(int32_t), cudaMemcpyDeviceToDevice, stream);
+    return cuda_rc(e);
 }
 
 int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info) {
@@ -434,22 +625,26 @@ int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info) {
     info->num_attrib = d.NA;
     info->tma_tiles = d.tma_tiles;
     info->ldg_blocks = d.ldg_blocks;
+    info->dense_tiles = d.dense_tiles;
     info->decode_smem_bytes = (int32_t)plan.dec_smem;
     info->decode_ctas_per_sm = plan.dec_ctas_per_sm;
     info->workspace_bytes = (int64_t)plan.total;
     for (int l = 0; l < d.L; ++l) {
         int64_t bytes = (int64_t)4 * d.A * d.NA * d.lv[l].HW;
-        if (d.lv[l].use_tma == 1) info->tma_level_mask |= 1 << l;
         if (d.lv[l].use_tma) {
+            info->tma_level_mask |= 1 << l;
             info->tma_bytes_per_image += bytes;
-        } else {
+        } else if (!d.nhwc) {
             info->ldg_bytes_per_image += bytes;
         }
     }
+    if (d.nhwc) info->ldg_bytes_per_image = (int64_t)4 * d.NA * d.R;
     int launches = 1;  // nms_image
     if (d.ntopk > 0) ++launches;
     if (d.tma_tiles > 0) ++launches;
     if (d.ldg_blocks > 0) ++launches;
+    if (d.dense_tiles > 0) ++launches;
+    if (d.nhwc) ++launches;
     info->kernel_launches = launches;
     return YOLOPP_OK;
 }
@@ -460,10 +655,10 @@ int yolopp_coder_decode(int mode, const float* bboxes, const float* pred, float 
     if (n < 0 || (n > 0 && (!bboxes || !pred || !out))) return YOLOPP_E_INVALID;
     if (n == 0) return YOLOPP_OK;
     if ((((uintptr_t)bboxes | (uintptr_t)pred | (uintptr_t)out) & 15) != 0) return YOLOPP_E_INVALID;
-    int rc = device_check();
-    if (rc != YOLOPP_OK) return rc;
+    const DeviceInfo di = device_info();
+    if (di.rc != YOLOPP_OK) return di.rc;
     long long blocks = (n + 255) / 256;
-    int cap = sm_count() * 8;
+    int cap = di.sms * 8;
     if (blocks > cap) blocks = cap;
     coder_decode_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mode, (const float4*)bboxes, (const float4*)pred,
                                                                       stride, n, (float4*)out);
@@ -473,10 +668,10 @@ int yolopp_coder_decode(int mode, const float* bboxes, const float* pred, float 
 static int unary(const float* in, float* out, int64_t n, int op, void* stream) {
     if (n < 0 || (n > 0 && (!in || !out))) return YOLOPP_E_INVALID;
     if (n == 0) return YOLOPP_OK;
-    int rc = device_check();
-    if (rc != YOLOPP_OK) return rc;
+    const DeviceInfo di = device_info();
+    if (di.rc != YOLOPP_OK) return di.rc;
     long long blocks = (n + 255) / 256;
-    int cap = sm_count() * 8;
+    int cap = di.sms * 8;
     if (blocks > cap) blocks = cap;
     unary_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, n, op);
     return cuda_rc(cudaGetLastError());
@@ -484,11 +679,61 @@ static int unary(const float* in, float* out, int64_t n, int op, void* stream) {
 int yolopp_sigmoid(const float* in, float* out, int64_t n, void* stream) { return unary(in, out, n, 0, stream); }
 int yolopp_exp(const float* in, float* out, int64_t n, void* stream) { return unary(in, out, n, 1, stream); }
 
+// grid of a streaming elementwise kernel: enough blocks for every vector, at most 8 resident blocks per SM, and a
+// whole number of blocks per SM when the tensor is large
+static int stream_grid(long long nvec, int per_block, int sms) {
+    long long blocks = (nvec + per_block - 1) / per_block;
+    if (blocks < 1) blocks = 1;
+    const long long cap = (long long)sms * 8;
+    if (blocks > cap) blocks = cap;
+    else if (blocks > sms) blocks = blocks / sms * sms;
+    return (int)blocks;
+}
+
+int yolopp_mish_forward(const void* in, void* out, int64_t n, int dtype, void* stream_) {
+    if (n < 0 || (n > 0 && (!in || !out))) return YOLOPP_E_INVALID;
+    if (dtype != YOLOPP_DTYPE_F32 && dtype != YOLOPP_DTYPE_F16 && dtype != YOLOPP_DTYPE_BF16) return YOLOPP_E_INVALID;
+    if (n == 0) return YOLOPP_OK;
+    if ((((uintptr_t)in | (uintptr_t)out) & 15) != 0) return YOLOPP_E_INVALID;
+    const DeviceInfo di = device_info();
+    if (di.rc != YOLOPP_OK) return di.rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int vec = dtype == YOLOPP_DTYPE_F32 ? 4 : 8;
+    const int grid = stream_grid(n / vec + 1, MISH_THREADS * MISH_UNROLL, di.sms);
+    if (dtype == YOLOPP_DTYPE_F32)
+        mish_fwd_kernel<float><<<grid, MISH_THREADS, 0, stream>>>((const float*)in, (float*)out, n);
+    else if (dtype == YOLOPP_DTYPE_F16)
+        mish_fwd_kernel<__half><<<grid, MISH_THREADS, 0, stream>>>((const __half*)in, (__half*)out, n);
+    else
+        mish_fwd_kernel<__nv_bfloat16><<<grid, MISH_THREADS, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, n);
+    return cuda_rc(cudaGetLastError());
+}
+
+int yolopp_mish_backward(const void* grad_out, const void* in, void* grad_in, int64_t n, int dtype, void* stream_) {
+    if (n < 0 || (n > 0 && (!grad_out || !in || !grad_in))) return YOLOPP_E_INVALID;
+    if (dtype != YOLOPP_DTYPE_F32 && dtype != YOLOPP_DTYPE_F16 && dtype != YOLOPP_DTYPE_BF16) return YOLOPP_E_INVALID;
+    if (n == 0) return YOLOPP_OK;
+    if ((((uintptr_t)grad_out | (uintptr_t)in | (uintptr_t)grad_in) & 15) != 0) return YOLOPP_E_INVALID;
+    const DeviceInfo di = device_info();
+    if (di.rc != YOLOPP_OK) return di.rc;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int vec = dtype == YOLOPP_DTYPE_F32 ? 4 : 8;
+    const int grid = stream_grid(n / vec + 1, MISH_THREADS * 2, di.sms);
+    if (dtype == YOLOPP_DTYPE_F32)
+        mish_bwd_kernel<float><<<grid, MISH_THREADS, 0, stream>>>((const float*)grad_out, (const float*)in, (float*)grad_in, n);
+    else if (dtype == YOLOPP_DTYPE_F16)
+        mish_bwd_kernel<__half><<<grid, MISH_THREADS, 0, stream>>>((const __half*)grad_out, (const __half*)in, (__half*)grad_in, n);
+    else
+        mish_bwd_kernel<__nv_bfloat16><<<grid, MISH_THREADS, 0, stream>>>((const __nv_bfloat16*)grad_out, (const __nv_bfloat16*)in,
+                                                                         (__nv_bfloat16*)grad_in, n);
+    return cuda_rc(cudaGetLastError());
+}
+
 int yolopp_synth_level(float* out, int32_t batch, int32_t num_anchors, int32_t num_attrib, int32_t hw,
                        const float* mean3, const float* std3, uint64_t seed, void* stream) {
     if (!out || !mean3 || !std3 || batch < 1 || num_anchors < 1 || num_attrib < 5 || hw < 1) return YOLOPP_E_INVALID;
-    int rc = device_check();
-    if (rc != YOLOPP_OK) return rc;
+    const DeviceInfo di = device_info();
+    if (di.rc != YOLOPP_OK) return di.rc;
     Synth3 st;
     for (int i = 0; i < 3; ++i) {
         st.mean[i] = mean3[i];
@@ -496,7 +741,7 @@ int yolopp_synth_level(float* out, int32_t batch, int32_t num_anchors, int32_t n
     }
     long long n = (long long)batch * num_anchors * num_attrib * hw;
     long long blocks = (n + 255) / 256;
-    int cap = sm_count() * 16;
+    int cap = di.sms * 16;
     if (blocks > cap) blocks = cap;
     synth_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(out, n, num_attrib, hw, st, (u64)seed);
     return cuda_rc(cudaGetLastError());
@@ -527,9 +772,7 @@ static int launch_nms_only(DevParams& d, int nlab, cudaStream_t stream) {
     size_t smem = nms_only_smem(d.keep_cap, nlab, &off);
     d.nms_rowkeys_off = off;
     smem = nms_add_stage(d, smem);
-    if (smem > 220 * 1024) return YOLOPP_E_INVALID;
-    cudaError_t e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_rc(e);
+    if (smem > SMEM_LIMIT) return YOLOPP_E_INVALID;
     nms_image_kernel<<<1, NMS_THREADS, smem, stream>>>(d);
     return cuda_rc(cudaGetLastError());
 }
@@ -545,8 +788,8 @@ int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* i
                        int64_t* keep, int32_t* num_keep, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 0 || n >= (1ll << 31) || !num_keep || (nms_offset != 0 && nms_offset != 1)) return YOLOPP_E_INVALID;
-    int rc = device_check();
-    if (rc != YOLOPP_OK) return rc;
+    const DeviceInfo di = device_info();
+    if (di.rc != YOLOPP_OK) return di.rc;
     if (n == 0) return cuda_rc(cudaMemsetAsync(num_keep, 0, 2 * sizeof(int32_t), stream));
     if (!boxes || !scores || !dets || !keep || (((uintptr_t)boxes) & 15)) return YOLOPP_E_INVALID;
     const int nlab = idxs ? num_labels : 1;
@@ -589,8 +832,8 @@ int yolopp_multiclass_nms(const float* multi_bboxes, int boxes_per_class, const 
     if (n < 0 || num_classes < 1 || num_classes > YOLOPP_MAX_CLASSES || n * num_classes >= (1ll << 31) || !num_keep ||
         (nms_offset != 0 && nms_offset != 1))
         return YOLOPP_E_INVALID;
-    int rc = device_check();
-    if (rc != YOLOPP_OK) return rc;
+    const DeviceInfo di = device_info();
+    if (di.rc != YOLOPP_OK) return di.rc;
     if (n == 0) {
         if (num_candidates) cudaMemsetAsync(num_candidates, 0, sizeof(int32_t), stream);
         return cuda_rc(cudaMemsetAsync(num_keep, 0, 2 * sizeof(int32_t), stream));

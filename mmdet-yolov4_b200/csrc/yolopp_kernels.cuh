@@ -46,7 +46,11 @@ struct LevelDev {
     int n_off;    // offset of this level in the concatenated anchor index n = n_off + (y*W+x)*A + a
     int m_off;    // offset in the plane-major, 4-element aligned index m = m_off + a*HW + hw
     int seg;      // top-k segment this level belongs to
-    int use_tma;  // 1: TMA tiles of decode_tma_kernel, 2: gather tiles of decode_tma_kernel, 0: decode_ldg_kernel
+    int use_tma;  // persistent decode_tma_kernel: 1 = TMA tiles (plane stride 16-byte aligned), 3 = quad-row TMA tiles
+                  // (unaligned plane stride: the tensor is viewed as rows of FOUR planes, whose stride always is a
+                  // multiple of 16 bytes), 2 = gather tiles (no tensor map possible); 0: decode_ldg / decode_dense kernel
+    int dense;    // use_tma == 0 only: 1 = most anchors are admitted -> decode_dense_kernel (thread per position)
+    int qrows;    // use_tma == 3: rows of the quad-row view = floor(B * A * NA / 4)
     int tile0;    // first tile id of this level in its kernel's tile enumeration
     int tpp;      // tiles per plane
     float sx, sy; // anchor-generator strides
@@ -81,10 +85,12 @@ struct DevParams {
     int split_thr, nms_agnostic, m_eff, keep_cap, out_cap, rescale;
     int sel_kcap;  // key buffer (power of two) of the select kernel
     int sel_stage; // 32-bit slots of the select kernel's logit staging buffer (0: exact path only)
+    int sel_stride;// 1: whole segments are staged; 2^j: every 2^j-th logit is staged (sample), the rest is streamed
+    int nhwc;      // level tensors are channels-last memory (B, H, W, A*NA): row-driven decode, no rank map
     int nms_rowkeys_off;  // byte offset of the sorted row-best keys inside the NMS kernel's dynamic smem
     int nms_stage_off, nms_stage_rows;  // staging ring of the candidate scan: NMS_STAGES x nms_stage_rows matrix rows
-    int tma_tiles, ldg_blocks;
-    int gather_tiles;        // tiles 0 .. gather_tiles-1 of the decode kernel's enumeration are gather tiles
+    int tma_tiles, ldg_blocks, dense_tiles;
+    int dec_quad;            // some level is streamed as quad-row tiles (stage geometry)
     unsigned* tile_ctr;      // workspace: next unclaimed position of the decode kernel's tile sequence (set by select_kernel)
     unsigned dec_first;      // positions [0, dec_first) of the tile sequence are dealt round-robin, the rest is claimed
     LevelDev lv[MAXL];
@@ -113,6 +119,8 @@ struct DevParams {
     int* o_count;
     int* o_ncand;
     int* o_status;
+    float* o_cls_dets;      // [B][out_cap][5] detections grouped by label (bbox2result), may be null
+    int* o_cls_offsets;     // [B][C+1] first row of each label's group in o_cls_dets
 };
 
 // ---- key sources of the bucket select (see select_sorted_prefix) --------------------------------------------
@@ -297,8 +305,15 @@ __device__ __forceinline__ bool seg_slot(const DevParams& P, const SegDev& sg, i
     return false;
 }
 
-// rank map + row -> anchor table from the sorted top-k keys
-__device__ __forceinline__ void select_write(const DevParams& P, const SegDev& sg, int b, const u64* sel, int k) {
+// address of the objectness logit of (level, image, anchor, position): NCHW (B, A*NA, H, W) or, with P.nhwc,
+// the channels-last memory of the same logical tensor (B, H, W, A*NA)
+__device__ __forceinline__ const float* obj_addr(const DevParams& P, const LevelDev& lv, int b, int a, int hw) {
+    if (P.nhwc) return lv.ptr + (((size_t)b * lv.HW + hw) * P.A + a) * P.NA + 4;
+    return lv.ptr + ((size_t)(b * P.A + a) * P.NA + 4) * lv.HW + hw;
+}
+
+// rank map + row -> anchor table from sorted top-k keys: sel[0..k) are the rows row0 .. row0+k-1 of the segment
+__device__ __forceinline__ void select_write(const DevParams& P, const SegDev& sg, int b, const u64* sel, int k, int row0 = 0) {
     uint32_t* rank = P.rank + (size_t)b * P.M_pad;
     const int first = sg.first_level, nl = sg.num_levels, A = P.A;
     for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
@@ -312,19 +327,28 @@ __device__ __forceinline__ void select_write(const DevParams& P, const SegDev& s
         const LevelDev& lv = P.lv[l];
         const int loc = n - lv.n_off;
         const int hw = loc / A, a = loc - hw * A;
-        rank[lv.m_off + a * lv.HW + hw] = (uint32_t)(sg.row_off + i);
-        P.row_anchor[(size_t)b * P.R + sg.row_off + i] = n;
+        if (!P.nhwc) rank[lv.m_off + a * lv.HW + hw] = (uint32_t)(sg.row_off + row0 + i);  // (the NHWC decode is row driven)
+        P.row_anchor[(size_t)b * P.R + sg.row_off + row0 + i] = n;
     }
+}
+
+// staging mode of a segment with M plane-major slots: 1 = staged whole, 2^j = 1-in-2^j sample + streamed pass
+__device__ __forceinline__ int sel_stride_of(const DevParams& P, int M) {
+    return (M <= P.sel_stage && M <= 32768) ? 1 : P.sel_stride;
 }
 
 // Fast path of the objectness top-k: work on the RAW logits. sigmoid is monotone, so the k best confidences
 // belong to the k best logits — except for ties: distinct logits can round to the same confidence, and the
 // canonical order breaks confidence ties by anchor index. Hence:
-//   1. the segment's objectness logits are copied to shared memory (4-byte async copies: one DRAM round trip
-//      for the whole segment) and mapped to order-preserving integers;
-//   2. a histogram of a 1-in-8 sample picks a cut that keeps ~1.3 k logits (the "stash");
-//   3. only the stash goes through sigmoid and becomes (~ord(conf) << 32 | anchor) keys, which are sorted;
-//   4. the result is exact iff every logit outside the stash is strictly worse than the k-th key: checked with
+//   1. STAGED (the segment fits the staging buffer, P.sel_stride == 1): the segment's objectness logits are copied
+//      to shared memory (bulk copies per plane / 4-byte async copies: one DRAM round trip for the whole segment)
+//      and mapped to order-preserving integers; a histogram of a 1-in-8 sample picks a cut that keeps ~1.3 k
+//      logits (the "stash").
+//      STREAMED (larger segments, e.g. 100 800 anchors at 1280^2; P.sel_stride = 2^j): only every sel_stride-th
+//      logit is staged; the histogram of that sample picks the cut (k + 4 sqrt(k * stride) expected survivors),
+//      then ONE pass over the segment in global memory stashes every logit above the cut.
+//   2. only the stash goes through sigmoid and becomes (~ord(conf) << 32 | anchor) keys, which are sorted;
+//   3. the result is exact iff every logit outside the stash is strictly worse than the k-th key: checked with
 //      a 16-ulp guard band on the confidence of the cut itself (covers ties and any last-ulp non-monotonicity
 //      of the polynomial). Otherwise — saturated / mass-tied objectness — the caller runs the exact path over
 //      all confidences.
@@ -334,57 +358,71 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     static_assert(SEL_THREADS * 2 == TS_BINS, "two histogram bins per thread in the pivot scan");
     const int M = sg.m_end - sg.m_begin;
+    const int stride = sel_stride_of(P, M);
+    const bool staged = stride == 1;
+    const int ns = staged ? M : (M + stride - 1) / stride;  // staged slots
     uint32_t* rank = P.rank + (size_t)b * P.M_pad + sg.m_begin;
     for (int i = tid; i < TS_BINS; i += SEL_THREADS) S.hist[i] = 0;
     if (tid == 0) S.count = 0;
-    // 1. stage the logits (slot order = plane-major order of the segment): one bulk copy per objectness plane
-    //    where planes are 16-byte aligned (issued by warp 0, one plane per lane), 4-byte async copies otherwise
     uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
-    if (tid == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-        uint32_t bulk_bytes = 0;
+    if (staged) {
+        // stage the logits (slot order = plane-major order of the segment): one bulk copy per objectness plane
+        // where planes are 16-byte aligned (issued by warp 0, one plane per lane), 4-byte async copies otherwise
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+            uint32_t bulk_bytes = 0;
+            for (int li = 0; li < sg.num_levels; ++li) {
+                const LevelDev& lv = P.lv[sg.first_level + li];
+                if (!P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && (((lv.m_off - sg.m_begin) & 3) == 0))
+                    bulk_bytes += (uint32_t)(P.A * lv.HW) * 4u;
+            }
+            mbar_arrive_expect_tx(bar, bulk_bytes);
+        }
+        __syncthreads();
         for (int li = 0; li < sg.num_levels; ++li) {
             const LevelDev& lv = P.lv[sg.first_level + li];
-            if (((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && (((lv.m_off - sg.m_begin) & 3) == 0))
-                bulk_bytes += (uint32_t)(P.A * lv.HW) * 4u;
-        }
-        mbar_arrive_expect_tx(bar, bulk_bytes);
-    }
-    __syncthreads();
-    for (int li = 0; li < sg.num_levels; ++li) {
-        const LevelDev& lv = P.lv[sg.first_level + li];
-        const float* lbase = lv.ptr + (size_t)b * P.A * P.NA * lv.HW;
-        const int AHW = P.A * lv.HW, s0 = lv.m_off - sg.m_begin;
-        const bool bulk = ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && ((s0 & 3) == 0);
-        if (bulk) {
-            if (warp == 0)
-                for (int a = lane; a < P.A; a += 32)
-                    bulk_load_1d(ox + s0 + a * lv.HW, lbase + ((size_t)a * P.NA + 4) * lv.HW, (uint32_t)lv.HW * 4u, bar);
-        } else {
-            for (int e = tid; e < AHW; e += SEL_THREADS) {
-                int a = 0, hw = e;
-                while (hw >= lv.HW) {
-                    hw -= lv.HW;
-                    ++a;
+            const float* lbase = lv.ptr + (size_t)b * P.A * P.NA * lv.HW;
+            const int AHW = P.A * lv.HW, s0 = lv.m_off - sg.m_begin;
+            const bool bulk = !P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && ((s0 & 3) == 0);
+            if (bulk) {
+                if (warp == 0)
+                    for (int a = lane; a < P.A; a += 32)
+                        bulk_load_1d(ox + s0 + a * lv.HW, lbase + ((size_t)a * P.NA + 4) * lv.HW, (uint32_t)lv.HW * 4u, bar);
+            } else {
+                for (int e = tid; e < AHW; e += SEL_THREADS) {
+                    int a = 0, hw = e;
+                    while (hw >= lv.HW) {
+                        hw -= lv.HW;
+                        ++a;
+                    }
+                    cp_async4(ox + s0 + e, obj_addr(P, lv, b, a, hw));
                 }
-                cp_async4(ox + s0 + e, lbase + ((size_t)a * P.NA + 4) * lv.HW + hw);
             }
+            const int pad0 = s0 + AHW, pad1 = li + 1 < sg.num_levels ? P.lv[sg.first_level + li + 1].m_off - sg.m_begin : M;
+            if (tid < pad1 - pad0) ox[pad0 + tid] = 0xFFFFFFFFu;  // alignment padding: becomes ord 0, never eligible
         }
-        const int pad0 = s0 + AHW, pad1 = li + 1 < sg.num_levels ? P.lv[sg.first_level + li + 1].m_off - sg.m_begin : M;
-        if (tid < pad1 - pad0) ox[pad0 + tid] = 0xFFFFFFFFu;  // alignment padding: becomes ord 0, never eligible
+        YPP_PHASE(0, b, 5);
+        cp_async_wait_all();
+        mbar_wait(bar, 0u);
+    } else {
+        // sample: every stride-th slot of the segment
+        for (int j = tid; j < ns; j += SEL_THREADS) {
+            int l = 0, a = 0, hw = 0;
+            if (seg_slot(P, sg, j * stride + sg.m_begin, l, a, hw)) cp_async4(ox + j, obj_addr(P, P.lv[l], b, a, hw));
+            else ox[j] = 0xFFFFFFFFu;
+        }
+        YPP_PHASE(0, b, 5);
+        cp_async_wait_all();
     }
-    YPP_PHASE(0, b, 5);
-    cp_async_wait_all();
-    mbar_wait(bar, 0u);
     __syncthreads();
     YPP_PHASE(0, b, 6);
     uint32_t omin = 0xFFFFFFFFu, omax = 0u;
-    for (int m = tid; m < M; m += SEL_THREADS) {
+    for (int m = tid; m < ns; m += SEL_THREADS) {
         const uint32_t raw = ox[m];
         const uint32_t o = raw == 0xFFFFFFFFu ? 0u : f2ord(__uint_as_float(raw));
         ox[m] = o;
-        rank[m] = RANK_INVALID;
+        if (staged && !P.nhwc) rank[m] = RANK_INVALID;
         omin = (o && o < omin) ? o : omin;
         omax = o > omax ? o : omax;
     }
@@ -402,15 +440,24 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     omin = __reduce_min_sync(0xffffffffu, omin);
     omax = __reduce_max_sync(0xffffffffu, omax);
     YPP_PHASE(0, b, 1);
+    if (omax == 0u) return false;  // nothing staged (cannot happen for a non-empty segment)
     const uint32_t range = omax - omin;
     const int shift = range >= (uint32_t)TS_BINS ? (32 - __clz(range)) - 11 : 0;
-    // 2. sampled histogram of (omax - o): bin 0 holds the best logits
-    for (int m = tid * 8; m < M; m += SEL_THREADS * 8) {
+    // sampled histogram of (omax - o): bin 0 holds the best logits (staged: 1-in-8 of the slots; streamed: the
+    // whole sample)
+    const int hstep = staged ? 8 : 1;
+    for (int m = tid * hstep; m < ns; m += SEL_THREADS * hstep) {
         const uint32_t o = ox[m];
         if (o) atomicAdd(&S.hist[(omax - o) >> shift], 1);
     }
     __syncthreads();
-    const int ks = (sg.k * 13 + 79) / 80 + 24;  // 1.3 k / 8 + slack, in samples
+    int ks;  // rank of the cut among the histogram's samples
+    if (staged) {
+        ks = (sg.k * 13 + 79) / 80 + 24;  // 1.3 k / 8 + slack
+    } else {
+        const float want = (float)sg.k + 4.0f * sqrtf((float)sg.k * (float)stride);
+        ks = (int)(want / (float)stride) + 3;
+    }
     {
         const int h0 = S.hist[2 * tid], h1 = S.hist[2 * tid + 1], s = h0 + h1;
         int incl = s;
@@ -439,14 +486,15 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     }
     const int pb = S.kb;
     const uint32_t cut = (uint32_t)((((u64)pb + 1ull) << shift) - 1ull);  // keep omax - o <= cut
-    // 3. stash: slots of the surviving logits (unordered)
+    const uint32_t cut_ord = cut >= omax ? 1u : omax - cut;               // i.e. o >= cut_ord (ord 0 = padding)
+    // stash: slots of the surviving logits (unordered)
     uint32_t* slots = reinterpret_cast<uint32_t*>(tmp);
-    {
+    if (staged) {
         static_assert(SEL_THREADS * 32 >= 32768, "one survivor bit per staged slot of a thread");
         unsigned em = 0u;
         for (int m = tid, j = 0; m < M; m += SEL_THREADS, ++j) {
             const uint32_t o = ox[m];
-            em |= ((o && omax - o <= cut) ? 1u : 0u) << j;
+            em |= ((o && o >= cut_ord) ? 1u : 0u) << j;
         }
         const int c = __popc(em);
         int incl = c;
@@ -464,6 +512,38 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
             if (sp < 2 * kcap) slots[sp] = (uint32_t)(tid + j * SEL_THREADS);
             ++sp;
         }
+    } else {
+        // one pass over the whole segment in global memory, 8 loads in flight per thread
+        constexpr int U = 8;
+        for (int li = 0; li < sg.num_levels; ++li) {
+            const LevelDev& lv = P.lv[sg.first_level + li];
+            const int s0 = lv.m_off - sg.m_begin;
+            for (int a = 0; a < P.A; ++a) {
+                for (int h0 = 0; h0 < lv.HW; h0 += SEL_THREADS * U) {
+                    float v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int hw = h0 + u * SEL_THREADS + tid;
+                        v[u] = hw < lv.HW ? __ldg(obj_addr(P, lv, b, a, hw)) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int hw = h0 + u * SEL_THREADS + tid;
+                        const bool in = hw < lv.HW;
+                        const int m = s0 + a * lv.HW + hw;
+                        if (in && !P.nhwc) rank[m] = RANK_INVALID;
+                        const bool surv = in && f2ord(v[u]) >= cut_ord;
+                        const unsigned bal = __ballot_sync(0xffffffffu, surv);
+                        if (bal) {
+                            int sp = 0;
+                            if (lane == 0) sp = atomicAdd(&S.count, __popc(bal));
+                            sp = __shfl_sync(0xffffffffu, sp, 0) + __popc(bal & ((1u << lane) - 1u));
+                            if (surv && sp < 2 * kcap) slots[sp] = (uint32_t)m;
+                        }
+                    }
+                }
+            }
+        }
     }
     __syncthreads();
     const int n_stash = S.count;
@@ -473,9 +553,10 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     uint32_t hmin = 0xFFFFFFFFu, hmax = 0u;
     for (int i = tid; i < n_stash; i += SEL_THREADS) {
         const int m = (int)slots[i];
-        const float conf = c_sigmoid(ord2f(ox[m]));
         int l = 0, a = 0, hw = 0;
         seg_slot(P, sg, m + sg.m_begin, l, a, hw);
+        const uint32_t o = staged ? ox[m] : f2ord(__ldg(obj_addr(P, P.lv[l], b, a, hw)));
+        const float conf = c_sigmoid(ord2f(o));
         const uint32_t h = ~f2ord(conf);
         sel[i] = ((u64)h << 32) | (u64)(uint32_t)(P.lv[l].n_off + hw * P.A + a);
         hmin = h < hmin ? h : hmin;
@@ -496,10 +577,11 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     const int cnt = select_sorted_prefix(none, (u64)hmin << 32, ((u64)hmax << 32) | 0xFFFFFFFFull, sg.k, sel, tmp, kcap, S, n_stash);
     YPP_PHASE(0, b, 3);
     if (cnt < sg.k) return false;
-    // 4. every logit outside the stash is below the cut: its confidence is at most conf(cut) (+ rounding noise)
-    const uint32_t conf_cut = f2ord(c_sigmoid(ord2f(omax - cut)));
+    // every logit outside the stash is below the cut: its confidence is at most conf(cut) (+ rounding noise)
+    const uint32_t conf_cut = f2ord(c_sigmoid(ord2f(cut_ord)));
     const uint32_t conf_k = ~(uint32_t)(sel[sg.k - 1] >> 32);
-    if (cut < range && !(conf_k >= conf_cut + 16u)) return false;
+    const bool excluded = staged ? (cut < range) : (n_stash < sg.N);
+    if (excluded && !(conf_k >= conf_cut + 16u)) return false;
     select_write(P, sg, b, sel, sg.k);
     return true;
 }
@@ -513,7 +595,10 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     const int b = blockIdx.y;
     const SegDev& sg = P.seg[P.topk_segs[blockIdx.x]];
     const int tid = threadIdx.x;
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *P.tile_ctr = P.dec_first;  // the decode kernel's tile scheduler
+    if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {
+        *P.tile_ctr = P.dec_first;  // the decode kernel's tile scheduler
+        if (P.o_status) *P.o_status = 0;  // first kernel of the call: the data-dependent status starts clean
+    }
     u64* ckey = P.ckey + (size_t)b * P.M_pad;
     uint32_t* rank = P.rank + (size_t)b * P.M_pad;
 
@@ -522,7 +607,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     if (threadIdx.x == 0) { S.prof_kernel = 0; S.prof_call = 0; }
     __syncthreads();
 #endif
-    if (P.sel_stage >= sg.m_end - sg.m_begin) {
+    const int seg_m = sg.m_end - sg.m_begin, seg_stride = sel_stride_of(P, seg_m);
+    if (P.sel_stage > 0 && sg.k <= SEL_MAX_K && (seg_m + seg_stride - 1) / seg_stride <= P.sel_stage) {
         // fast path on the raw logits; falls through to the exact path when it cannot prove its result
         if (select_fast(P, sg, b, sel, sel + P.sel_kcap, reinterpret_cast<uint32_t*>(sel + 2 * P.sel_kcap), P.sel_kcap, S)) {
             YPP_PHASE(0, b, 4);
@@ -535,17 +621,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     u64 kmin = ~0ull, kmax = 0ull;
     for (int li = 0; li < sg.num_levels; ++li) {
         const LevelDev& lv = P.lv[sg.first_level + li];
-        const float* lbase = lv.ptr + (size_t)b * P.A * P.NA * lv.HW;
         constexpr int U = 8;
         for (int a = 0; a < P.A; ++a) {
-            const float* plane = lbase + ((size_t)a * P.NA + 4) * lv.HW;
             const int m0 = lv.m_off + a * lv.HW;
             for (int h0 = 0; h0 < lv.HW; h0 += SEL_THREADS * U) {
                 float v[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int hw = h0 + u * SEL_THREADS + tid;
-                    v[u] = hw < lv.HW ? __ldg(plane + hw) : 0.f;
+                    v[u] = hw < lv.HW ? __ldg(obj_addr(P, lv, b, a, hw)) : 0.f;
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -554,7 +638,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
                         const float conf = c_sigmoid(v[u]);
                         const u64 key = ((u64)(~f2ord(conf)) << 32) | (u64)(uint32_t)(lv.n_off + hw * P.A + a);
                         ckey[m0 + hw] = key;
-                        rank[m0 + hw] = RANK_INVALID;
+                        if (!P.nhwc) rank[m0 + hw] = RANK_INVALID;
                         kmin = key < kmin ? key : kmin;
                         kmax = key > kmax ? key : kmax;
                     }
@@ -573,6 +657,27 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     CkeySource src;
     src.p = reinterpret_cast<const ulonglong2*>(ckey + sg.m_begin);
     src.n = (sg.m_end - sg.m_begin + 1) / 2;
+    if (sg.k > SEL_MAX_K) {
+        // nms_pre beyond the shared-memory sort capacity: the sorted prefix is produced in chunks, each one a
+        // select over the keys above the previous chunk's last key (keys are unique)
+        const int chunk = P.sel_kcap / 2;
+        u64 lo = gmin;
+        int done = 0;
+        while (done < sg.k) {
+            const int want = min(chunk, sg.k - done);
+            const int cnt = select_sorted_prefix(src, lo, gmax, want, sel, sel + P.sel_kcap, P.sel_kcap, S);
+            const int take = min(cnt, sg.k - done);
+            if (take <= 0) break;
+            select_write(P, sg, b, sel, take, done);
+            done += take;
+            const u64 last = sel[take - 1];
+            __syncthreads();  // sel is rewritten by the next chunk
+            if (cnt < want || last == ~0ull) break;
+            lo = last + 1ull;
+        }
+        YPP_PHASE(0, b, 4);
+        return;
+    }
     u64 hi_sel = gmax;
     // Pivot from a 1-in-16 sample: the objectness distribution is extremely skewed (most anchors share a few
     // histogram buckets), so the exact select only looks at keys up to ~1.5x the expected k-th key. If the
@@ -842,15 +947,23 @@ __device__ __forceinline__ void process_batch(const DevParams& P, const LevelDev
 // pattern is a function of the offset alone).
 struct StageGeom {
     uint32_t sub_bytes;    // one (NA x 32) box, padded to 1024
-    uint32_t rank_off;     // 64-entry rank row
+    uint32_t quad_rows;    // quad-row tiles: rows of four planes a box spans
+    uint32_t quad_box;     // one (quad_rows x 32) box, padded to 1024
+    uint32_t rank_off;     // rank row: 64 entries + 4 (aligned superset when the row is not 16-byte aligned)
     uint32_t desc_off;     // tile descriptor written by the producer
     uint32_t stage_bytes;
 };
-__host__ __device__ inline StageGeom stage_geom(int NA) {
+constexpr uint32_t RANK_ROW_BYTES = (TILE_T + 4) * 4u;  // quad-row tiles fetch the 16-byte aligned superset
+__host__ __device__ inline StageGeom stage_geom(int NA, int quad) {
     StageGeom g;
     g.sub_bytes = ((uint32_t)NA * 128u + 1023u) & ~1023u;
-    g.rank_off = 2u * g.sub_bytes;
-    g.desc_off = g.rank_off + TILE_T * 4u;
+    // NA consecutive planes starting at plane p0 live in rows p0/4 .. (p0 + NA - 1)/4 of the four-plane view
+    g.quad_rows = (((uint32_t)NA + 2u) >> 2) + 1u;
+    g.quad_box = (g.quad_rows * 128u + 1023u) & ~1023u;
+    uint32_t data = 2u * g.sub_bytes;
+    if (quad && 8u * g.quad_box > data) data = 8u * g.quad_box;
+    g.rank_off = data;
+    g.desc_off = g.rank_off + ((RANK_ROW_BYTES + 31u) & ~31u);
     g.stage_bytes = (g.desc_off + 32u + 1023u) & ~1023u;
     return g;
 }
@@ -862,6 +975,16 @@ __device__ __forceinline__ uint32_t tile_off(uint32_t sub_bytes, int k, int p) {
 }
 __device__ __forceinline__ float tile_at(const unsigned char* stage, uint32_t sub_bytes, int k, int p) {
     return *reinterpret_cast<const float*>(stage + tile_off(sub_bytes, k, p));
+}
+// The same for a quad-row tile: the level is viewed as rows of four planes (row stride 16 * HW bytes); the tile
+// arrives as 8 boxes, box (j, h) = plane-in-row j, positions h*32 .. h*32+31, rows r0 .. r0 + quad_rows - 1.
+// Attribute k of the slab is plane p0 + k, i.e. row (pl0 + k) / 4 - relative to r0 - and plane-in-row (pl0 + k) % 4,
+// pl0 = p0 % 4.
+__device__ __forceinline__ float quad_at(const unsigned char* stage, uint32_t quad_box, int pl0, int k, int p) {
+    const int pk = pl0 + k, j = pk & 3, r = pk >> 2, col = p & 31;
+    const uint32_t off = (uint32_t)(2 * j + (p >> 5)) * quad_box + (uint32_t)r * 128u +
+                         ((uint32_t)(((col >> 2) ^ (r & 7)) << 4) | (uint32_t)((col & 3) << 2));
+    return *reinterpret_cast<const float*>(stage + off);
 }
 
 // Persistent, warp-specialised. Warp 0 is the producer: its 32 lanes work out the coordinates of the CTA's next
@@ -904,7 +1027,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
     // 1024-byte aligned base (swizzle) — the launch reserves 1 KB of slack
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int NA = P.NA;
-    const StageGeom g = stage_geom(NA);
+    const StageGeom g = stage_geom(NA, P.dec_quad);
     const uint32_t box_bytes = (uint32_t)NA * 128u;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [DEC_STAGES]: the tile streamed into stage s has landed
     uint64_t* empty = full + DEC_STAGES;                      // [DEC_STAGES]: stage s may be refilled
@@ -992,7 +1115,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             // lane j < n: coordinates of its sequence position
             int d_t = -1, d_l = 0, d_plane = 0, d_hw0 = 0, d_b = 0, d_a = 0, d_hw = 0, d_rbase = 0, d_topk = 0, d_kind = 0;
             if ((unsigned)lane < n && q_lane < (unsigned)total) {
-                const int t = (int)q_lane;  // gather tiles (ids below P.gather_tiles) sit at the head of the sequence
+                const int t = (int)q_lane;
                 int best0 = -1;  // the level with the largest first-tile id <= t (gather levels are enumerated first)
                 for (int i = 0; i < P.L; ++i)
                     if (P.lv[i].use_tma && t >= P.lv[i].tile0 && P.lv[i].tile0 > best0) {
@@ -1010,6 +1133,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                 d_hw = lv.HW;
                 d_topk = sg.has_topk;
                 d_kind = lv.use_tma;
+                // quad-row view: the slab's last plane must lie inside the view (only the tensor's very last slab can
+                // fall outside, when B * A * NA is not a multiple of four) — otherwise the tile is gathered
+                if (d_kind == 3 && ((d_plane * NA + NA - 1) >> 2) >= lv.qrows) d_kind = 2;
                 d_rbase = sg.row_off + (lv.n_off - P.lv[sg.first_level].n_off) + d_a;  // row of position 0 (no top-k)
             }
             for (unsigned j = 0; j < n; ++j, ++k) {
@@ -1036,10 +1162,27 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                         YPP_STAMP(t, 1);
                         // descriptor first (it carries the iteration number the consumer matches and everything the
                         // consumer needs before it can release the stage), then arm the barrier
-                        *reinterpret_cast<int4*>(dst + g.desc_off + 16) = make_int4(hwn, rbase, tk, t);
+                        // quad-row tiles: first plane of the slab in its row of four, misalignment of the rank row
+                        const int q_pl = plane * NA, q_m = P.lv[l].m_off + a * hwn + hw0, q_shift = q_m & 3;
+                        const int tkz = kind == 3 ? (tk | (q_shift << 4) | ((q_pl & 3) << 8)) : tk;
+                        *reinterpret_cast<int4*>(dst + g.desc_off + 16) = make_int4(hwn, rbase, tkz, t);
                         *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l | (a << 8) | (kind << 16), bb, hw0, it);
                         if (kind == 2) {
                             mbar_arrive(fb);  // gather tile: nothing to stream, the consumer reads global memory itself
+                        } else if (kind == 3) {
+                            // quad-row tile: 4 planes-in-row x 2 halves; the rank row is not 16-byte aligned, its
+                            // aligned superset is fetched and the consumer skips `shift` entries
+                            const int r0 = q_pl >> 2;
+                            const bool two = hw0 + TILE_SUB < hwn;
+                            mbar_arrive_expect_tx(fb, g.quad_rows * 128u * (two ? 8u : 4u) + (tk ? RANK_ROW_BYTES : 0u));
+#pragma unroll
+                            for (int qj = 0; qj < 4; ++qj) {
+                                tma_load_2d(dst + (size_t)(2 * qj) * g.quad_box, &maps.m[l], qj * hwn + hw0, r0, fb);
+                                if (two)
+                                    tma_load_2d(dst + (size_t)(2 * qj + 1) * g.quad_box, &maps.m[l], qj * hwn + hw0 + TILE_SUB, r0, fb);
+                            }
+                            if (tk)
+                                bulk_load_1d(dst + g.rank_off, P.rank + (size_t)bb * P.M_pad + (q_m - q_shift), RANK_ROW_BYTES, fb);
                         } else {
                             const bool topk = tk != 0;
                             const bool two = hw0 + TILE_SUB < hwn;  // the second box is not entirely out of bounds
@@ -1119,7 +1262,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         const int4 desc2 = *reinterpret_cast<const int4*>(stage + g.desc_off + 16);
         const int b = desc.y, a = (desc.x >> 8) & 0xFF, hw0 = desc.z;
         const int lvl = desc.x & 0xFF, HWn = desc2.x, rbase = desc2.y;
-        const bool topk = desc2.z != 0;
+        const bool topk = (desc2.z & 1) != 0;
         const int tile_id = desc2.w;
         (void)tile_id;
         YPP_STAMP(tile_id, 2);
@@ -1152,6 +1295,34 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             continue;
         }
         const uint32_t* rk = reinterpret_cast<const uint32_t*>(stage + g.rank_off);
+        if (kind == 3) {
+            // quad-row tile (plane stride not 16-byte aligned, e.g. 19x19): logits are read from the tile in place,
+            // one admitted anchor at a time; 4.8 % of the bytes at 608^2
+            const int shift = (desc2.z >> 4) & 3, pl0 = (desc2.z >> 8) & 3;
+            const LevelDev& lv = P.lv[lvl];
+            const SegDev& sg = P.seg[lv.seg];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int ps0 = h * 32 + lane;
+                uint32_t r = RANK_INVALID;
+                if (hw0 + ps0 < HWn) r = rk[shift + ps0];
+                unsigned adm = __ballot_sync(0xffffffffu, r != RANK_INVALID);
+                while (adm) {
+                    const int src = __ffs(adm) - 1;
+                    adm &= adm - 1;
+                    const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+                    const int ps = h * 32 + src;
+                    const float av = lane < 5 ? quad_at(stage, g.quad_box, pl0, lane, ps) : 0.f;
+                    process_anchor<MODE>(P, lv, sg, b, a, hw0 + ps, rr, lane, av, [&](int u) -> float {
+                        return quad_at(stage, g.quad_box, pl0, 5 + u * 32 + lane, ps);
+                    });
+                }
+            }
+            stage_release_fence();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            continue;
+        }
 
         // admitted positions of the tile as a 64-bit mask (everything needed comes from the stage header: no
         // parameter-space lookups before the stage is released)
@@ -1254,16 +1425,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
 #endif
 }
 
-// Generic path for levels the TMA kernel cannot take (plane stride not 16-byte aligned, e.g. 19x19) and for
-// dense admission (no top-k: every anchor is computed anyway).
-//   SPARSE: a warp scans 32 positions, then gathers each admitted anchor's logits (lanes over classes).
-//   dense : one thread per position, coalesced loads, loop over classes.
+// Sparse admission on levels the persistent kernel cannot take (more than 256 attributes per anchor): a warp scans
+// 32 positions, then gathers each admitted anchor's logits (lanes over classes).
 template <int MODE>
 __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__ DevParams P) {
     const int t = blockIdx.x;
     int l = 0;
     for (int q = 0; q < P.L; ++q)
-        if (!P.lv[q].use_tma && t >= P.lv[q].tile0) l = q;
+        if (!P.lv[q].use_tma && !P.lv[q].dense && t >= P.lv[q].tile0) l = q;
     const LevelDev& lv = P.lv[l];
     const int loc = t - lv.tile0;
     const int plane = loc / lv.tpp;
@@ -1277,75 +1446,149 @@ __global__ void __launch_bounds__(128) decode_ldg_kernel(const __grid_constant__
 
     uint32_t r = RANK_INVALID;
     if (hw < lv.HW) r = row_of(P, lv, b, a, hw);
+    unsigned adm = __ballot_sync(0xffffffffu, r != RANK_INVALID);
+    const int hw_w = hw - lane;  // first position of this warp
+    while (adm) {
+        const int src = __ffs(adm) - 1;
+        adm &= adm - 1;
+        const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+        const int hwp = hw_w + src;
+        const float av = lane < 5 ? __ldg(slab + (size_t)lane * HW + hwp) : 0.f;
+        process_anchor<MODE>(P, lv, sg, b, a, hwp, rr, lane, av,
+                             [&](int u) -> float { return __ldg(slab + (size_t)(5 + u * 32 + lane) * HW + hwp); });
+    }
+}
 
-    if (sg.has_topk) {
-        // sparse admission: warp-cooperative gather per admitted anchor
-        unsigned adm = __ballot_sync(0xffffffffu, r != RANK_INVALID);
-        const int hw_w = hw - lane;  // first position of this warp
-        while (adm) {
-            const int src = __ffs(adm) - 1;
-            adm &= adm - 1;
-            const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
-            const int hwp = hw_w + src;
-            const float av = lane < 5 ? __ldg(slab + (size_t)lane * HW + hwp) : 0.f;
-            process_anchor<MODE>(P, lv, sg, b, a, hwp, rr, lane, av,
-                                 [&](int u) -> float { return __ldg(slab + (size_t)(5 + u * 32 + lane) * HW + hwp); });
+// Channels-last head tensors (P.nhwc: memory order (B, H, W, A*NA), what a cuDNN NHWC convolution writes): the
+// 5+C logits of one anchor are CONTIGUOUS, so the decode is driven by the rows instead of streaming the tensor —
+// one warp per (image, row): anchor index from the top-k's row table (or arithmetic when the segment keeps every
+// anchor), one coalesced 4*NA-byte read, the same process_anchor as everywhere else. HBM traffic: only the
+// admitted anchors' logits (1000 x 340 B per image at 608^2 instead of 7.7 MB).
+constexpr int ROWS_WARPS = 8;
+template <int MODE>
+__global__ void __launch_bounds__(32 * ROWS_WARPS) decode_rows_kernel(const __grid_constant__ DevParams P) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * ROWS_WARPS + warp;
+    if (w >= (long long)P.B * P.R) return;
+    const int b = (int)(w / P.R), r = (int)(w - (long long)b * P.R);
+    int s = 0;
+    for (int q = 1; q < P.nsegs; ++q)
+        if (r >= P.seg[q].row_off) s = q;
+    const SegDev& sg = P.seg[s];
+    int n;  // concatenated anchor index of the row
+    if (sg.has_topk) n = P.row_anchor[(size_t)b * P.R + r];
+    else n = P.lv[sg.first_level].n_off + (r - sg.row_off);
+    int l = sg.first_level;
+    for (int q = sg.num_levels - 1; q >= 0; --q)
+        if (n >= P.lv[sg.first_level + q].n_off) {
+            l = sg.first_level + q;
+            break;
         }
-        return;
+    const LevelDev& lv = P.lv[l];
+    const int loc = n - lv.n_off;
+    const int hw = loc / P.A, a = loc - hw * P.A;
+    const float* src = lv.ptr + (((size_t)b * lv.HW + hw) * P.A + a) * P.NA;
+    const float av = lane < 5 ? __ldg(src + lane) : 0.f;
+    process_anchor<MODE>(P, lv, sg, b, a, hw, (uint32_t)r, lane, av, [&](int u) -> float { return __ldg(src + 5 + u * 32 + lane); });
+}
+
+// Dense admission (no top-k, or a top-k that keeps most of the level's anchors — e.g. YOLOv3's 20x20 level with
+// nms_pre = 1000 of 1200): every position is computed, one thread per position, loads coalesced across the warp's
+// 32 consecutive positions of a plane. Scores are transposed through shared memory in chunks of DENSE_CH classes
+// so that the rows of the score matrix leave as coalesced 4*DENSE_CH-byte runs (a thread owning a whole row would
+// write 32 scattered words per instruction). One warp = one tile of 32 positions; 4 independent warps per block.
+constexpr int DENSE_CH = 64;
+constexpr int DENSE_WARPS = 4;
+template <int MODE>
+__global__ void __launch_bounds__(32 * DENSE_WARPS) decode_dense_kernel(const __grid_constant__ DevParams P) {
+    __shared__ uint32_t sm_all[DENSE_WARPS][32][DENSE_CH + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * DENSE_WARPS + warp;
+    if (t >= P.dense_tiles) return;
+    uint32_t (*sm)[DENSE_CH + 1] = sm_all[warp];
+    int l = 0;
+    for (int q = 0; q < P.L; ++q)
+        if (!P.lv[q].use_tma && P.lv[q].dense && t >= P.lv[q].tile0) l = q;
+    const LevelDev& lv = P.lv[l];
+    const SegDev& sg = P.seg[lv.seg];
+    const int loc = t - lv.tile0;
+    const int plane = loc / lv.tpp;
+    const int b = plane / P.A, a = plane - b * P.A;
+    const int hw = (loc - plane * lv.tpp) * 32 + lane;
+    const float* slab = lv.ptr + (size_t)plane * P.NA * lv.HW;
+    const size_t HW = (size_t)lv.HW;
+    const bool inb = hw < lv.HW;
+    const int hwc = inb ? hw : lv.HW - 1;  // out-of-range lanes recompute the last position (keeps loads uniform)
+
+    uint32_t r = RANK_INVALID;
+    if (inb) r = row_of(P, lv, b, a, hw);
+    bool adm = r != RANK_INVALID;
+    if (!__any_sync(0xffffffffu, adm)) return;
+    const float t0 = __ldg(slab + 0 * HW + hwc), t1 = __ldg(slab + 1 * HW + hwc);
+    const float t2 = __ldg(slab + 2 * HW + hwc), t3 = __ldg(slab + 3 * HW + hwc);
+    const float conf = c_sigmoid(__ldg(slab + 4 * HW + hwc));
+    const bool drop = (MODE == 1) && P.conf_thr > 0.f && !(conf >= P.conf_thr);  // yolo_head.py:365-376
+    if (adm && !drop) {
+        const float a0 = c_sigmoid(t0), a1 = c_sigmoid(t1);
+        const float a2 = (MODE == 0) ? c_sigmoid(t2) : c_expf(t2);
+        const float a3 = (MODE == 0) ? c_sigmoid(t3) : c_expf(t3);
+        int x, y;
+        pos_xy(lv, hw, x, y);
+        float4 bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
+        if (P.rescale) bx = rescale_box(bx, P.scale + 4 * b);
+        P.row_box[(size_t)b * P.R + r] = bx;
+        if (!sg.has_topk) P.row_anchor[(size_t)b * P.R + r] = lv.n_off + hw * P.A + a;
     }
-    // dense admission
-    if (r == RANK_INVALID) return;
-    uint32_t* mrow = P.mat + ((size_t)b * P.R + r) * P.C;
-    const float t0 = __ldg(slab + 0 * HW + hw), t1 = __ldg(slab + 1 * HW + hw);
-    const float t2 = __ldg(slab + 2 * HW + hw), t3 = __ldg(slab + 3 * HW + hw);
-    const float conf = c_sigmoid(__ldg(slab + 4 * HW + hw));
-    if (MODE == 1 && P.conf_thr > 0.f && !(conf >= P.conf_thr)) {
-        for (int c = 0; c < P.C; ++c) mrow[c] = SCORE_NONE;
-        P.row_stat[(size_t)b * P.R + r] = make_uint4(0u, 0u, 0u, 0u);
-        return;
-    }
-    const float a0 = c_sigmoid(t0), a1 = c_sigmoid(t1);
-    const float a2 = (MODE == 0) ? c_sigmoid(t2) : c_expf(t2);
-    const float a3 = (MODE == 0) ? c_sigmoid(t3) : c_expf(t3);
-    const int y = hw / lv.W, x = hw - y * lv.W;
-    float4 bx = decode_box<MODE>(lv, a, x, y, a0, a1, a2, a3);
-    if (P.rescale) bx = rescale_box(bx, P.scale + 4 * b);
-    P.row_box[(size_t)b * P.R + r] = bx;
-    P.row_anchor[(size_t)b * P.R + r] = lv.n_off + hw * P.A + a;
     uint32_t best = 0u, worst = 0u;
     int npass = 0;
+    const unsigned admm = __ballot_sync(0xffffffffu, adm);
     if (P.agnostic) {
-        const bool pass = conf > P.score_thr;
-        mrow[0] = pass ? __float_as_uint(conf) : SCORE_NONE;
+        // cls_pred = conf_pred[:, None]  (yolocsp_head.py:360): one class, score = objectness
+        const bool pass = adm && conf > P.score_thr;
+        if (adm) P.mat[((size_t)b * P.R + r) * P.C] = pass ? __float_as_uint(conf) : SCORE_NONE;
         if (pass) {
             best = f2ord(conf);
             worst = ~best;
             npass = 1;
         }
     } else {
-        const float* cls = slab + 5 * HW + hw;
+        const float* cls = slab + 5 * HW + hwc;
+        for (int c0 = 0; c0 < P.C; c0 += DENSE_CH) {
+            const int nc = min(DENSE_CH, P.C - c0);
 #pragma unroll 8
-        for (int c = 0; c < P.C; ++c) {
-            const float sgm = c_sigmoid(__ldg(cls + (size_t)c * HW));
-            float score;
-            bool pass;
-            if (MODE == 0) {
-                score = fmul(sgm, conf);
-                pass = score > P.score_thr;
-            } else {
-                pass = sgm > P.score_thr;
-                score = fmul(sgm, conf);
+            for (int j = 0; j < nc; ++j) {
+                const float sgm = c_sigmoid(__ldg(cls + (size_t)(c0 + j) * HW));
+                float score;
+                bool pass;
+                if (MODE == 0) {
+                    score = fmul(sgm, conf);     // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
+                    pass = score > P.score_thr;  // bbox_nms.py:54
+                } else {
+                    pass = sgm > P.score_thr;    // threshold on the class score alone (bbox_nms.py:54) ...
+                    score = fmul(sgm, conf);     // ... then scores * score_factors    (bbox_nms.py:57-62)
+                }
+                pass = pass && !drop;
+                sm[lane][j] = pass ? __float_as_uint(score) : SCORE_NONE;
+                if (pass && adm) {
+                    const uint32_t o = f2ord(score);
+                    best = o > best ? o : best;
+                    worst = ~o > worst ? ~o : worst;
+                    ++npass;
+                }
             }
-            mrow[c] = pass ? __float_as_uint(score) : SCORE_NONE;
-            if (pass) {
-                const uint32_t o = f2ord(score);
-                best = o > best ? o : best;
-                worst = ~o > worst ? ~o : worst;
-                ++npass;
+            __syncwarp();
+            unsigned todo = admm;
+            while (todo) {
+                const int q = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t rq = __shfl_sync(0xffffffffu, r, q);
+                uint32_t* mrow = P.mat + ((size_t)b * P.R + rq) * P.C + c0;
+                for (int j = lane; j < nc; j += 32) mrow[j] = sm[q][j];
             }
+            __syncwarp();
         }
     }
-    P.row_stat[(size_t)b * P.R + r] = make_uint4(best, worst, (uint32_t)npass, 0u);
+    if (adm) P.row_stat[(size_t)b * P.R + r] = make_uint4(best, worst, (uint32_t)npass, 0u);
 }
 
 // Candidate scan of the NMS kernel through shared memory: the score-matrix rows of the `nrows` best rows
@@ -1440,6 +1683,54 @@ __device__ __noinline__ int nms_stage_scan(const DevParams& P, const uint32_t* m
     cp_async_wait_group<0>();
     __syncthreads();
     return *count;
+}
+
+// bbox2result (mmdet/core/bbox/transforms.py:110-116): `bboxes[labels == i, :]` for every class, i.e. a STABLE
+// counting sort of the <= max_per_img output rows by label. Done on the device so that the host gets one block it
+// can slice into num_classes views. All threads of the NMS block call; `cnt` = C ints of scratch.
+__device__ __noinline__ void nms_group_by_label(const DevParams& P, int b, int nk, const int* kcl, const u64* kkey, int* cnt,
+                                                const float4* row_box) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, C = P.C;
+    for (int c = tid; c < C; c += NMS_THREADS) cnt[c] = 0;
+    __syncthreads();
+    for (int i = tid; i < nk; i += NMS_THREADS) atomicAdd(&cnt[kcl[i]], 1);
+    __syncthreads();
+    if (warp == 0) {
+        // exclusive scan over the classes: each lane owns a contiguous run
+        const int per = (C + 31) / 32, c0 = lane * per, c1 = min(C, c0 + per);
+        int sum = 0;
+        for (int c = c0; c < c1; ++c) sum += cnt[c];
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int run = incl - sum;
+        int* offs = P.o_cls_offsets + (size_t)b * (C + 1);
+        for (int c = c0; c < c1; ++c) {
+            const int v = cnt[c];
+            cnt[c] = run;
+            offs[c] = run;
+            run += v;
+        }
+        if (lane == 31) offs[C] = incl;  // == nk
+    }
+    __syncthreads();
+    for (int i = tid; i < nk; i += NMS_THREADS) {
+        const int c = kcl[i];
+        int pos = cnt[c];
+        for (int j = 0; j < i; ++j) pos += (kcl[j] == c) ? 1 : 0;  // rows are few (<= max_per_img)
+        const u64 key = kkey[i];
+        const uint32_t flat = key_flat(key);
+        const float4 bx = row_box[P.boxes_per_class ? flat : flat / (uint32_t)C];
+        float* d = P.o_cls_dets + ((size_t)b * P.out_cap + pos) * 5;
+        d[0] = bx.x;
+        d[1] = bx.y;
+        d[2] = bx.z;
+        d[3] = bx.w;
+        d[4] = key_score(key);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1545,6 +1836,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     if (tid == 0 && P.o_ncand) P.o_ncand[b] = ntot;
     if (ntot == 0) {
         if (tid == 0) P.o_count[b] = 0;
+        if (P.o_cls_offsets && !generic) nms_group_by_label(P, b, 0, kcl, kkey, chead, row_box);  // all groups empty
         return;
     }
     const u64 gmin = (u64)(~s_red[0]) << 32;
@@ -1831,6 +2123,10 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         if (P.o_rows) P.o_rows[(size_t)b * P.out_cap + i] = r;
     }
     if (tid == 0) P.o_count[b] = nk;
+    if (P.o_cls_offsets && !generic) {
+        __syncthreads();
+        nms_group_by_label(P, b, nk, kcl, kkey, chead, row_box);
+    }
     YPP_PHASE(1, b, 6);
 }
 
@@ -1876,6 +2172,18 @@ __global__ void __launch_bounds__(256) multiclass_prep_kernel(const float* __res
 // ------------------------------------------------------------------------------------------------
 // small standalone kernels
 // ------------------------------------------------------------------------------------------------
+// yolopp_topk_conf: rows of the segments that keep every anchor (no top-k) are the anchors in order
+__global__ void fill_rows_kernel(const __grid_constant__ DevParams P) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)P.B * P.R) return;
+    const int r = (int)(i % P.R);
+    int s = 0;
+    for (int q = 1; q < P.nsegs; ++q)
+        if (r >= P.seg[q].row_off) s = q;
+    const SegDev& sg = P.seg[s];
+    if (!sg.has_topk) P.row_anchor[i] = P.lv[sg.first_level].n_off + (r - sg.row_off);
+}
+
 __global__ void unary_kernel(const float* __restrict__ in, float* __restrict__ out, long long n, int op) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long step = (long long)gridDim.x * blockDim.x;

@@ -9,7 +9,7 @@ from ctypes import c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_LEVELS = 8
 MAX_ANCHORS = 8
 MAX_CLASSES = 4096
@@ -17,6 +17,9 @@ MAX_ROWS = 1 << 20
 
 MODE_CSP = 0
 MODE_V3 = 1
+LAYOUT_NCHW = 0
+LAYOUT_NHWC = 1
+DTYPE_F32, DTYPE_F16, DTYPE_BF16 = 0, 1, 2
 
 OK, E_INVALID, E_WORKSPACE, E_OVERFLOW, E_NO_DEVICE, E_CUDA = 0, 1, 2, 3, 4, 1000
 
@@ -52,7 +55,8 @@ class YoloppParams(ctypes.Structure):
         ('rescale', c_int32),
         ('out_capacity', c_int32),
         ('batches_in_flight', c_int32),
-        ('reserved', c_int32 * 6),
+        ('layout', c_int32),
+        ('reserved', c_int32 * 5),
     ]
 
     # convenience -----------------------------------------------------------------------------
@@ -65,7 +69,12 @@ class YoloppParams(ctypes.Structure):
         return 1 if self.class_agnostic else self.num_classes
 
     def level_shape(self, l):
+        """LOGICAL shape of level l (both layouts: NHWC is the channels-last memory of this shape)."""
         return (self.batch, self.num_anchors * self.num_attrib, self.height[l], self.width[l])
+
+    @property
+    def rows_per_image(self):
+        return describe(self).rows_per_image
 
     @property
     def anchors_per_image(self):
@@ -86,6 +95,8 @@ class YoloppOutputs(ctypes.Structure):
         ('count', c_void_p),
         ('num_candidates', c_void_p),
         ('status', c_void_p),
+        ('cls_dets', c_void_p),
+        ('cls_offsets', c_void_p),
     ]
 
 
@@ -101,7 +112,7 @@ class YoloppPlanInfo(ctypes.Structure):
         ('decode_smem_bytes', c_int32),
         ('decode_ctas_per_sm', c_int32),
         ('kernel_launches', c_int32),
-        ('reserved0', c_int32),
+        ('dense_tiles', c_int32),
         ('tma_bytes_per_image', c_int64),
         ('ldg_bytes_per_image', c_int64),
         ('workspace_bytes', c_int64),
@@ -134,7 +145,7 @@ def yolo_base_anchors(base_sizes, strides):
 def make_params(mode, batch, featmap_sizes, anchor_strides, coder_strides, base_sizes, num_classes,
                 class_agnostic=False, nms_pre=-1, score_thr=0.0, conf_thr=-1.0, iou_thr=0.5, nms_offset=0,
                 split_thr=10000, nms_class_agnostic=False, nms_max_num=-1, max_per_img=-1, rescale=False,
-                out_capacity=0, base_anchors=None):
+                out_capacity=0, base_anchors=None, layout=LAYOUT_NCHW):
     """Builds yolopp_params from what the reference reads off the head instance and test_cfg
     (yolocsp_head.py:112-114,151,162,170-178,345-348,374-376; yolo_head.py:52-59,281,365,378-384)."""
     L = len(featmap_sizes)
@@ -175,6 +186,7 @@ def make_params(mode, batch, featmap_sizes, anchor_strides, coder_strides, base_
     p.max_per_img = int(max_per_img)
     p.rescale = int(bool(rescale))
     p.out_capacity = int(out_capacity)
+    p.layout = int(layout)
     return p
 
 
@@ -206,6 +218,24 @@ def load_library(path=None):
     lib.yolopp_get_bboxes_profiled.restype = ctypes.c_int
     lib.yolopp_get_bboxes_profiled.argtypes = [pp, ctypes.POINTER(c_void_p), c_void_p, po, c_void_p, c_size_t,
                                                c_void_p, ctypes.POINTER(c_void_p), ctypes.c_int]
+    lib.yolopp_plan_create.restype = ctypes.c_int
+    lib.yolopp_plan_create.argtypes = [pp, ctypes.POINTER(c_void_p), c_void_p, po, c_void_p, c_size_t,
+                                       ctypes.POINTER(c_void_p)]
+    lib.yolopp_plan_run.restype = ctypes.c_int
+    lib.yolopp_plan_run.argtypes = [c_void_p, c_void_p]
+    lib.yolopp_plan_run_profiled.restype = ctypes.c_int
+    lib.yolopp_plan_run_profiled.argtypes = [c_void_p, c_void_p, ctypes.POINTER(c_void_p), ctypes.c_int]
+    lib.yolopp_plan_destroy.restype = None
+    lib.yolopp_plan_destroy.argtypes = [c_void_p]
+    lib.yolopp_topk_conf.restype = ctypes.c_int
+    lib.yolopp_topk_conf.argtypes = [pp, ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.yolopp_decode.restype = ctypes.c_int
+    lib.yolopp_decode.argtypes = [pp, ctypes.POINTER(c_void_p), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p]
+    lib.yolopp_mish_forward.restype = ctypes.c_int
+    lib.yolopp_mish_forward.argtypes = [c_void_p, c_void_p, c_int64, ctypes.c_int, c_void_p]
+    lib.yolopp_mish_backward.restype = ctypes.c_int
+    lib.yolopp_mish_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, ctypes.c_int, c_void_p]
     lib.yolopp_describe.restype = ctypes.c_int
     lib.yolopp_describe.argtypes = [pp, ctypes.POINTER(YoloppPlanInfo)]
     lib.yolopp_coder_decode.restype = ctypes.c_int
@@ -234,7 +264,9 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = ('yolopp_abi_version', 'yolopp_strerror', 'yolopp_workspace_bytes', 'yolopp_get_bboxes',
-                    'yolopp_get_bboxes_profiled', 'yolopp_describe',
+                    'yolopp_get_bboxes_profiled', 'yolopp_describe', 'yolopp_plan_create', 'yolopp_plan_run',
+                    'yolopp_plan_run_profiled', 'yolopp_plan_destroy', 'yolopp_topk_conf', 'yolopp_decode',
+                    'yolopp_mish_forward', 'yolopp_mish_backward',
                     'yolopp_coder_decode', 'yolopp_nms_workspace_bytes', 'yolopp_batched_nms', 'yolopp_multiclass_nms',
                     'yolopp_synth_level',
                     'yolopp_sigmoid', 'yolopp_exp')

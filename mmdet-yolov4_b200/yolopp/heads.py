@@ -164,17 +164,10 @@ def _run_raw(mode, head, pred_maps, img_metas, cfg, rescale, with_nms):
     batch = pred_maps[0].shape[0]
     if mode == _capi.MODE_CSP:
         assert len(img_metas) == batch
-    ag = head.anchor_generator
     num_anchors = head.num_anchors[0] if isinstance(head.num_anchors, (list, tuple)) else head.num_anchors
-    class_agnostic = bool(getattr(head, 'class_agnostic', False))
     for l in range(num_levels):
         assert pred_maps[l].shape[1] == num_anchors * head.num_attrib
-    params = _capi.make_params(
-        mode, batch, [tuple(m.shape[-2:]) for m in pred_maps], ag.strides, head.featmap_strides, ag.base_sizes,
-        head.num_classes, class_agnostic=class_agnostic, nms_pre=int(_cfg_get(cfg, 'nms_pre', -1)),
-        score_thr=float(_cfg_attr(cfg, 'score_thr')),
-        conf_thr=float(_cfg_get(cfg, 'conf_thr', -1)) if mode == _capi.MODE_V3 else -1.0,
-        max_per_img=int(_cfg_attr(cfg, 'max_per_img')), rescale=bool(rescale), **parse_nms_cfg(nms_cfg))
+    params = head_params(mode, head, [tuple(m.shape[-2:]) for m in pred_maps], batch, cfg, rescale)
     sf = _scale_factors(img_metas, batch) if rescale else None
     if sf is not None:
         sf = sf.to(pred_maps[0].device, non_blocking=True)
@@ -185,10 +178,8 @@ def _get_bboxes_impl(mode, head, pred_maps, img_metas, cfg, rescale, with_nms):
     params, out = _run_raw(mode, head, pred_maps, img_metas, cfg, rescale, with_nms)
     batch = params.batch
     # one small device->host read: counts + status (the reference syncs dozens of times per image)
-    host = torch.cat([out['count'], out['num_candidates'], out['status']]).cpu()
-    count, ncand, status = host[:batch], host[batch:2 * batch], int(host[-1])
-    if status != 0:
-        raise RuntimeError(f'yolopp_get_bboxes: {_capi.load_library().yolopp_strerror(status).decode()}')
+    host = _pull(head, params, out, ())['meta'].clone()
+    count, ncand = host[:batch], host[batch:2 * batch]
     result = []
     for b in range(batch):
         n = int(count[b])
@@ -200,27 +191,64 @@ def _get_bboxes_impl(mode, head, pred_maps, img_metas, cfg, rescale, with_nms):
     return result
 
 
-def _get_results_host(mode, head, pred_maps, img_metas, cfg, rescale):
-    """get_bboxes + bbox2result's device->host step fused: ONE D2H of the fixed-capacity block into pinned
-    memory, then numpy views. Returns list[(ndarray(n,5) f32, ndarray(n,) i64)]."""
-    params, out = _run_raw(mode, head, pred_maps, img_metas, cfg, rescale, True)
-    B, cap = params.batch, params.capacity
-    key = (B, cap, out['dets'].device)
+def _host_block(head, out, B, cap, C):
+    """Pinned host staging block of a head (one per (B, cap, device)); overwritten by every call — callers get
+    copies, never views of it."""
+    key = (B, cap, C, out['dets'].device)
     buf = getattr(head, '_yolopp_host', None)
     if buf is None or buf[0] != key:
-        buf = (key, torch.empty((B, cap, 5), dtype=torch.float32).pin_memory(),
-               torch.empty((B, cap), dtype=torch.int64).pin_memory(),
-               torch.empty((2 * B + 1, ), dtype=torch.int32).pin_memory())
+        buf = (key, dict(dets=torch.empty((B, cap, 5), dtype=torch.float32).pin_memory(),
+                         labels=torch.empty((B, cap), dtype=torch.int64).pin_memory(),
+                         cls_dets=torch.empty((B, cap, 5), dtype=torch.float32).pin_memory(),
+                         cls_offsets=torch.empty((B, C + 1), dtype=torch.int32).pin_memory(),
+                         meta=torch.empty((2 * B + 1, ), dtype=torch.int32).pin_memory()))
         head._yolopp_host = buf
-    _, h_dets, h_labels, h_meta = buf
-    h_dets.copy_(out['dets'], non_blocking=True)
-    h_labels.copy_(out['labels'], non_blocking=True)
-    h_meta.copy_(torch.cat([out['count'], out['num_candidates'], out['status']]), non_blocking=True)
+    return buf[1]
+
+
+def _pull(head, params, out, names):
+    """ONE stream-ordered batch of device->host copies of the named output blocks (+ counts / status) into pinned
+    memory, one synchronize, status check. Returns the pinned block dict."""
+    B, cap, C = params.batch, params.capacity, params.eff_classes
+    h = _host_block(head, out, B, cap, C)
+    for n in names:
+        h[n].copy_(out[n], non_blocking=True)
+    h['meta'][:B].copy_(out['count'], non_blocking=True)
+    h['meta'][B:2 * B].copy_(out['num_candidates'], non_blocking=True)
+    h['meta'][2 * B:].copy_(out['status'], non_blocking=True)
     torch.cuda.current_stream().synchronize()
-    if int(h_meta[-1]) != 0:
-        raise RuntimeError(f'yolopp_get_bboxes: {_capi.load_library().yolopp_strerror(int(h_meta[-1])).decode()}')
-    d, l, cnt = h_dets.numpy(), h_labels.numpy(), h_meta.numpy()[:B]
-    return [(d[b, :cnt[b]], l[b, :cnt[b]]) for b in range(B)]
+    status = int(h['meta'][-1])
+    if status != 0:
+        raise RuntimeError(f'yolopp_get_bboxes: {_capi.load_library().yolopp_strerror(status).decode()}')
+    return h
+
+
+def _get_results_host(mode, head, pred_maps, img_metas, cfg, rescale):
+    """get_bboxes + bbox2result's device->host step fused: the fixed-capacity block goes to pinned memory in one
+    batch of copies. Returns list[(ndarray(n,5) f32, ndarray(n,) i64)] — independent arrays (the reference returns
+    fresh tensors per call, so results collected over a dataset loop must not alias the staging block)."""
+    params, out = _run_raw(mode, head, pred_maps, img_metas, cfg, rescale, True)
+    B = params.batch
+    h = _pull(head, params, out, ('dets', 'labels'))
+    d, l, cnt = h['dets'].numpy(), h['labels'].numpy(), h['meta'].numpy()[:B]
+    return [(d[b, :cnt[b]].copy(), l[b, :cnt[b]].copy()) for b in range(B)]
+
+
+def _get_bbox_results(mode, head, pred_maps, img_metas, cfg, rescale):
+    """The tail of SingleStageDetector.simple_test (mmdet/models/detectors/single_stage.py:102-111):
+    `[bbox2result(det_bboxes, det_labels, num_classes) for ...]`. The NMS kernel already wrote the detections grouped
+    by label with the group offsets (yolopp_outputs.cls_dets / cls_offsets), so the per-class split is
+    `num_classes` zero-copy VIEWS of one small per-image array instead of `num_classes` boolean-mask gathers."""
+    params, out = _run_raw(mode, head, pred_maps, img_metas, cfg, rescale, True)
+    B, C = params.batch, params.eff_classes
+    h = _pull(head, params, out, ('cls_dets', 'cls_offsets'))
+    d, off, cnt = h['cls_dets'].numpy(), h['cls_offsets'].numpy(), h['meta'].numpy()[:B]
+    results = []
+    for b in range(B):
+        block = d[b, :cnt[b]].copy()  # one small copy per image; the class arrays below are views of it
+        o = off[b]
+        results.append([block[o[c]:o[c + 1]] for c in range(C)])
+    return results
 
 
 class _HeadBase:
@@ -256,6 +284,12 @@ class _HeadBase:
         """Host-side results (numpy) with a single device->host copy per batch — what `simple_test` needs
         before `bbox2result` (mmdet/models/detectors/single_stage.py:102-111)."""
         return _get_results_host(self._mode, self, pred_maps, img_metas, cfg, rescale)
+
+    def get_bbox_results(self, pred_maps, img_metas, cfg=None, rescale=False):
+        """`bbox_results` of SingleStageDetector.simple_test (single_stage.py:102-111): per image a list of
+        `num_classes` arrays (k_c, 5), == [bbox2result(*r, num_classes) for r in get_bboxes(...)], with the
+        per-class grouping done on the device."""
+        return _get_bbox_results(self._mode, self, pred_maps, img_metas, cfg, rescale)
 
 
 class YOLOCSPHead(_HeadBase):
@@ -303,8 +337,34 @@ def patch_head(head):
     def get_bboxes(self, pred_maps, img_metas, cfg=None, rescale=False, with_nms=True):
         return _get_bboxes_impl(mode, self, [m.detach() for m in pred_maps], img_metas, cfg, rescale, with_nms)
 
+    def get_results_host(self, pred_maps, img_metas, cfg=None, rescale=False):
+        return _get_results_host(mode, self, [m.detach() for m in pred_maps], img_metas, cfg, rescale)
+
+    def get_bbox_results(self, pred_maps, img_metas, cfg=None, rescale=False):
+        return _get_bbox_results(mode, self, [m.detach() for m in pred_maps], img_metas, cfg, rescale)
+
     head.get_bboxes = types.MethodType(get_bboxes, head)
+    head.get_results_host = types.MethodType(get_results_host, head)
+    head.get_bbox_results = types.MethodType(get_bbox_results, head)
     return head
+
+
+def head_params(mode_or_head, head=None, pred_shapes=None, batch=None, cfg=None, rescale=False):
+    """yolopp_params for a head instance (ours or a live mmdet head) and a list of level shapes (H, W) — what
+    `get_bboxes` builds internally; exposed for Session / Pipeline / HostPipeline users."""
+    if head is None:
+        head = mode_or_head
+        mode = _capi.MODE_CSP if type(head).__name__ == 'YOLOCSPHead' else _capi.MODE_V3
+    else:
+        mode = mode_or_head
+    cfg = head.test_cfg if cfg is None else cfg
+    ag = head.anchor_generator
+    return _capi.make_params(
+        mode, batch, [tuple(s) for s in pred_shapes], ag.strides, head.featmap_strides, ag.base_sizes,
+        head.num_classes, class_agnostic=bool(getattr(head, 'class_agnostic', False)),
+        nms_pre=int(_cfg_get(cfg, 'nms_pre', -1)), score_thr=float(_cfg_attr(cfg, 'score_thr')),
+        conf_thr=float(_cfg_get(cfg, 'conf_thr', -1)) if mode == _capi.MODE_V3 else -1.0,
+        max_per_img=int(_cfg_attr(cfg, 'max_per_img')), rescale=bool(rescale), **parse_nms_cfg(_cfg_get(cfg, 'nms')))
 
 
 def bbox2result(bboxes, labels, num_classes):

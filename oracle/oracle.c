@@ -372,9 +372,16 @@ int64_t oracle_multiclass_nms(const float* multi_bboxes, int per_class_boxes, co
 static int num_attrib(const yolopp_params* p) { return p->class_agnostic ? 5 : 5 + p->num_classes; }
 
 /* one image; out_* have capacity `cap` rows. Returns number of detections (<= cap) or -1. */
+/* intermediate results of one image (SURVEY.md A.3 parity taps); any pointer may be NULL */
+typedef struct oracle_taps {
+    int32_t* topk_inds; /* [R]     topk_inds of yolocsp_head.py:350-355 / yolo_head.py:281-302 (concatenated anchor index) */
+    float* boxes;       /* [R][4]  bbox_pred entering multiclass_nms (after rescale) */
+    float* scores;      /* [R][C]  score of candidate (row, class), NaN where valid_mask is false (bbox_nms.py:54-67) */
+} oracle_taps;
+
 static int64_t get_bboxes_single(const yolopp_params* p, const float* const* levels, int b, const float* scale,
                                  int64_t cap, float* out_dets, int64_t* out_labels, int32_t* out_anchor,
-                                 int32_t* out_row, int32_t* out_ncand) {
+                                 int32_t* out_row, int32_t* out_ncand, const oracle_taps* taps) {
     const int L = p->num_levels, A = p->num_anchors, NA = num_attrib(p);
     const int C = p->class_agnostic ? 1 : p->num_classes;
     int64_t N = 0;
@@ -483,6 +490,29 @@ static int64_t get_bboxes_single(const yolopp_params* p, const float* const* lev
         for (int64_t r = 0; r < R; ++r)
             for (int k = 0; k < 4; ++k) box[4 * r + k] = box[4 * r + k] / scale[k];
 
+    if (taps) {
+        /* rows are indexed in top-k rank order BEFORE the V3 conf_thr row filter (like the `rows` tap) */
+        for (int64_t r = 0; r < R; ++r) {
+            if (taps->topk_inds) taps->topk_inds[r] = (int32_t)src[r];
+            if (taps->boxes) memcpy(taps->boxes + 4 * r, box + 4 * r, sizeof(float) * 4);
+            if (taps->scores) {
+                const int dropped = p->mode == YOLOPP_MODE_V3 && p->conf_thr > 0.f && !(conf[r] >= p->conf_thr);
+                for (int c = 0; c < C; ++c) {
+                    float sc;
+                    int valid;
+                    if (p->mode == YOLOPP_MODE_CSP) {
+                        sc = p->class_agnostic ? conf[r] : cls[r * C + c] * conf[r]; /* yolocsp_head.py:358 / :360 */
+                        valid = sc > p->score_thr;                                    /* bbox_nms.py:54 */
+                    } else {
+                        valid = cls[r * C + c] > p->score_thr; /* bbox_nms.py:54 on the class score ... */
+                        sc = cls[r * C + c] * conf[r];         /* ... then * score_factors (:57-62) */
+                    }
+                    taps->scores[r * C + c] = (!dropped && valid) ? sc : NAN;
+                }
+            }
+        }
+    }
+
     /* scores (R, C+1) with zero background column */
     float* ms = (float*)malloc(sizeof(float) * (size_t)(R > 0 ? R : 1) * (size_t)(C + 1));
     const float* factors = NULL;
@@ -564,7 +594,7 @@ int oracle_get_bboxes(const yolopp_params* p, const float* const* levels, const 
         int64_t nk = get_bboxes_single(p, levels, b, scale_factors ? scale_factors + 4 * b : NULL, cap,
                                        dets + (int64_t)b * cap * 5, labels + (int64_t)b * cap,
                                        anchors ? anchors + (int64_t)b * cap : NULL, rows ? rows + (int64_t)b * cap : NULL,
-                                       num_candidates ? num_candidates + b : NULL);
+                                       num_candidates ? num_candidates + b : NULL, NULL);
         if (nk < 0) {
 #ifdef _OPENMP
 #pragma omp atomic write
@@ -575,6 +605,55 @@ int oracle_get_bboxes(const yolopp_params* p, const float* const* levels, const 
         count[b] = (int32_t)nk;
     }
     return rc;
+}
+
+/* Host mirror of yolopp_decode / yolopp_topk_conf: the taps of every image. rows = rows entering multiclass_nms
+ * per image (sum over segments of min(nms_pre, N_segment)); arrays are [B][rows]... like the device entries. */
+int oracle_get_taps(const yolopp_params* p, const float* const* levels, const float* scale_factors, int64_t rows,
+                    int32_t* topk_inds, float* boxes, float* scores) {
+    const int C = p->class_agnostic ? 1 : p->num_classes;
+    const int64_t cap = 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1)
+#endif
+    for (int b = 0; b < p->batch; ++b) {
+        oracle_taps t;
+        t.topk_inds = topk_inds ? topk_inds + (int64_t)b * rows : NULL;
+        t.boxes = boxes ? boxes + (int64_t)b * rows * 4 : NULL;
+        t.scores = scores ? scores + (int64_t)b * rows * C : NULL;
+        float d[5];
+        int64_t lab[1];
+        yolopp_params q = *p;
+        q.max_per_img = 1; /* the detections themselves are not wanted here */
+        q.nms_max_num = -1;
+        get_bboxes_single(&q, levels, b, scale_factors ? scale_factors + 4 * b : NULL, cap, d, lab, NULL, NULL, NULL, &t);
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Mish (mmdet/ops/mish_cuda/src/mish.h:17-29) as mish_cpu.cc:6-29 instantiates it for float tensors. NOTE the
+ * types: the header calls exp / log1p / tanh UNQUALIFIED, which in the host build resolve to the C library's
+ * double functions, so every call computes in double and only assignments to `scalar_t` round to float. Verified
+ * bit for bit against the reference header compiled here (oracle/_ref/libmish_ref.so, tests/test_cpu_oracle.py). */
+/* ------------------------------------------------------------------------------------------------ */
+float oracle_mish_fwd(float inp) {
+    const double sp = inp < 20.0f ? log1p(exp((double)inp)) : (double)inp;
+    return (float)((double)inp * tanh(sp));
+}
+float oracle_mish_bwd(float grad_out, float inp) {
+    const float sp = (float)(inp < 20.0f ? log1p(exp((double)inp)) : (double)inp);
+    const float grad_sp = (float)(1 - exp((double)-sp));
+    const float tsp = (float)tanh((double)sp);
+    const float grad_tsp = (1 - tsp * tsp) * grad_sp;
+    const float grad = inp * grad_tsp + tsp;
+    return grad_out * grad;
+}
+void oracle_mish_fwd_array(const float* in, float* out, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) out[i] = oracle_mish_fwd(in[i]);
+}
+void oracle_mish_bwd_array(const float* grad_out, const float* in, float* grad_in, int64_t n) {
+    for (int64_t i = 0; i < n; ++i) grad_in[i] = oracle_mish_bwd(grad_out[i], in[i]);
 }
 
 /* ------------------------------------------------------------------------------------------------ */

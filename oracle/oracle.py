@@ -49,6 +49,10 @@ def lib():
         L.oracle_get_bboxes.restype = c_int
         L.oracle_get_bboxes.argtypes = [c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_int64, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_int]
+        L.oracle_get_taps.restype = c_int
+        L.oracle_get_taps.argtypes = [c_void_p, ctypes.POINTER(c_void_p), c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+        L.oracle_mish_fwd_array.argtypes = [c_void_p, c_void_p, c_int64]
+        L.oracle_mish_bwd_array.argtypes = [c_void_p, c_void_p, c_void_p, c_int64]
         L.oracle_synth_level.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_uint64]
         _lib = L
     return _lib
@@ -159,4 +163,34 @@ def synth_level(batch, num_anchors, num_attrib, hw, mean, std, seed):
     m, s = _f32(mean), _f32(std)
     assert m.size == num_attrib and s.size == num_attrib
     lib().oracle_synth_level(_ptr(out), batch, num_anchors, num_attrib, hw, _ptr(m), _ptr(s), c_uint64(seed))
+    return out
+
+
+def get_taps(params, levels, rows, scale_factors=None):
+    """Host mirror of yolopp_topk_conf / yolopp_decode (SURVEY.md A.3 taps): topk_inds (B,R) int32, boxes (B,R,4),
+    scores (B,R,C) with NaN where (row, class) is not a candidate."""
+    B = params.batch
+    C = 1 if params.class_agnostic else params.num_classes
+    lv = [_f32(x) for x in levels]
+    ptrs = (c_void_p * len(lv))(*[x.ctypes.data for x in lv])
+    sf = None if scale_factors is None else _f32(scale_factors).reshape(B, 4)
+    topk = np.zeros((B, rows), np.int32)
+    boxes = np.zeros((B, rows, 4), np.float32)
+    scores = np.zeros((B, rows, C), np.float32)
+    rc = lib().oracle_get_taps(ctypes.byref(params), ptrs, _ptr(sf), rows, _ptr(topk), _ptr(boxes), _ptr(scores))
+    assert rc == 0
+    return topk, boxes, scores
+
+
+def mish_forward(x):
+    x = _f32(x)
+    out = np.empty_like(x)
+    lib().oracle_mish_fwd_array(_ptr(x), _ptr(out), x.size)
+    return out
+
+
+def mish_backward(grad_out, x):
+    g, x = _f32(grad_out), _f32(x)
+    out = np.empty_like(x)
+    lib().oracle_mish_bwd_array(_ptr(g), _ptr(x), _ptr(out), x.size)
     return out

@@ -6,31 +6,11 @@ test_cfg dict). Inputs are synthetic, from the bit-reproducible generator (yolop
 import numpy as np
 
 from yolopp import _capi as capi
-from yolopp import synth as ysynth
+from yolopp import synth as ysynth  # noqa: F401
+from workloads import (V4_SIZES, V3_SIZES, COCO_NMS, csp_case as _csp, v3_case as _v3, build_params, ref_cfg,  # noqa: F401
+                       scale_factors, host_levels)
 
-V4_SIZES = [[(12, 16), (19, 36), (40, 28)], [(36, 75), (76, 55), (72, 146)], [(142, 110), (192, 243), (459, 401)]]
-V3_SIZES = [[(116, 90), (156, 198), (373, 326)], [(30, 61), (62, 45), (59, 119)], [(10, 13), (16, 30), (33, 23)]]
 TENCENT_SIZES = [[(8, 8)], [(16, 16)], [(32, 32)], [(64, 64)]]
-
-COCO_NMS = dict(type='nms', iou_threshold=0.65)
-
-
-def _csp(img, batch, dist, seed, C=80, nms_pre=1000, score_thr=0.001, nms=None, max_per_img=300, **kw):
-    strides = [8, 16, 32]
-    d = dict(mode=capi.MODE_CSP, batch=batch, sizes=[(img // s, img // s) for s in strides], strides=strides,
-             base_sizes=V4_SIZES, num_classes=C, nms_pre=nms_pre, score_thr=score_thr, nms=dict(nms or COCO_NMS),
-             max_per_img=max_per_img, dist=dist, seed=seed)
-    d.update(kw)
-    return d
-
-
-def _v3(img, batch, dist, seed, C=80, nms_pre=1000, score_thr=0.05, conf_thr=0.005, nms=None, max_per_img=100, **kw):
-    strides = [32, 16, 8]
-    d = dict(mode=capi.MODE_V3, batch=batch, sizes=[(img // s, img // s) for s in strides], strides=strides,
-             base_sizes=V3_SIZES, num_classes=C, nms_pre=nms_pre, score_thr=score_thr, conf_thr=conf_thr,
-             nms=dict(nms or dict(type='nms', iou_threshold=0.45)), max_per_img=max_per_img, dist=dist, seed=seed)
-    d.update(kw)
-    return d
 
 
 SAT = ((0.0, 0.0, 0.0), (30.0, 30.0, 30.0))        # saturated logits: sigmoid hits 0/1 exactly -> many exact ties
@@ -97,53 +77,19 @@ CASES = {
     'csp1280_sparse': _csp(1280, 2, 'sparse', 48),
 }
 
+# The reference's own ready-made deterministic input: tests/test_onnx/data/yolov3_head_get_bboxes.pkl with the head
+# of tests/test_onnx/test_head.py:103-129 (YOLOV3Head, 4 classes, maps (1,27,32,32),(1,27,16,16),(1,27,8,8) from
+# torch.rand, no nms_pre). The tensors themselves are stored in tests/golden/v3_onnx_pkl.npz (36 KB) next to the
+# reference's outputs, because /root/reference does not exist on the GPU box.
+PKL_CASE = dict(mode=capi.MODE_V3, batch=1, sizes=[(32, 32), (16, 16), (8, 8)], strides=[32, 16, 8], base_sizes=V3_SIZES,
+                num_classes=4, nms_pre=-1, score_thr=0.05, conf_thr=0.005, nms=dict(type='nms', iou_threshold=0.45),
+                max_per_img=100, dist=None, seed=0)
+
 # subset that is also frozen as golden vectors produced by the reference's own source (tests/golden)
 GOLDEN_CASES = ['csp608_sparse', 'csp608_dense', 'csp608_dense_thr07', 'csp608_sparse_thr002', 'csp320_nopre_sparse', 'csp_odd', 'csp416_rescale',
                 'csp_saturated', 'tencent_agnostic', 'csp_nms_agnostic', 'csp_nms_offset1', 'csp_nms_maxnum',
                 'csp_force_global', 'v3_416_sparse', 'v3_416_dense', 'v3_320_mid', 'v3_rescale', 'csp640_sparse',
                 'csp_empty', 'v3_640_sparse', 'csp1280_sparse']
-
-
-def build_params(case, batch=None):
-    from yolopp.heads import parse_nms_cfg
-    mode = case['mode']
-    return capi.make_params(
-        mode, batch or case['batch'], case['sizes'], case['strides'], case['strides'], case['base_sizes'],
-        case['num_classes'], class_agnostic=case.get('class_agnostic', False), nms_pre=case['nms_pre'],
-        score_thr=case['score_thr'], conf_thr=case.get('conf_thr', -1.0) if mode == capi.MODE_V3 else -1.0,
-        max_per_img=case['max_per_img'], rescale=case.get('rescale', False), out_capacity=case.get('out_capacity', 0),
-        **parse_nms_cfg(case['nms']))
-
-
-def ref_cfg(case):
-    """The reference's test_cfg for this case."""
-    cfg = dict(nms_pre=case['nms_pre'], score_thr=case['score_thr'], nms=dict(case['nms']),
-               max_per_img=case['max_per_img'], min_bbox_size=0)
-    if case['mode'] == capi.MODE_V3:
-        cfg['conf_thr'] = case.get('conf_thr', -1)
-    return cfg
-
-
-def scale_factors(case):
-    if not case.get('rescale', False):
-        return None
-    return np.asarray(case['scale_factors'], np.float32)
-
-
-def host_levels(case, params=None):
-    """The case's synthetic head tensors generated on the HOST (oracle.synth_level; same bits as the device)."""
-    from oracle import oracle
-    p = params or build_params(case)
-    mean, std = ysynth.dist_stats(case['dist'])
-    na = p.num_attrib
-    m = np.array([mean[0]] * 4 + [mean[1]] + [mean[2]] * (na - 5), np.float32)
-    s = np.array([std[0]] * 4 + [std[1]] + [std[2]] * (na - 5), np.float32)
-    out = []
-    for l in range(p.num_levels):
-        hw = p.height[l] * p.width[l]
-        x = oracle.synth_level(p.batch, p.num_anchors, na, hw, m, s, ysynth.level_seed(case['seed'], l))
-        out.append(x.reshape(p.level_shape(l)))
-    return out
 
 
 def asis_rel_err(ref_dets, got_dets):
@@ -162,3 +108,19 @@ def asis_rel_err(ref_dets, got_dets):
     box = (np.abs(a[:, :4] - o[:, :4]) / np.maximum(np.abs(a[:, :4]), scale)).max()
     score = (np.abs(a[:, 4] - o[:, 4]) / np.maximum(np.abs(a[:, 4]), 1e-3)).max()
     return float(max(box, score))
+
+
+def asis_strict_rel_err(ref_dets, got_dets):
+    """north_star's tolerance read literally: |a - b| / |a| per COORDINATE (and per score), floor 1e-3 on the
+    denominator. Reported next to `asis_rel_err`; see STRICT_OUTLIERS."""
+    a = np.asarray(ref_dets, np.float64).reshape(-1, 5)
+    o = np.asarray(got_dets, np.float64).reshape(-1, 5)
+    if a.shape[0] == 0:
+        return 0.0
+    return float((np.abs(a - o) / np.maximum(np.abs(a), 1e-3)).max())
+
+
+# Golden cases whose strict per-coordinate deviation from the reference-as-it-runs exceeds 1e-5, with the measured
+# value (documented in INTEGRATION.md §3a): one corner of one box at 1280^2 is -0.39 = 34.1 - 34.5, a 2-ulp-of-34
+# absolute difference (7.6e-6) between torch's SIMD sigmoid and the canonical polynomial is 1.94e-5 of the corner.
+STRICT_OUTLIERS = {'csp1280_sparse': 2.0e-5}

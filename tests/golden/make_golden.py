@@ -97,6 +97,91 @@ def run_reference(case, levels, canonical):
     return res
 
 
+def run_reference_taps(case, levels):
+    """Intermediate tensors of the reference (canonical flavour, CSP convention), per image: what enters
+    multiclass_nms (yolocsp_head.py:374-376) — `bbox_pred` (R,4), `cls_pred` (R,C) — the candidate mask / scores the
+    reference derives from them (bbox_nms.py:42-62) and `topk_inds` (yolocsp_head.py:350-355). SURVEY.md A.3."""
+    assert case['mode'] == capi.MODE_CSP
+    ref = refexec.load_reference()
+    head = build_ref_head(ref, case)
+    B = case['batch']
+    sf = cases.scale_factors(case)
+    metas = [dict(scale_factor=(sf[b] if sf is not None else 1.0)) for b in range(B)]
+    topk_rec, rec = [], []
+    mod = ref.yolocsp_module
+    orig_mnms = mod.multiclass_nms
+
+    def mnms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None, return_inds=False):
+        scores = multi_scores[:, :-1]
+        valid = scores > score_thr                      # bbox_nms.py:54
+        if score_factors is not None:
+            scores = scores * score_factors[:, None]    # bbox_nms.py:57-62
+        tap = torch.where(valid, scores, torch.full_like(scores, float('nan')))
+        rec.append(dict(boxes=multi_bboxes.clone(), scores=tap.clone()))
+        return orig_mnms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num, score_factors, return_inds)
+
+    mod.multiclass_nms = mnms
+    try:
+        with refexec.canonical_ties(topk_rec), refexec.canonical_transcendentals(oracle), torch.no_grad():
+            head.get_bboxes([torch.from_numpy(x.copy()) for x in levels], metas, rescale=case.get('rescale', False))
+    finally:
+        mod.multiclass_nms = orig_mnms
+    assert len(rec) == B and len(topk_rec) == B
+    return (np.stack([t.numpy().astype(np.int32) for t in topk_rec]),
+            np.stack([r['boxes'].numpy() for r in rec]).astype(np.float32),
+            np.stack([r['scores'].numpy() for r in rec]).astype(np.float32))
+
+
+TAP_CASES = ['csp608_sparse', 'csp416_rescale', 'csp_odd', 'csp_saturated']
+
+
+def main_taps(names):
+    """tests/golden/taps_<case>.npz: topk_inds (B,R), boxes bits (B,R,4), scores bits (B,R,C; NaN = no candidate)."""
+    for name in names or TAP_CASES:
+        case = cases.CASES[name]
+        p = cases.build_params(case)
+        levels = cases.host_levels(case, p)
+        topk, boxes, scores = run_reference_taps(case, levels)
+        R = topk.shape[1]
+        o_topk, o_boxes, o_scores = oracle.get_taps(p, levels, R, cases.scale_factors(case))
+        nan_ref, nan_orc = np.isnan(scores), np.isnan(o_scores)
+        ok = (np.array_equal(topk, o_topk) and np.array_equal(boxes.view(np.uint32), o_boxes.view(np.uint32))
+              and np.array_equal(nan_ref, nan_orc)
+              and np.array_equal(scores[~nan_ref].view(np.uint32), o_scores[~nan_orc].view(np.uint32)))
+        np.savez_compressed(os.path.join(HERE, f'taps_{name}.npz'), topk_inds=topk, boxes_bits=boxes.view(np.uint32),
+                            scores_bits=np.where(nan_ref, np.uint32(0xFFFFFFFF), scores.view(np.uint32)))
+        print(f'taps {name:22s} rows={R} candidates={int((~nan_ref).sum())} oracle_bit_exact={ok}')
+        if not ok:
+            raise SystemExit(f'{name}: the C oracle taps do not reproduce the reference bit-exactly')
+
+
+def main_pkl():
+    """tests/golden/v3_onnx_pkl.npz: the reference's own fixed input tensors (tests/test_onnx/data/
+    yolov3_head_get_bboxes.pkl, head config of tests/test_onnx/test_head.py:103-129) and what its YOLOV3Head.get_bboxes
+    returns for them (with_nms=True), both flavours."""
+    import pickle
+    with open(os.path.join(refexec.REF_ROOT, 'tests/test_onnx/data/yolov3_head_get_bboxes.pkl'), 'rb') as f:
+        maps = pickle.load(f)
+    levels = [np.ascontiguousarray(t.numpy(), np.float32) for t in maps]
+    case = cases.PKL_CASE
+    p = cases.build_params(case)
+    assert [tuple(x.shape) for x in levels] == [p.level_shape(l) for l in range(p.num_levels)]
+    canon = pack(run_reference(case, levels, True), p.capacity)
+    asis = pack(run_reference(case, levels, False), p.capacity)
+    orc = oracle.get_bboxes(p, levels)
+    n = canon['count'][0]
+    ok = (np.array_equal(orc['count'], canon['count']) and np.array_equal(orc['labels'][0], canon['labels'][0, :n])
+          and np.array_equal(orc['dets'][0].view(np.uint32), canon['dets'][0, :n].view(np.uint32)))
+    np.savez_compressed(os.path.join(HERE, 'v3_onnx_pkl.npz'), level0=levels[0], level1=levels[1], level2=levels[2],
+                        canon_count=canon['count'], canon_ncand=canon['ncand'], canon_dets_bits=canon['dets'].view(np.uint32),
+                        canon_labels=canon['labels'], asis_count=asis['count'], asis_dets=asis['dets'],
+                        asis_labels=asis['labels'])
+    print(f'v3_onnx_pkl count={canon["count"]} ncand={canon["ncand"]} oracle_bit_exact={ok} '
+          f'asis_labels_equal={np.array_equal(canon["labels"], asis["labels"])}')
+    if not ok:
+        raise SystemExit('v3_onnx_pkl: the C oracle does not reproduce the reference bit-exactly')
+
+
 def pack(res, cap):
     B = len(res)
     out = dict(count=np.zeros(B, np.int32), ncand=np.zeros(B, np.int32), dets=np.zeros((B, cap, 5), np.float32),
@@ -114,6 +199,14 @@ def pack(res, cap):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == '--taps':
+        assert refexec.available(), 'reference tree not found'
+        torch.set_num_threads(8)
+        return main_taps(sys.argv[2:])
+    if len(sys.argv) > 1 and sys.argv[1] == '--pkl':
+        assert refexec.available(), 'reference tree not found'
+        torch.set_num_threads(8)
+        return main_pkl()
     names = sys.argv[1:] or cases.GOLDEN_CASES
     assert refexec.available(), 'reference tree not found'
     torch.set_num_threads(8)

@@ -37,7 +37,8 @@ def test_planning_calls_need_no_device():
     assert 20e6 < ws < 200e6
     info = capi.describe(p)
     assert info.anchors_per_image == 22743 and info.rows_per_image == 1000 and info.num_attrib == 85
-    assert info.tma_level_mask == 0b011          # 76^2 and 38^2 planes are 16-byte aligned, 19^2 is not
+    assert info.tma_level_mask == 0b111          # 76^2 / 38^2: plain TMA tiles; 19^2 (plane stride not 16-byte
+                                                 # aligned): quad-row TMA tiles — every level is streamed
     assert info.tma_bytes_per_image + info.ldg_bytes_per_image == 7732620  # 4*3*85*7581
     assert info.kernel_launches == 3             # select, persistent decode (TMA + gather tiles), per-image NMS
     assert info.ldg_blocks == 0 and info.ldg_bytes_per_image == 0
@@ -45,6 +46,7 @@ def test_planning_calls_need_no_device():
     p2 = cases.build_params(cases.CASES['csp320_nopre_dense'])
     i2 = capi.describe(p2)
     assert i2.tma_level_mask == 0 and i2.kernel_launches == 2 and i2.rows_per_image == i2.anchors_per_image
+    assert i2.dense_tiles > 0 and i2.ldg_blocks == 0   # dense admission: thread-per-position kernel
     # V3: one top-k segment per level
     p3 = cases.build_params(cases.CASES['v3_416_sparse'])
     assert capi.describe(p3).rows_per_image == 507 + 1000 + 1000   # 13^2*3 < nms_pre: that level keeps all rows
@@ -53,7 +55,7 @@ def test_planning_calls_need_no_device():
 @pytest.mark.parametrize('mutate', [
     lambda p: setattr(p, 'abi_version', 99), lambda p: setattr(p, 'mode', 5), lambda p: setattr(p, 'batch', 0),
     lambda p: setattr(p, 'num_levels', 9), lambda p: setattr(p, 'num_anchors', 0), lambda p: setattr(p, 'num_classes', 5000),
-    lambda p: setattr(p, 'nms_offset', 2), lambda p: setattr(p, 'nms_pre', 5000), lambda p: setattr(p, 'max_per_img', 5000),
+    lambda p: setattr(p, 'nms_offset', 2), lambda p: setattr(p, 'layout', 2), lambda p: setattr(p, 'max_per_img', 5000),
     lambda p: (setattr(p, 'max_per_img', -1), setattr(p, 'out_capacity', 0)),
 ])
 def test_invalid_params_are_rejected(mutate):
@@ -70,7 +72,7 @@ def test_get_bboxes_rejects_bad_calls_without_touching_the_device():
     out = capi.YoloppOutputs()
     ptrs = (ctypes.c_void_p * 3)()
     assert lib.yolopp_get_bboxes(ctypes.byref(p), ptrs, None, ctypes.byref(out), None, 0, None) == capi.E_INVALID
-    out = capi.YoloppOutputs(1, 1, 1, 1, 1, 1, 1)
+    out = capi.YoloppOutputs(1, 1, 1, 1, 1, 1, 1, None, None)
     assert lib.yolopp_get_bboxes(ctypes.byref(p), ptrs, None, ctypes.byref(out), None, 0, None) == capi.E_WORKSPACE
 
 
@@ -168,3 +170,65 @@ def test_bbox2result_split():
     np.testing.assert_array_equal(out[2], dets[[0, 2]])
     empty = yolopp.bbox2result(np.zeros((0, 5), np.float32), np.zeros((0, ), np.int64), 3)
     assert [o.shape for o in empty] == [(0, 5)] * 3 and empty[0].dtype == np.float32
+
+
+def test_plans_for_layouts_and_large_nms_pre():
+    """NHWC: row-driven decode (select + rows + NMS), bytes = the admitted rows only; nms_pre beyond the select
+    kernel's shared-memory sort capacity is planned (chunked sort), not rejected; 1280^2 keeps the fast top-k by
+    staging a sample."""
+    nh = cases.build_params(dict(cases.CASES['csp608_sparse'], batch=64))
+    nh.layout = capi.LAYOUT_NHWC
+    i = capi.describe(nh)
+    assert i.kernel_launches == 3 and i.tma_tiles == 0 and i.dense_tiles == 0
+    assert i.ldg_bytes_per_image == 4 * 85 * 1000 and i.tma_bytes_per_image == 0
+    big = cases.build_params(dict(cases.CASES['csp608_sparse'], nms_pre=5000))
+    assert capi.describe(big).rows_per_image == 5000
+    assert capi.load_library().yolopp_workspace_bytes(ctypes.byref(big)) > 0
+    p1280 = cases.build_params(dict(cases.CASES['csp1280_sparse'], batch=8))
+    assert capi.describe(p1280).tma_level_mask == 0b111
+
+
+def test_plan_and_stage_entries_reject_bad_calls_without_a_device():
+    lib = capi.load_library()
+    p = cases.build_params(cases.CASES['csp_tiny'])
+    ptrs = (ctypes.c_void_p * 3)()
+    h = ctypes.c_void_p()
+    out = capi.YoloppOutputs(1, 1, 1, 1, 1, 1, 1, None, None)
+    assert lib.yolopp_plan_create(ctypes.byref(p), ptrs, None, ctypes.byref(out), None, 0, ctypes.byref(h)) == capi.E_WORKSPACE
+    assert not h.value
+    assert lib.yolopp_plan_run(None, None) == capi.E_INVALID
+    lib.yolopp_plan_destroy(None)
+    assert lib.yolopp_topk_conf(ctypes.byref(p), ptrs, None, None, 0, None) == capi.E_INVALID
+    assert lib.yolopp_decode(ctypes.byref(p), ptrs, None, None, None, None, None, 0, None) == capi.E_INVALID
+    assert lib.yolopp_mish_forward(None, None, -1, 0, None) == capi.E_INVALID
+    assert lib.yolopp_mish_forward(ctypes.c_void_p(16), ctypes.c_void_p(16), 4, 7, None) == capi.E_INVALID
+    assert lib.yolopp_mish_backward(ctypes.c_void_p(16), ctypes.c_void_p(16), ctypes.c_void_p(8), 4, 0, None) == capi.E_INVALID
+
+
+@pytest.mark.skipif(not os.path.isfile('/root/reference/mmdet/models/dense_heads/yolocsp_head.py'),
+                    reason='reference tree not present (GPU box)')
+@pytest.mark.parametrize('name', ['csp608_sparse', 'tencent_agnostic', 'csp416_rescale', 'v3_416_sparse', 'csp_nms_offset1'])
+def test_patch_head_on_the_live_reference_head(name):
+    """patch_head() on an instance of the REFERENCE's own head class (mmdet/models/dense_heads/yolocsp_head.py:54-178,
+    yolo_head.py:20-110, executed from /root/reference): the yolopp_params it extracts from that instance
+    (anchor_generator, featmap_strides, num_classes, class_agnostic, test_cfg) are byte-identical to the params the
+    parity tests use for the same configuration — i.e. the drop-in binding reads a real mmdet head correctly."""
+    import importlib.util
+    import torch
+    import yolopp
+    from yolopp import heads
+    from oracle import refexec
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(ROOT, 'tests', 'golden', 'make_golden.py'))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    case = cases.CASES[name]
+    ref = refexec.load_reference()
+    head = mg.build_ref_head(ref, case)
+    assert type(head).__module__ != yolopp.heads.__name__  # really the reference's class
+    yolopp.patch_head(head)
+    p_ref = heads.head_params(head, pred_shapes=case['sizes'], batch=case['batch'], rescale=case.get('rescale', False))
+    p_own = cases.build_params(case)
+    assert bytes(p_ref) == bytes(p_own)
+    # the patched method validates like the reference (level count) before touching the device
+    with pytest.raises(AssertionError):
+        head.get_bboxes([torch.zeros(1, 1, 1, 1)], [dict(scale_factor=1.0)])

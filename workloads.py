@@ -1,0 +1,86 @@
+"""Path configurations shared by bench.py and the tests: the BASELINE.json workloads and the helpers that turn a
+configuration dict into yolopp_params / the reference's test_cfg. (tests/cases.py adds the parity-only cases.)"""
+import numpy as np
+
+from yolopp import _capi as capi
+from yolopp import synth as ysynth
+
+V4_SIZES = [[(12, 16), (19, 36), (40, 28)], [(36, 75), (76, 55), (72, 146)], [(142, 110), (192, 243), (459, 401)]]
+V3_SIZES = [[(116, 90), (156, 198), (373, 326)], [(30, 61), (62, 45), (59, 119)], [(10, 13), (16, 30), (33, 23)]]
+
+COCO_NMS = dict(type='nms', iou_threshold=0.65)
+
+
+def csp_case(img, batch, dist, seed, C=80, nms_pre=1000, score_thr=0.001, nms=None, max_per_img=300, **kw):
+    """YOLOCSPHead + YOLOV4BBoxCoder (configs/yolov4, configs/yolov5), COCO eval setting by default."""
+    strides = [8, 16, 32]
+    d = dict(mode=capi.MODE_CSP, batch=batch, sizes=[(img // s, img // s) for s in strides], strides=strides,
+             base_sizes=V4_SIZES, num_classes=C, nms_pre=nms_pre, score_thr=score_thr, nms=dict(nms or COCO_NMS),
+             max_per_img=max_per_img, dist=dist, seed=seed)
+    d.update(kw)
+    return d
+
+
+def v3_case(img, batch, dist, seed, C=80, nms_pre=1000, score_thr=0.05, conf_thr=0.005, nms=None, max_per_img=100, **kw):
+    """YOLOV3Head + YOLOBBoxCoder (configs/yolo/yolov3_d53_mstrain-608_273e_coco.py:48-54)."""
+    strides = [32, 16, 8]
+    d = dict(mode=capi.MODE_V3, batch=batch, sizes=[(img // s, img // s) for s in strides], strides=strides,
+             base_sizes=V3_SIZES, num_classes=C, nms_pre=nms_pre, score_thr=score_thr, conf_thr=conf_thr,
+             nms=dict(nms or dict(type='nms', iou_threshold=0.45)), max_per_img=max_per_img, dist=dist, seed=seed)
+    d.update(kw)
+    return d
+
+
+# bench.py workloads (BASELINE.json configs[1..4]); `batch` = images per call on one GPU, `global_batch` (strong
+# scaling only) = images of the whole job, split over the GPUs and processed `batch` at a time.
+WORKLOADS = {
+    'yolov4_608_b64_coco_sparse': csp_case(608, 64, 'sparse', 11),      # configs[1]: the headline
+    'yolov4_608_b64_dense': csp_case(608, 64, 'dense', 12),             # configs[2]
+    'yolov5_640_b128_sparse': csp_case(640, 128, 'sparse', 46),         # configs[3] (i): configs/yolov5 = the same head
+    'yolov3_640_b128_sparse': v3_case(640, 128, 'sparse', 47),          # configs[3] (ii): the other decode convention
+    'yolov4_1280_b128_sparse': csp_case(1280, 128, 'sparse', 48),       # one GPU's shard of configs[4]
+    'yolov4_1280_b1024_sparse': csp_case(1280, 128, 'sparse', 48, global_batch=1024),  # configs[4]: strong scaling
+}
+
+
+def build_params(case, batch=None):
+    from yolopp.heads import parse_nms_cfg
+    mode = case['mode']
+    return capi.make_params(
+        mode, batch or case['batch'], case['sizes'], case['strides'], case['strides'], case['base_sizes'],
+        case['num_classes'], class_agnostic=case.get('class_agnostic', False), nms_pre=case['nms_pre'],
+        score_thr=case['score_thr'], conf_thr=case.get('conf_thr', -1.0) if mode == capi.MODE_V3 else -1.0,
+        max_per_img=case['max_per_img'], rescale=case.get('rescale', False), out_capacity=case.get('out_capacity', 0),
+        **parse_nms_cfg(case['nms']))
+
+
+def ref_cfg(case):
+    """The reference's test_cfg for this case."""
+    cfg = dict(nms_pre=case['nms_pre'], score_thr=case['score_thr'], nms=dict(case['nms']),
+               max_per_img=case['max_per_img'], min_bbox_size=0)
+    if case['mode'] == capi.MODE_V3:
+        cfg['conf_thr'] = case.get('conf_thr', -1)
+    return cfg
+
+
+def scale_factors(case):
+    if not case.get('rescale', False):
+        return None
+    return np.asarray(case['scale_factors'], np.float32)
+
+
+def host_levels(case, params=None):
+    """The case's synthetic head tensors generated on the HOST by the checker's generator (oracle.synth_level; same
+    bits as the device generator). Test / CPU-baseline infrastructure: imports oracle/."""
+    from oracle import oracle
+    p = params or build_params(case)
+    mean, std = ysynth.dist_stats(case['dist'])
+    na = p.num_attrib
+    m = np.array([mean[0]] * 4 + [mean[1]] + [mean[2]] * (na - 5), np.float32)
+    s = np.array([std[0]] * 4 + [std[1]] + [std[2]] * (na - 5), np.float32)
+    out = []
+    for l in range(p.num_levels):
+        hw = p.height[l] * p.width[l]
+        x = oracle.synth_level(p.batch, p.num_anchors, na, hw, m, s, ysynth.level_seed(case['seed'], l))
+        out.append(x.reshape(p.level_shape(l)))
+    return out
