@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-verify', action='store_true')
     ap.add_argument('--no-affinity', action='store_true')
-    ap.add_argument('--pipeline-depth', type=int, default=3,
+    ap.add_argument('--pipeline-depth', type=int, default=6,
                     help='batches in flight on separate CUDA streams (1 = strictly one batch after the other)')
     return ap.parse_args()
 
@@ -352,7 +352,7 @@ def run_yolopp(args):
     t_host0 = time.perf_counter()
     last = None
     for i in range(calls):
-        last = (i % n_sets, pipe.submit(inputs[i % n_sets], sf))
+        last = (i % n_sets, pipe.submit(inputs[i % n_sets], sf, inputs_ready=True))  # (synthetic inputs: synchronised above)
     host_submit_ms = (time.perf_counter() - t_host0) * 1e3 / calls  # host time to issue one call (not a GPU time)
     pipe.join()
     ev1.record()

@@ -104,7 +104,10 @@ typedef struct yolopp_params {
        logical tensor, (B, H, W, A*(5+C)) — what a cuDNN NHWC convolution writes. With NHWC the 5+C logits of an
        anchor are contiguous and only the admitted anchors are read (no pass over the whole tensor). */
     int32_t layout;
-    int32_t reserved[5];
+    /* nms_cfg.get('score_threshold', 0) (mmcv NMSop.forward): when > 0 only candidates with score > threshold take
+       part in the greedy pass (the regime decision and boxes.max() still see every candidate) */
+    float nms_score_thr;
+    int32_t reserved[4];
 } yolopp_params;
 
 #define YOLOPP_LAYOUT_NCHW 0
@@ -161,8 +164,9 @@ int yolopp_get_bboxes_profiled(const yolopp_params* p, const float* const* level
 /*
  * Plan handle for serving loops: everything yolopp_get_bboxes derives per call (validation, workspace layout, TMA
  * tensor maps, grid sizes) is computed once for a fixed set of buffers; yolopp_plan_run is then three kernel
- * launches and nothing else on the host. The handle is ordinary host memory owned by the caller (create / destroy),
- * holds no device memory and no global state; the buffers it was created for must stay alive while it is used.
+ * launches — captured once into an executable CUDA graph, so a run is a single cudaGraphLaunch — and nothing else on
+ * the host. The handle is host memory owned by the caller (create / destroy) plus that graph object; it holds no
+ * device buffers and no global state; the buffers it was created for must stay alive while it is used.
  * One plan may be run on any stream, but not concurrently with itself (it owns its workspace).
  */
 typedef struct yolopp_plan yolopp_plan;
@@ -228,7 +232,8 @@ int yolopp_coder_decode(int mode, const float* bboxes, const float* pred, float 
  * Replaces the third-party call at mmdet/core/post_processing/bbox_nms.py:84 and the direct callers
  * (rpn_head.py:247, cascade_rpn_head.py:670, ...). Same semantics as the in-path NMS: class-offset boxes
  * boxes + idx*(max+1) unless class_agnostic, ONE greedy pass when n < split_thr else classes independent,
- * result in (score desc, index asc) order, first max_num kept.
+ * result in (score desc, index asc) order, first max_num kept. score_threshold > 0: mmcv's NMSop prefilter
+ * (only boxes with score > score_threshold enter the greedy pass).
  *   boxes  DEVICE [n][4] fp32 (16-byte aligned), scores DEVICE [n], idxs DEVICE [n] int64 in [0, num_labels) or NULL
  *   dets   DEVICE [cap][5], keep DEVICE [cap] int64 (indices into the inputs), cap = min(4096, max_num if
  *          0 < max_num < n else n)  — the kept list lives in shared memory, so max_num must be <= 4096
@@ -236,8 +241,8 @@ int yolopp_coder_decode(int mode, const float* bboxes, const float* pred, float 
  *          4096 boxes survive)
  */
 int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, int32_t num_labels,
-                       float iou_thr, int nms_offset, int split_thr, int class_agnostic, int max_num, float* dets,
-                       int64_t* keep, int32_t* num_keep, void* stream);
+                       float iou_thr, float score_threshold, int nms_offset, int split_thr, int class_agnostic,
+                       int max_num, float* dets, int64_t* keep, int32_t* num_keep, void* stream);
 
 /*
  * multiclass_nms (mmdet/core/post_processing/bbox_nms.py:7-93) on device, for the other heads that share the
@@ -253,7 +258,8 @@ int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* i
 size_t yolopp_nms_workspace_bytes(int64_t n, int32_t num_classes);
 int yolopp_multiclass_nms(const float* multi_bboxes, int boxes_per_class, const float* multi_scores, int64_t n,
                           int32_t num_classes, float score_thr, const float* score_factors, float iou_thr,
-                          int nms_offset, int split_thr, int class_agnostic, int nms_max_num, int max_num, float* dets,
+                          float nms_score_threshold, int nms_offset, int split_thr, int class_agnostic, int nms_max_num,
+                          int max_num, float* dets,
                           int64_t* labels, int64_t* flat_inds, int32_t* num_keep, int32_t* num_candidates,
                           void* workspace, size_t workspace_bytes, void* stream);
 

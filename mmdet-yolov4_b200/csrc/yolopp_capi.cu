@@ -58,7 +58,8 @@ struct Plan {
         if (!(cond)) return false; \
     } while (0)
 
-constexpr size_t SMEM_LIMIT = 227 * 1024;  // dynamic shared memory a CTA may opt into on sm_100
+constexpr size_t SMEM_LIMIT = 232448 - 10448;  // dynamic shared memory a CTA may use on sm_100: the 227 KB opt-in limit
+                                               // minus the per-image kernels' static shared memory (10 448 B)
 
 // Validates the params and lays the workspace out. Level pointers are filled in by the caller.
 bool make_plan(const yolopp_params* p, Plan* plan) {
@@ -89,6 +90,7 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     d.score_thr = p->score_thr;
     d.conf_thr = p->conf_thr;
     d.iou_thr = p->iou_thr;
+    d.nms_score_thr = p->nms_score_thr;
     d.foff = (float)p->nms_offset;
     d.split_thr = p->split_thr;
     d.nms_agnostic = p->nms_class_agnostic ? 1 : 0;
@@ -173,9 +175,9 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
             int slots = max_m;
             if (!(max_m <= 32768 && plan->sel_smem + (size_t)max_m * 4 <= 200 * 1024)) {
                 int stride = 2;
-                while ((max_m + stride - 1) / stride > 16384) stride <<= 1;
+                while ((max_m + stride - 1) / stride + 4 * d.L * d.A > 16384) stride <<= 1;
                 d.sel_stride = stride;
-                slots = (max_m + stride - 1) / stride;
+                slots = (max_m + stride - 1) / stride + 4 * d.L * d.A;  // (+ per-plane alignment padding of the sample)
             }
             d.sel_stage = slots;
             plan->sel_smem += (size_t)slots * 4;
@@ -199,33 +201,41 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
         plan->rows_blocks = (int)(((long long)d.B * d.R + ROWS_WARPS - 1) / ROWS_WARPS);
     } else {
         bool tma_fits = NA <= 256;
+#ifdef YPP_QUAD
         for (int l = 0; l < d.L && tma_fits; ++l) {
             const SegDev& sg = d.seg[d.lv[l].seg];
             if (sg.has_topk && (long long)sg.k * 4 <= sg.N && d.lv[l].HW % 4 != 0) d.dec_quad = 1;
         }
+#endif
         StageGeom geom = stage_geom(NA, d.dec_quad);
         plan->dec_smem = 1024 /*alignment slack*/ + 1024 /*barriers*/ + (size_t)DEC_STAGES * geom.stage_bytes;
         tma_fits = tma_fits && plan->dec_smem <= 200 * 1024;
         plan->dec_ctas_per_sm = plan->dec_smem <= 110 * 1024 ? 2 : 1;
         // persistent decode kernel: sparse-admission levels — TMA tiles where the plane stride is 16-byte aligned,
-        // quad-row TMA tiles where it is not
+        // gather tiles where it is not (quad-row TMA tiles in the -DYPP_QUAD build: measured slower)
         for (int l = 0; l < d.L; ++l) {
             LevelDev& lv = d.lv[l];
             const SegDev& sg = d.seg[lv.seg];
             const bool sparse = sg.has_topk && (long long)sg.k * 4 <= sg.N;
-            lv.use_tma = (tma_fits && sparse) ? ((lv.HW % 4 == 0) ? 1 : 3) : 0;
+#ifdef YPP_QUAD
+            lv.use_tma = (tma_fits && sparse) ? ((lv.HW % 4 == 0) ? 1 : 3) : 0;  // (opt-in build: quad-row TMA tiles)
+#else
+            lv.use_tma = (tma_fits && sparse) ? ((lv.HW % 4 == 0) ? 1 : 2) : 0;
+#endif
             lv.dense = (!lv.use_tma && !sparse) ? 1 : 0;
             lv.qrows = (int)(((long long)d.B * d.A * NA) / 4);
         }
-#ifdef YPP_QUAD_LAST
-        const int order[3] = {1, 3, -1};
-#else
-        const int order[3] = {3, 1, -1};  // unaligned levels first (they are the small, coarse levels)
-#endif
+        // tile enumeration of the persistent kernel: unaligned levels (quad-row / gather tiles) first — they are the
+        // small, coarse levels — then the plain TMA levels
         for (int pi = 0; pi < 2; ++pi) {
             for (int l = 0; l < d.L; ++l) {
                 LevelDev& lv = d.lv[l];
-                if (lv.use_tma != order[pi]) continue;
+#ifdef YPP_QUAD_LAST
+                const bool mine = pi == 0 ? lv.use_tma == 1 : (lv.use_tma == 2 || lv.use_tma == 3);
+#else
+                const bool mine = pi == 0 ? (lv.use_tma == 2 || lv.use_tma == 3) : lv.use_tma == 1;
+#endif
+                if (!mine) continue;
                 lv.tpp = (lv.HW + TILE_T - 1) / TILE_T;
                 lv.tile0 = tma_tiles;
                 long long t = (long long)lv.tpp * d.B * d.A;
@@ -333,10 +343,17 @@ DeviceInfo device_info() {
     if (major != 10) return di;  // sm_100a only: no other code path exists
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaError_t e = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(decode_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+    // (the opt-in limit covers static + dynamic shared memory of a kernel)
+    auto opt_in = [&](const void* fn) -> cudaError_t {
+        cudaFuncAttributes fa;
+        cudaError_t e2 = cudaFuncGetAttributes(&fa, fn);
+        if (e2 != cudaSuccess) return e2;
+        return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    };
+    cudaError_t e = opt_in((const void*)select_kernel);
+    if (e == cudaSuccess) e = opt_in((const void*)decode_tma_kernel<0>);
+    if (e == cudaSuccess) e = opt_in((const void*)decode_tma_kernel<1>);
+    if (e == cudaSuccess) e = opt_in((const void*)nms_image_kernel);
     if (e != cudaSuccess) {
         di.rc = cuda_rc(e);
         return di;
@@ -356,6 +373,7 @@ struct yolopp_plan {
     TmapPack maps;
     int dec_grid;
     int stop_after;  // 0: whole path, 1: after the top-k, 2: after the decode (stage entries)
+    cudaGraphExec_t exec;  // plan handles only: the call's launches as one executable graph (null: launch directly)
 };
 
 namespace {
@@ -373,6 +391,7 @@ int prepare(const yolopp_params* p, const float* const* level_ptrs, const float*
     const DeviceInfo di = device_info();
     if (di.rc != YOLOPP_OK) return di.rc;
     pl->stop_after = stop_after;
+    pl->exec = nullptr;
     DevParams& d = plan.d;
     for (int l = 0; l < d.L; ++l) {
         if (!level_ptrs[l] || ((uintptr_t)level_ptrs[l] & 3) != 0) return YOLOPP_E_INVALID;
@@ -427,17 +446,17 @@ int prepare(const yolopp_params* p, const float* const* level_ptrs, const float*
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             } else if (lv.use_tma == 3) {
                 // plane stride 4 * HW bytes is not a multiple of 16: view the tensor as rows of FOUR planes (stride
-                // 16 * HW bytes); a box = 32 positions of one plane-in-row x the rows a slab spans
+                // 16 * HW bytes); a box = the aligned superset of 64 positions of one plane-in-row x the rows a slab spans
                 if (lv.qrows < 1) {
                     d.lv[l].use_tma = 2;
                     continue;
                 }
                 cuuint64_t gdim[2] = {(cuuint64_t)lv.HW * 4, (cuuint64_t)lv.qrows};
                 cuuint64_t gstr[1] = {(cuuint64_t)lv.HW * 16};
-                cuuint32_t box[2] = {(cuuint32_t)TILE_SUB, (cuuint32_t)geom.quad_rows};
+                cuuint32_t box[2] = {(cuuint32_t)QUAD_W, (cuuint32_t)geom.quad_rows};
                 cuuint32_t estr[2] = {1, 1};
                 r = enc(&pl->maps.m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)lv.ptr, gdim, gstr, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             }
             if (r != CUDA_SUCCESS) return YOLOPP_E_CUDA + 999;
@@ -568,12 +587,32 @@ int yolopp_plan_create(const yolopp_params* p, const float* const* level_ptrs, c
         free(pl);
         return rc;
     }
+    // The launches of one call, captured once into an executable graph: a run is then ONE driver call instead of
+    // three launches (+ a memset where no top-k runs). Captured on a private stream in thread-local mode (other
+    // threads' streams are not affected); any failure just leaves the direct-launch path in place.
+    {
+        cudaStream_t cs = nullptr;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess) {
+            if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                const int lrc = launch(pl, cs, nullptr, 0);
+                const cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+                if (lrc == YOLOPP_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess)
+                    pl->exec = exec;
+                if (graph) cudaGraphDestroy(graph);
+            }
+            cudaStreamDestroy(cs);
+        }
+        (void)cudaGetLastError();  // a failed capture must not poison the caller's error state
+    }
     *plan = pl;
     return YOLOPP_OK;
 }
 
 int yolopp_plan_run(const yolopp_plan* plan, void* stream) {
     if (!plan) return YOLOPP_E_INVALID;
+    if (plan->exec) return cuda_rc(cudaGraphLaunch(plan->exec, (cudaStream_t)stream));
     return launch(plan, (cudaStream_t)stream, nullptr, 0);
 }
 
@@ -582,7 +621,11 @@ int yolopp_plan_run_profiled(const yolopp_plan* plan, void* stream, void* const*
     return launch(plan, (cudaStream_t)stream, events, num_events);
 }
 
-void yolopp_plan_destroy(yolopp_plan* plan) { free(plan); }
+void yolopp_plan_destroy(yolopp_plan* plan) {
+    if (!plan) return;
+    if (plan->exec) cudaGraphExecDestroy(plan->exec);
+    free(plan);
+}
 
 int yolopp_topk_conf(const yolopp_params* p, const float* const* level_ptrs, int32_t* topk_inds, void* workspace,
                      size_t workspace_bytes, void* stream) {
@@ -679,12 +722,15 @@ static int unary(const float* in, float* out, int64_t n, int op, void* stream) {
 int yolopp_sigmoid(const float* in, float* out, int64_t n, void* stream) { return unary(in, out, n, 0, stream); }
 int yolopp_exp(const float* in, float* out, int64_t n, void* stream) { return unary(in, out, n, 1, stream); }
 
-// grid of a streaming elementwise kernel: enough blocks for every vector, at most 8 resident blocks per SM, and a
-// whole number of blocks per SM when the tensor is large
+// grid of a streaming elementwise kernel: enough blocks for every vector, at most MISH_GRID_MULT blocks per SM (grid-
+// stride loop beyond that), and a whole number of blocks per SM when the tensor is large
 static int stream_grid(long long nvec, int per_block, int sms) {
     long long blocks = (nvec + per_block - 1) / per_block;
     if (blocks < 1) blocks = 1;
-    const long long cap = (long long)sms * 8;
+#ifndef MISH_GRID_MULT
+#define MISH_GRID_MULT 32  // measured on B200 (tools/mish_bench.py): 8 -> 0.92 / 0.94, 32 -> 0.95 / 0.99 of the copy peak (fwd / bwd, f32)
+#endif
+    const long long cap = (long long)sms * MISH_GRID_MULT;
     if (blocks > cap) blocks = cap;
     else if (blocks > sms) blocks = blocks / sms * sms;
     return (int)blocks;
@@ -784,8 +830,8 @@ size_t yolopp_nms_workspace_bytes(int64_t n, int32_t num_classes) {
 }
 
 int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, int32_t num_labels,
-                       float iou_thr, int nms_offset, int split_thr, int class_agnostic, int max_num, float* dets,
-                       int64_t* keep, int32_t* num_keep, void* stream_) {
+                       float iou_thr, float score_threshold, int nms_offset, int split_thr, int class_agnostic,
+                       int max_num, float* dets, int64_t* keep, int32_t* num_keep, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 0 || n >= (1ll << 31) || !num_keep || (nms_offset != 0 && nms_offset != 1)) return YOLOPP_E_INVALID;
     const DeviceInfo di = device_info();
@@ -810,6 +856,7 @@ int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* i
     d.g_labels = (const long long*)idxs;
     d.row_box = (float4*)boxes;
     d.iou_thr = iou_thr;
+    d.nms_score_thr = score_threshold;
     d.foff = (float)nms_offset;
     d.split_thr = split_thr;
     d.nms_agnostic = (class_agnostic || !idxs) ? 1 : 0;
@@ -825,7 +872,8 @@ int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* i
 
 int yolopp_multiclass_nms(const float* multi_bboxes, int boxes_per_class, const float* multi_scores, int64_t n,
                           int32_t num_classes, float score_thr, const float* score_factors, float iou_thr,
-                          int nms_offset, int split_thr, int class_agnostic, int nms_max_num, int max_num, float* dets,
+                          float nms_score_threshold, int nms_offset, int split_thr, int class_agnostic, int nms_max_num,
+                          int max_num, float* dets,
                           int64_t* labels, int64_t* flat_inds, int32_t* num_keep, int32_t* num_candidates,
                           void* workspace, size_t workspace_bytes, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -868,6 +916,7 @@ int yolopp_multiclass_nms(const float* multi_bboxes, int boxes_per_class, const 
     d.row_stat = row_stat;
     d.mat = mat;
     d.iou_thr = iou_thr;
+    d.nms_score_thr = nms_score_threshold;
     d.foff = (float)nms_offset;
     d.split_thr = split_thr;
     d.nms_agnostic = class_agnostic ? 1 : 0;

@@ -82,6 +82,7 @@ struct DevParams {
     int topk_segs[MAXL];
     int N, M_pad, R;
     float score_thr, conf_thr, iou_thr, foff;
+    float nms_score_thr;  // mmcv NMSop score_threshold (0: off)
     int split_thr, nms_agnostic, m_eff, keep_cap, out_cap, rescale;
     int sel_kcap;  // key buffer (power of two) of the select kernel
     int sel_stage; // 32-bit slots of the select kernel's logit staging buffer (0: exact path only)
@@ -360,7 +361,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     const int M = sg.m_end - sg.m_begin;
     const int stride = sel_stride_of(P, M);
     const bool staged = stride == 1;
-    const int ns = staged ? M : (M + stride - 1) / stride;  // staged slots
+    int ns = staged ? M : 0;  // staged slots (streamed: counted while the sample is issued)
     uint32_t* rank = P.rank + (size_t)b * P.M_pad + sg.m_begin;
     for (int i = tid; i < TS_BINS; i += SEL_THREADS) S.hist[i] = 0;
     if (tid == 0) S.count = 0;
@@ -406,11 +407,25 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
         cp_async_wait_all();
         mbar_wait(bar, 0u);
     } else {
-        // sample: every stride-th slot of the segment
-        for (int j = tid; j < ns; j += SEL_THREADS) {
-            int l = 0, a = 0, hw = 0;
-            if (seg_slot(P, sg, j * stride + sg.m_begin, l, a, hw)) cp_async4(ox + j, obj_addr(P, P.lv[l], b, a, hw));
-            else ox[j] = 0xFFFFFFFFu;
+        // sample 1 in `stride` logits of every plane: four consecutive logits every 4 * stride (16-byte copies) where
+        // the plane is 16-byte aligned, single logits every `stride` otherwise. `ns` = samples staged.
+        ns = 0;
+        for (int li = 0; li < sg.num_levels; ++li) {
+            const LevelDev& lv = P.lv[sg.first_level + li];
+            const bool vec = !P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0);
+            for (int a = 0; a < P.A; ++a) {
+                if (vec) {
+                    const float* plane = obj_addr(P, lv, b, a, 0);
+                    const int n4 = lv.HW / (4 * stride);
+                    for (int i = tid; i < n4; i += SEL_THREADS) cp_async16(ox + ns + 4 * i, plane + (size_t)4 * stride * i);
+                    ns += 4 * n4;
+                } else {
+                    const int n1 = lv.HW / stride, n1p = (n1 + 3) & ~3;  // (running offset stays 16-byte aligned)
+                    for (int i = tid; i < n1; i += SEL_THREADS) cp_async4(ox + ns + i, obj_addr(P, lv, b, a, i * stride));
+                    if (tid < n1p - n1) ox[ns + n1 + tid] = 0xFFFFFFFFu;  // padding: becomes ord 0, never counted
+                    ns += n1p;
+                }
+            }
         }
         YPP_PHASE(0, b, 5);
         cp_async_wait_all();
@@ -513,32 +528,61 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
             ++sp;
         }
     } else {
-        // one pass over the whole segment in global memory, 8 loads in flight per thread
-        constexpr int U = 8;
+        // one pass over the whole segment in global memory: 16-byte loads (4 x 4 logits in flight per thread) where
+        // the planes are 16-byte aligned, 8 scalar loads in flight otherwise. Survivors are rare (~1.4 k of the
+        // segment): each takes its stash slot with one shared-memory atomic.
         for (int li = 0; li < sg.num_levels; ++li) {
             const LevelDev& lv = P.lv[sg.first_level + li];
             const int s0 = lv.m_off - sg.m_begin;
+            const bool vec = !P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0);
             for (int a = 0; a < P.A; ++a) {
-                for (int h0 = 0; h0 < lv.HW; h0 += SEL_THREADS * U) {
-                    float v[U];
+                if (vec) {
+                    constexpr int U = 4;
+                    const float4* plane4 = reinterpret_cast<const float4*>(obj_addr(P, lv, b, a, 0));
+                    uint4* rank4 = reinterpret_cast<uint4*>(rank + s0 + a * lv.HW);  // (m_begin, m_off, HW: multiples of 4)
+                    const int n4 = lv.HW >> 2;
+                    for (int i0 = 0; i0 < n4; i0 += SEL_THREADS * U) {
+                        float4 v[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int hw = h0 + u * SEL_THREADS + tid;
-                        v[u] = hw < lv.HW ? __ldg(obj_addr(P, lv, b, a, hw)) : 0.f;
+                        for (int u = 0; u < U; ++u) {
+                            const int i = i0 + u * SEL_THREADS + tid;
+                            v[u] = i < n4 ? __ldg(plane4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int i = i0 + u * SEL_THREADS + tid;
+                            if (i < n4) {
+                                rank4[i] = make_uint4(RANK_INVALID, RANK_INVALID, RANK_INVALID, RANK_INVALID);
+                                const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    if (f2ord(e[q]) >= cut_ord) {
+                                        const int sp = atomicAdd(&S.count, 1);
+                                        if (sp < 2 * kcap) slots[sp] = (uint32_t)(s0 + a * lv.HW + 4 * i + q);
+                                    }
+                            }
+                        }
                     }
+                } else {
+                    constexpr int U = 8;
+                    for (int h0 = 0; h0 < lv.HW; h0 += SEL_THREADS * U) {
+                        float v[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int hw = h0 + u * SEL_THREADS + tid;
-                        const bool in = hw < lv.HW;
-                        const int m = s0 + a * lv.HW + hw;
-                        if (in && !P.nhwc) rank[m] = RANK_INVALID;
-                        const bool surv = in && f2ord(v[u]) >= cut_ord;
-                        const unsigned bal = __ballot_sync(0xffffffffu, surv);
-                        if (bal) {
-                            int sp = 0;
-                            if (lane == 0) sp = atomicAdd(&S.count, __popc(bal));
-                            sp = __shfl_sync(0xffffffffu, sp, 0) + __popc(bal & ((1u << lane) - 1u));
-                            if (surv && sp < 2 * kcap) slots[sp] = (uint32_t)m;
+                        for (int u = 0; u < U; ++u) {
+                            const int hw = h0 + u * SEL_THREADS + tid;
+                            v[u] = hw < lv.HW ? __ldg(obj_addr(P, lv, b, a, hw)) : 0.f;
+                        }
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            const int hw = h0 + u * SEL_THREADS + tid;
+                            if (hw < lv.HW) {
+                                const int m = s0 + a * lv.HW + hw;
+                                if (!P.nhwc) rank[m] = RANK_INVALID;
+                                if (f2ord(v[u]) >= cut_ord) {
+                                    const int sp = atomicAdd(&S.count, 1);
+                                    if (sp < 2 * kcap) slots[sp] = (uint32_t)m;
+                                }
+                            }
                         }
                     }
                 }
@@ -948,20 +992,25 @@ __device__ __forceinline__ void process_batch(const DevParams& P, const LevelDev
 struct StageGeom {
     uint32_t sub_bytes;    // one (NA x 32) box, padded to 1024
     uint32_t quad_rows;    // quad-row tiles: rows of four planes a box spans
-    uint32_t quad_box;     // one (quad_rows x 32) box, padded to 1024
+    uint32_t quad_box;     // one (quad_rows x QUAD_W) box, padded to 1024
     uint32_t rank_off;     // rank row: 64 entries + 4 (aligned superset when the row is not 16-byte aligned)
     uint32_t desc_off;     // tile descriptor written by the producer
     uint32_t stage_bytes;
 };
 constexpr uint32_t RANK_ROW_BYTES = (TILE_T + 4) * 4u;  // quad-row tiles fetch the 16-byte aligned superset
+// A TMA box must START on a 16-byte boundary of the innermost dimension (an unaligned start coordinate raises an
+// illegal-instruction fault on sm_100), so a quad-row box fetches the aligned superset of its 64 positions: 68
+// floats per row, not swizzled (the 128-byte swizzle would cap the row at 32 floats).
+constexpr int QUAD_W = TILE_T + 4;
+constexpr uint32_t QUAD_ROW_BYTES = QUAD_W * 4u;
 __host__ __device__ inline StageGeom stage_geom(int NA, int quad) {
     StageGeom g;
     g.sub_bytes = ((uint32_t)NA * 128u + 1023u) & ~1023u;
     // NA consecutive planes starting at plane p0 live in rows p0/4 .. (p0 + NA - 1)/4 of the four-plane view
     g.quad_rows = (((uint32_t)NA + 2u) >> 2) + 1u;
-    g.quad_box = (g.quad_rows * 128u + 1023u) & ~1023u;
+    g.quad_box = (g.quad_rows * QUAD_ROW_BYTES + 1023u) & ~1023u;
     uint32_t data = 2u * g.sub_bytes;
-    if (quad && 8u * g.quad_box > data) data = 8u * g.quad_box;
+    if (quad && 4u * g.quad_box > data) data = 4u * g.quad_box;
     g.rank_off = data;
     g.desc_off = g.rank_off + ((RANK_ROW_BYTES + 31u) & ~31u);
     g.stage_bytes = (g.desc_off + 32u + 1023u) & ~1023u;
@@ -977,15 +1026,45 @@ __device__ __forceinline__ float tile_at(const unsigned char* stage, uint32_t su
     return *reinterpret_cast<const float*>(stage + tile_off(sub_bytes, k, p));
 }
 // The same for a quad-row tile: the level is viewed as rows of four planes (row stride 16 * HW bytes); the tile
-// arrives as 8 boxes, box (j, h) = plane-in-row j, positions h*32 .. h*32+31, rows r0 .. r0 + quad_rows - 1.
-// Attribute k of the slab is plane p0 + k, i.e. row (pl0 + k) / 4 - relative to r0 - and plane-in-row (pl0 + k) % 4,
-// pl0 = p0 % 4.
-__device__ __forceinline__ float quad_at(const unsigned char* stage, uint32_t quad_box, int pl0, int k, int p) {
-    const int pk = pl0 + k, j = pk & 3, r = pk >> 2, col = p & 31;
-    const uint32_t off = (uint32_t)(2 * j + (p >> 5)) * quad_box + (uint32_t)r * 128u +
-                         ((uint32_t)(((col >> 2) ^ (r & 7)) << 4) | (uint32_t)((col & 3) << 2));
+// arrives as 4 boxes, box j = plane-in-row j, rows r0 .. r0 + quad_rows - 1, QUAD_W floats from the 16-byte aligned
+// position at or below j*HW + hw0 (the first `sh` floats of a row are the alignment slack). Attribute k of the slab
+// is plane p0 + k, i.e. row (pl0 + k) / 4 - relative to r0 - and plane-in-row (pl0 + k) % 4, pl0 = p0 % 4.
+__device__ __forceinline__ float quad_at(const unsigned char* stage, uint32_t quad_box, int pl0, int hwn, int hw0, int k, int p) {
+    const int pk = pl0 + k, j = pk & 3, r = pk >> 2;
+    const int sh = (j * hwn + hw0) & 3;
+    const uint32_t off = (uint32_t)j * quad_box + (uint32_t)r * QUAD_ROW_BYTES + (uint32_t)(sh + p) * 4u;
     return *reinterpret_cast<const float*>(stage + off);
 }
+
+#ifdef YPP_QUAD
+// One quad-row tile, consumed in place by one warp: logits are read from the four boxes, one admitted anchor at a
+// time (4.8 % of the bytes at 608^2). `z` = descriptor word: bit 0 top-k, bits 4..5 misalignment of the rank row,
+// bits 8..9 first plane of the slab within its row of four.
+template <int MODE>
+__device__ __noinline__ void consume_quad_tile(const DevParams& P, const unsigned char* stage, uint32_t quad_box, const uint32_t* rk,
+                                               int lvl, int b, int a, int hw0, int HWn, int z, int lane) {
+    const int shift = (z >> 4) & 3, pl0 = (z >> 8) & 3;
+    const LevelDev& lv = P.lv[lvl];
+    const SegDev& sg = P.seg[lv.seg];
+#pragma unroll 1
+    for (int h = 0; h < 2; ++h) {
+        const int ps0 = h * 32 + lane;
+        uint32_t r = RANK_INVALID;
+        if (hw0 + ps0 < HWn) r = rk[shift + ps0];
+        unsigned adm = __ballot_sync(0xffffffffu, r != RANK_INVALID);
+        while (adm) {
+            const int src = __ffs(adm) - 1;
+            adm &= adm - 1;
+            const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
+            const int ps = h * 32 + src;
+            const float av = lane < 5 ? quad_at(stage, quad_box, pl0, HWn, hw0, lane, ps) : 0.f;
+            process_anchor<MODE>(P, lv, sg, b, a, hw0 + ps, rr, lane, av, [&](int u) -> float {
+                return quad_at(stage, quad_box, pl0, HWn, hw0, 5 + u * 32 + lane, ps);
+            });
+        }
+    }
+}
+#endif
 
 // Persistent, warp-specialised. Warp 0 is the producer: its 32 lanes work out the coordinates of the CTA's next
 // 32 tiles in parallel (the level lookup and the integer divisions are the long latency chain of a tile), then
@@ -1018,7 +1097,7 @@ __device__ __forceinline__ long long ypp_globaltimer() {
 // 400 runs differed, at no measurable cost.
 __device__ __forceinline__ void stage_release_fence() { fence_proxy_async(); }
 
-constexpr int DEC_KIND_STOP = 3;  // stage header: the producer has run out of tiles
+constexpr int DEC_KIND_STOP = 7;  // stage header: the producer has run out of tiles (tile kinds are 1, 2, 3)
 
 template <int MODE>
 __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid_constant__ DevParams P,
@@ -1169,20 +1248,18 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                         *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l | (a << 8) | (kind << 16), bb, hw0, it);
                         if (kind == 2) {
                             mbar_arrive(fb);  // gather tile: nothing to stream, the consumer reads global memory itself
+#ifdef YPP_QUAD
                         } else if (kind == 3) {
-                            // quad-row tile: 4 planes-in-row x 2 halves; the rank row is not 16-byte aligned, its
-                            // aligned superset is fetched and the consumer skips `shift` entries
+                            // quad-row tile: one box per plane-in-row; neither the boxes nor the rank row start 16-byte
+                            // aligned: the aligned supersets are fetched and the consumer skips the slack
                             const int r0 = q_pl >> 2;
-                            const bool two = hw0 + TILE_SUB < hwn;
-                            mbar_arrive_expect_tx(fb, g.quad_rows * 128u * (two ? 8u : 4u) + (tk ? RANK_ROW_BYTES : 0u));
+                            mbar_arrive_expect_tx(fb, g.quad_rows * QUAD_ROW_BYTES * 4u + (tk ? RANK_ROW_BYTES : 0u));
 #pragma unroll
-                            for (int qj = 0; qj < 4; ++qj) {
-                                tma_load_2d(dst + (size_t)(2 * qj) * g.quad_box, &maps.m[l], qj * hwn + hw0, r0, fb);
-                                if (two)
-                                    tma_load_2d(dst + (size_t)(2 * qj + 1) * g.quad_box, &maps.m[l], qj * hwn + hw0 + TILE_SUB, r0, fb);
-                            }
+                            for (int qj = 0; qj < 4; ++qj)
+                                tma_load_2d(dst + (size_t)qj * g.quad_box, &maps.m[l], (qj * hwn + hw0) & ~3, r0, fb);
                             if (tk)
                                 bulk_load_1d(dst + g.rank_off, P.rank + (size_t)bb * P.M_pad + (q_m - q_shift), RANK_ROW_BYTES, fb);
+#endif
                         } else {
                             const bool topk = tk != 0;
                             const bool two = hw0 + TILE_SUB < hwn;  // the second box is not entirely out of bounds
@@ -1295,34 +1372,26 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             continue;
         }
         const uint32_t* rk = reinterpret_cast<const uint32_t*>(stage + g.rank_off);
+#ifdef YPP_QUAD
         if (kind == 3) {
-            // quad-row tile (plane stride not 16-byte aligned, e.g. 19x19): logits are read from the tile in place,
-            // one admitted anchor at a time; 4.8 % of the bytes at 608^2
-            const int shift = (desc2.z >> 4) & 3, pl0 = (desc2.z >> 8) & 3;
-            const LevelDev& lv = P.lv[lvl];
-            const SegDev& sg = P.seg[lv.seg];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int ps0 = h * 32 + lane;
-                uint32_t r = RANK_INVALID;
-                if (hw0 + ps0 < HWn) r = rk[shift + ps0];
-                unsigned adm = __ballot_sync(0xffffffffu, r != RANK_INVALID);
-                while (adm) {
-                    const int src = __ffs(adm) - 1;
-                    adm &= adm - 1;
-                    const uint32_t rr = __shfl_sync(0xffffffffu, r, src);
-                    const int ps = h * 32 + src;
-                    const float av = lane < 5 ? quad_at(stage, g.quad_box, pl0, lane, ps) : 0.f;
-                    process_anchor<MODE>(P, lv, sg, b, a, hw0 + ps, rr, lane, av, [&](int u) -> float {
-                        return quad_at(stage, g.quad_box, pl0, 5 + u * 32 + lane, ps);
-                    });
-                }
-            }
+            // quad-row tile (plane stride not 16-byte aligned, e.g. 19x19): behind a call, so that the hot loop of the
+            // ordinary tiles keeps its instruction footprint (with this block inlined every tile got 10 % slower)
+            consume_quad_tile<MODE>(P, stage, g.quad_box, rk, lvl, b, a, hw0, HWn, desc2.z, lane);
             stage_release_fence();
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            YPP_STAMP(tile_id, 3);
+            YPP_STAMP(tile_id, 4);
+#ifdef YPP_PROFILE
+            if (lane == 0 && tile_id < (1 << 16)) {
+                unsigned smid;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+                g_prof[(size_t)tile_id * 8 + 5] = (long long)smid | ((long long)blockIdx.x << 16);
+            }
+#endif
             continue;
         }
+#endif  // YPP_QUAD
 
         // admitted positions of the tile as a 64-bit mask (everything needed comes from the stage header: no
         // parameter-space lookups before the stage is released)
@@ -1497,10 +1566,10 @@ __global__ void __launch_bounds__(32 * ROWS_WARPS) decode_rows_kernel(const __gr
 // 32 consecutive positions of a plane. Scores are transposed through shared memory in chunks of DENSE_CH classes
 // so that the rows of the score matrix leave as coalesced 4*DENSE_CH-byte runs (a thread owning a whole row would
 // write 32 scattered words per instruction). One warp = one tile of 32 positions; 4 independent warps per block.
-constexpr int DENSE_CH = 64;
+constexpr int DENSE_CH = 32;
 constexpr int DENSE_WARPS = 4;
 template <int MODE>
-__global__ void __launch_bounds__(32 * DENSE_WARPS) decode_dense_kernel(const __grid_constant__ DevParams P) {
+__global__ void __launch_bounds__(32 * DENSE_WARPS, 6) decode_dense_kernel(const __grid_constant__ DevParams P) {
     __shared__ uint32_t sm_all[DENSE_WARPS][32][DENSE_CH + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * DENSE_WARPS + warp;
@@ -1555,25 +1624,37 @@ __global__ void __launch_bounds__(32 * DENSE_WARPS) decode_dense_kernel(const __
         const float* cls = slab + 5 * HW + hwc;
         for (int c0 = 0; c0 < P.C; c0 += DENSE_CH) {
             const int nc = min(DENSE_CH, P.C - c0);
-#pragma unroll 8
-            for (int j = 0; j < nc; ++j) {
-                const float sgm = c_sigmoid(__ldg(cls + (size_t)(c0 + j) * HW));
-                float score;
-                bool pass;
-                if (MODE == 0) {
-                    score = fmul(sgm, conf);     // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
-                    pass = score > P.score_thr;  // bbox_nms.py:54
-                } else {
-                    pass = sgm > P.score_thr;    // threshold on the class score alone (bbox_nms.py:54) ...
-                    score = fmul(sgm, conf);     // ... then scores * score_factors    (bbox_nms.py:57-62)
-                }
-                pass = pass && !drop;
-                sm[lane][j] = pass ? __float_as_uint(score) : SCORE_NONE;
-                if (pass && adm) {
-                    const uint32_t o = f2ord(score);
-                    best = o > best ? o : best;
-                    worst = ~o > worst ? ~o : worst;
-                    ++npass;
+            // the chunk's logits first (DENSE_CH independent coalesced loads in flight per thread), then the math
+            float tl[DENSE_CH];
+#pragma unroll
+            for (int j = 0; j < DENSE_CH; ++j) tl[j] = j < nc ? __ldg(cls + (size_t)(c0 + j) * HW) : 0.f;
+#pragma unroll
+            for (int j4 = 0; j4 < DENSE_CH; j4 += 4) {
+                if (j4 < nc) {  // (uniform; classes beyond nc compute on zeros and are not stored)
+                    const float4 sg4 = c_sigmoid4(make_float4(tl[j4], tl[j4 + 1], tl[j4 + 2], tl[j4 + 3]));
+                    const float sv[4] = {sg4.x, sg4.y, sg4.z, sg4.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = j4 + q;
+                        const float sgm = sv[q];
+                        float score;
+                        bool pass;
+                        if (MODE == 0) {
+                            score = fmul(sgm, conf);     // cls_pred *= conf_pred[:, None]   (yolocsp_head.py:358)
+                            pass = score > P.score_thr;  // bbox_nms.py:54
+                        } else {
+                            pass = sgm > P.score_thr;    // threshold on the class score alone (bbox_nms.py:54) ...
+                            score = fmul(sgm, conf);     // ... then scores * score_factors    (bbox_nms.py:57-62)
+                        }
+                        pass = pass && !drop && j < nc;
+                        if (j < nc) sm[lane][j] = pass ? __float_as_uint(score) : SCORE_NONE;
+                        if (pass && adm) {
+                            const uint32_t o = f2ord(score);
+                            best = o > best ? o : best;
+                            worst = ~o > worst ? ~o : worst;
+                            ++npass;
+                        }
+                    }
                 }
             }
             __syncwarp();
@@ -1840,7 +1921,19 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         return;
     }
     const u64 gmin = (u64)(~s_red[0]) << 32;
-    const u64 gmax = ((u64)s_red[1] << 32) | 0xFFFFFFFFull;
+    u64 gmax = ((u64)s_red[1] << 32) | 0xFFFFFFFFull;
+    if (P.nms_score_thr > 0.f) {
+        // NMSop.forward: `valid_mask = scores > score_threshold` before the greedy pass — in key space: keys whose high
+        // word is >= ~ord(threshold) are out. (The regime decision above `ntot` and boxes.max() stay unfiltered, as
+        // in batched_nms, which filters inside nms().)
+        const u64 lim = (u64)(~f2ord(P.nms_score_thr)) << 32;
+        if (lim == 0ull || lim - 1ull < gmin) {
+            if (tid == 0) P.o_count[b] = 0;
+            if (P.o_cls_offsets && !generic) nms_group_by_label(P, b, 0, kcl, kkey, chead, row_box);
+            return;
+        }
+        gmax = gmax < lim - 1ull ? gmax : lim - 1ull;
+    }
     const uint32_t img_max_ord = s_red[2];
     const bool per_class = !(ntot < P.split_thr);  // regime of mmcv batched_nms
     for (int c = tid; c < nlab; c += NMS_THREADS) chead[c] = -1;

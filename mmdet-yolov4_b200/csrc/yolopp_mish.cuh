@@ -11,8 +11,8 @@
 //     1 - tanh^2     = 4 (n + 1) / (n + 2)^2 = 4 (1 + e)^2 / (n + 2)^2
 //     1 - exp(-sp)   = e / (1 + e)
 //     => dx = dy * (4 x e (1 + e) / (n + 2)^2 + n / (n + 2))
-// x >= 20 takes the reference's branch (sp = x; tanh(x) == 1 in fp32 for x >= 9.02), x <= -87 underflows to 0 like
-// the reference. 128-bit loads and stores (4 x f32 / 8 x f16 / 8 x bf16 per thread per iteration), grid = a multiple
+// x >= 20 (the reference's softplus threshold) needs no branch: the exponential's argument is clamped there and
+// the closed form rounds to the reference's value; x <= -87 underflows to 0 like the reference. 128-bit loads and stores (4 x f32 / 8 x f16 / 8 x bf16 per thread per iteration), grid = a multiple
 // of the SM count, on the caller's stream. HBM bound: 8 B/element forward, 12 B/element backward in f32.
 #pragma once
 #include <cuda_bf16.h>
@@ -22,24 +22,21 @@
 
 namespace ypp {
 
+// x is clamped at the reference's threshold for the exponential only: for x >= 20, n = e(e+2) ~ 2e17, n / (n + 2)
+// rounds to 1 and y = x — the reference's own branch (mish.h:18: sp = x, tanh(x) == 1 in fp32) without a branch.
 __device__ __forceinline__ float mish_fwd_f(float x) {
-    if (x >= 20.0f) return x * tanhf(x);  // the reference's own branch (mish.h:18); tanh(x) = 1 here
-    const float e = __expf(x);
+    const float e = __expf(fminf(x, 20.0f));
     const float n = e * (e + 2.0f);
     return x * __fdividef(n, n + 2.0f);
 }
 
 __device__ __forceinline__ float mish_bwd_f(float dy, float x) {
-    if (x >= 20.0f) {
-        // sp = x: grad_sp = 1 - exp(-x), tsp = tanh(x) (mish.h:23-28)
-        const float tsp = tanhf(x);
-        return dy * (x * ((1.0f - tsp * tsp) * (1.0f - __expf(-x))) + tsp);
-    }
-    const float e = __expf(x);
+    // x >= 20: e(1+e)/(n+2)^2 ~ 1/e^2 -> 0 and n/(n+2) -> 1: grad = 1, as the reference's branch gives (mish.h:23-28)
+    const float e = __expf(fminf(x, 20.0f));
     const float n = e * (e + 2.0f);
     const float inv = __fdividef(1.0f, n + 2.0f);
     const float tsp = n * inv;
-    const float g = 4.0f * x * e * (1.0f + e) * inv * inv + tsp;
+    const float g = 4.0f * x * (e * inv) * ((1.0f + e) * inv) + tsp;
     return dy * g;
 }
 
@@ -110,18 +107,29 @@ struct MishVec<__nv_bfloat16> {
 
 // streaming loads / stores: every byte is touched once
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+#ifdef MISH_PLAIN
+    return *p;
+#else
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(p));
     return v;
+#endif
 }
 __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+#ifdef MISH_PLAIN
+    *p = v;
+#else
     asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+#endif
 }
 
 constexpr int MISH_THREADS = 256;
-constexpr int MISH_UNROLL = 4;  // independent 128-bit loads in flight per thread
+#ifndef MISH_UNROLL_N
+#define MISH_UNROLL_N 4
+#endif
+constexpr int MISH_UNROLL = MISH_UNROLL_N;  // independent 128-bit loads in flight per thread
 
 template <typename T>
 __global__ void __launch_bounds__(MISH_THREADS) mish_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, long long n) {

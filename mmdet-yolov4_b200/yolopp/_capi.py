@@ -56,7 +56,8 @@ class YoloppParams(ctypes.Structure):
         ('out_capacity', c_int32),
         ('batches_in_flight', c_int32),
         ('layout', c_int32),
-        ('reserved', c_int32 * 5),
+        ('nms_score_thr', c_float),
+        ('reserved', c_int32 * 4),
     ]
 
     # convenience -----------------------------------------------------------------------------
@@ -145,7 +146,7 @@ def yolo_base_anchors(base_sizes, strides):
 def make_params(mode, batch, featmap_sizes, anchor_strides, coder_strides, base_sizes, num_classes,
                 class_agnostic=False, nms_pre=-1, score_thr=0.0, conf_thr=-1.0, iou_thr=0.5, nms_offset=0,
                 split_thr=10000, nms_class_agnostic=False, nms_max_num=-1, max_per_img=-1, rescale=False,
-                out_capacity=0, base_anchors=None, layout=LAYOUT_NCHW):
+                out_capacity=0, base_anchors=None, layout=LAYOUT_NCHW, nms_score_thr=0.0):
     """Builds yolopp_params from what the reference reads off the head instance and test_cfg
     (yolocsp_head.py:112-114,151,162,170-178,345-348,374-376; yolo_head.py:52-59,281,365,378-384)."""
     L = len(featmap_sizes)
@@ -187,6 +188,7 @@ def make_params(mode, batch, featmap_sizes, anchor_strides, coder_strides, base_
     p.rescale = int(bool(rescale))
     p.out_capacity = int(out_capacity)
     p.layout = int(layout)
+    p.nms_score_thr = float(nms_score_thr)
     return p
 
 
@@ -243,11 +245,11 @@ def load_library(path=None):
     lib.yolopp_nms_workspace_bytes.restype = c_size_t
     lib.yolopp_nms_workspace_bytes.argtypes = [c_int64, c_int32]
     lib.yolopp_batched_nms.restype = ctypes.c_int
-    lib.yolopp_batched_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, ctypes.c_int,
+    lib.yolopp_batched_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, ctypes.c_int,
                                        ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.yolopp_multiclass_nms.restype = ctypes.c_int
     lib.yolopp_multiclass_nms.argtypes = [c_void_p, ctypes.c_int, c_void_p, c_int64, c_int32, c_float, c_void_p, c_float,
-                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
+                                          c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.yolopp_synth_level.restype = ctypes.c_int
     lib.yolopp_synth_level.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, ctypes.POINTER(c_float),

@@ -45,8 +45,7 @@ def parse_nms_cfg(nms_cfg):
     out = dict(iou_thr=float(c.pop('iou_threshold')), nms_offset=int(c.pop('offset', 0)),
                split_thr=int(c.pop('split_thr', 10000)), nms_class_agnostic=bool(c.pop('class_agnostic', False)),
                nms_max_num=int(c.pop('max_num', -1)))
-    if float(c.pop('score_threshold', 0)) > 0:
-        raise NotImplementedError('nms_cfg.score_threshold > 0 is not supported')
+    out['nms_score_thr'] = float(c.pop('score_threshold', 0))  # mmcv NMSop prefilter (0 = off)
     if c:
         raise TypeError(f'unexpected nms_cfg keys: {sorted(c)}')
     return out

@@ -5,7 +5,7 @@
     nms              mmcv.ops.nms.nms
 
 Same argument meaning and return types; results follow the canonical tie order (score desc, index asc).
-Not supported (raise): nms types other than 'nms', score_threshold > 0, numpy inputs, more than 4096 kept boxes.
+Not supported (raise): nms types other than 'nms', numpy inputs, more than 4096 kept boxes.
 CUDA tensors only — there is no CPU fallback.
 """
 import ctypes
@@ -32,7 +32,7 @@ def _require_cuda(*ts):
             raise NotImplementedError('yolopp NMS ops run on CUDA tensors only (no CPU fallback)')
 
 
-def _run_batched(boxes, scores, idxs, iou_thr, offset, split_thr, class_agnostic, max_num):
+def _run_batched(boxes, scores, idxs, iou_thr, offset, split_thr, class_agnostic, max_num, score_threshold=0.0):
     lib = _capi.load_library()
     assert boxes.size(1) == 4
     assert boxes.size(0) == scores.size(0)
@@ -52,7 +52,8 @@ def _run_batched(boxes, scores, idxs, iou_thr, offset, split_thr, class_agnostic
     keep = torch.empty((max(cap, 1), ), dtype=torch.int64, device=boxes.device)
     cnt = torch.zeros((2, ), dtype=torch.int32, device=boxes.device)
     with torch.cuda.device(boxes.device):
-        rc = lib.yolopp_batched_nms(_p(b), _p(s), _p(lab), n, num_labels, float(iou_thr), int(offset), int(split_thr),
+        rc = lib.yolopp_batched_nms(_p(b), _p(s), _p(lab), n, num_labels, float(iou_thr), float(score_threshold),
+                                    int(offset), int(split_thr),
                                     int(bool(class_agnostic)), int(max_num), _p(dets), _p(keep), _p(cnt), _stream())
     _capi.check(rc, 'yolopp_batched_nms')
     k, status = (int(v) for v in cnt.tolist())
@@ -65,9 +66,7 @@ def nms(boxes, scores, iou_threshold, offset=0, score_threshold=0, max_num=-1):
     """mmcv.ops.nms.nms -> (dets (k,5), inds (k,)) in descending score order."""
     if not isinstance(boxes, torch.Tensor):
         raise NotImplementedError('numpy inputs are not supported')
-    if score_threshold > 0:
-        raise NotImplementedError('score_threshold > 0 is not supported')
-    return _run_batched(boxes, scores, None, iou_threshold, offset, INT_MAX, True, max_num)
+    return _run_batched(boxes, scores, None, iou_threshold, offset, INT_MAX, True, max_num, score_threshold)
 
 
 def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
@@ -75,7 +74,7 @@ def batched_nms(boxes, scores, idxs, nms_cfg, class_agnostic=False):
     cfg = parse_nms_cfg(nms_cfg)
     agnostic = bool(cfg['nms_class_agnostic'] or class_agnostic)
     return _run_batched(boxes, scores, idxs, cfg['iou_thr'], cfg['nms_offset'], cfg['split_thr'], agnostic,
-                        cfg['nms_max_num'])
+                        cfg['nms_max_num'], cfg['nms_score_thr'])
 
 
 def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, score_factors=None, return_inds=False):
@@ -107,7 +106,7 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, s
         ws_bytes = lib.yolopp_nms_workspace_bytes(n, C)
         ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=dev)
         rc = lib.yolopp_multiclass_nms(_p(mb), int(per_class), _p(ms), n, C, float(score_thr), _p(sf), cfg['iou_thr'],
-                                       cfg['nms_offset'], cfg['split_thr'], int(cfg['nms_class_agnostic']),
+                                       cfg['nms_score_thr'], cfg['nms_offset'], cfg['split_thr'], int(cfg['nms_class_agnostic']),
                                        cfg['nms_max_num'], int(max_num), _p(dets), _p(labels), _p(flat), _p(cnt[0:2]),
                                        _p(cnt[2:3]), _p(ws), ws.numel(), _stream())
         ws.record_stream(torch.cuda.current_stream())

@@ -49,6 +49,13 @@ def params_to_blob(p):
     return torch.frombuffer(bytearray(bytes(p)), dtype=torch.uint8).clone()
 
 
+def _norm_dev(device):
+    dev = torch.device(device)
+    if dev.type == 'cuda' and dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+    return dev
+
+
 def check_maps(p, pred_maps, device=None):
     """Validates the level tensors against the params the way the reference's asserts would (yolocsp_head.py:216,
     yolov4_bbox_coder.py:50-51) plus what a raw-pointer interface must insist on: CUDA, float32, one device, the
@@ -59,6 +66,8 @@ def check_maps(p, pred_maps, device=None):
     if len(pred_maps) != L:
         raise AssertionError(f'expected {L} prediction maps, got {len(pred_maps)}')
     dev = pred_maps[0].device if device is None else torch.device(device)
+    if dev.type == 'cuda' and dev.index is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
     if dev.type != 'cuda':
         raise NotImplementedError('yolopp runs on CUDA tensors only (no CPU fallback)')
     nhwc = []
@@ -297,7 +306,7 @@ class Session:
     def __init__(self, params, device='cuda', max_plans=8):
         self.lib = _capi.load_library()
         self.p = params
-        self.dev = torch.device(device)
+        self.dev = _norm_dev(device)
         self.max_plans = int(max_plans)
         with torch.cuda.device(self.dev):
             self.ws_bytes = self.lib.yolopp_workspace_bytes(ctypes.byref(params))
@@ -324,7 +333,9 @@ class Session:
         return evs
 
     def _plan(self, pred_maps, scale_factors):
-        key = tuple(m.data_ptr() for m in pred_maps) + ((scale_factors.data_ptr(), ) if scale_factors is not None else ())
+        # (pointer, shape, strides) per map: a view of a known tensor with another shape must not hit its plan
+        key = tuple((m.data_ptr(), m.shape, m.stride()) for m in pred_maps) + \
+            ((scale_factors.data_ptr(), ) if scale_factors is not None else ())
         ent = self._plans.get(key)
         if ent is not None:
             return ent
@@ -360,11 +371,11 @@ class Session:
         self._plans[key] = ent
         return ent
 
-    def run(self, pred_maps, scale_factors=None, profile=False, stream=None):
+    def run(self, pred_maps, scale_factors=None, profile=False, stream=None, _sp=None):
         ent = self._plan(pred_maps, scale_factors)
         st = torch.cuda.current_stream(self.dev) if stream is None else stream
         ent[2] = st
-        sp = ctypes.c_void_p(st.cuda_stream)
+        sp = _sp if _sp is not None else ctypes.c_void_p(st.cuda_stream)
         if profile:
             if self._events is None:
                 self._events = self._make_events()
@@ -397,21 +408,25 @@ class Pipeline:
 
     def __init__(self, params, depth=3, device='cuda'):
         self.depth = int(depth)
-        self.dev = torch.device(device)
+        self.dev = _norm_dev(device)
         p = type(params).from_buffer_copy(params)
         p.batches_in_flight = self.depth  # scheduling hint: decode CTAs retire progressively, neighbours overlap
         self.sessions = [Session(p, device) for _ in range(self.depth)]
         with torch.cuda.device(self.dev):
             self.streams = [torch.cuda.Stream(self.dev) for _ in range(self.depth)]
             self.done = [torch.cuda.Event() for _ in range(self.depth)]
+        self._sp = [ctypes.c_void_p(s.cuda_stream) for s in self.streams]
         self.n = 0
 
-    def submit(self, pred_maps, scale_factors=None):
+    def submit(self, pred_maps, scale_factors=None, inputs_ready=False):
+        """Queues one batch on the next slot. `inputs_ready=True`: the caller guarantees that the inputs are complete
+        (e.g. produced earlier and synchronised) — skips making the slot's stream wait for the caller's stream."""
         slot = self.n % self.depth
         self.n += 1
         st = self.streams[slot]
-        st.wait_stream(torch.cuda.current_stream(self.dev))  # the inputs were produced on the caller's stream
-        self.sessions[slot].run(pred_maps, scale_factors, stream=st)
+        if not inputs_ready:
+            st.wait_stream(torch.cuda.current_stream(self.dev))  # the inputs were produced on the caller's stream
+        self.sessions[slot].run(pred_maps, scale_factors, stream=st, _sp=self._sp[slot])
         self.done[slot].record(st)
         return slot
 
@@ -439,7 +454,7 @@ class HostPipeline:
 
     def __init__(self, params, depth=2, device='cuda'):
         self.depth = int(depth)
-        self.dev = torch.device(device)
+        self.dev = _norm_dev(device)
         self.p = params
         B, cap = params.batch, params.capacity
         self.slots = []

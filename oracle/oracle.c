@@ -223,8 +223,30 @@ int64_t oracle_nms(const float* boxes, const float* scores, int64_t n, float iou
 
 /* mmcv.ops.nms.nms (python wrapper + NMSop.forward): max_num cut; dets = cat(boxes[inds], scores[inds]). */
 static int64_t nms_op(const float* boxes, const float* scores, int64_t n, float iou_thr, int offset, int max_num,
-                      int64_t* keep) {
-    int64_t k = oracle_nms(boxes, scores, n, iou_thr, offset, keep);
+                      float score_threshold, int64_t* keep) {
+    int64_t k;
+    if (score_threshold > 0.f) {
+        /* NMSop.forward: valid_mask = scores > score_threshold; nms on the subset; inds = valid_inds[inds] */
+        float* vb = (float*)malloc(sizeof(float) * 4 * (size_t)(n > 0 ? n : 1));
+        float* vs = (float*)malloc(sizeof(float) * (size_t)(n > 0 ? n : 1));
+        int64_t* vi = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+        int64_t m = 0;
+        for (int64_t i = 0; i < n; ++i)
+            if (scores[i] > score_threshold) {
+                memcpy(vb + 4 * m, boxes + 4 * i, sizeof(float) * 4);
+                vs[m] = scores[i];
+                vi[m] = i;
+                ++m;
+            }
+        k = oracle_nms(vb, vs, m, iou_thr, offset, keep);
+        if (max_num > 0 && k > max_num) k = max_num;
+        for (int64_t q = 0; q < k; ++q) keep[q] = vi[keep[q]];
+        free(vb);
+        free(vs);
+        free(vi);
+        return k;
+    }
+    k = oracle_nms(boxes, scores, n, iou_thr, offset, keep);
     if (max_num > 0 && k > max_num) k = max_num;
     return k;
 }
@@ -233,8 +255,9 @@ static int64_t nms_op(const float* boxes, const float* scores, int64_t n, float 
  * mmcv.ops.nms.batched_nms. idxs may be NULL (== class_agnostic). Returns number kept; keep[] holds indices
  * into the inputs in output order; dets[k][5] = (boxes[keep], score).
  */
-int64_t oracle_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, float iou_thr,
-                           int offset, int split_thr, int class_agnostic, int max_num, float* dets, int64_t* keep) {
+int64_t oracle_batched_nms2(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, float iou_thr,
+                            int offset, int split_thr, int class_agnostic, int max_num, float score_threshold, float* dets,
+                            int64_t* keep) {
     if (n == 0) return 0;
     float* bfn = (float*)malloc(sizeof(float) * 4 * (size_t)n);
     if (class_agnostic || idxs == NULL) {
@@ -250,7 +273,7 @@ int64_t oracle_batched_nms(const float* boxes, const float* scores, const int64_
     }
     int64_t nk = 0;
     if (n < split_thr) {
-        nk = nms_op(bfn, scores, n, iou_thr, offset, max_num, keep);
+        nk = nms_op(bfn, scores, n, iou_thr, offset, max_num, score_threshold, keep);
     } else {
         /* per-class loop over torch.unique(idxs) (sorted ascending) */
         unsigned char* total = (unsigned char*)calloc((size_t)n, 1);
@@ -284,7 +307,7 @@ int64_t oracle_batched_nms(const float* boxes, const float* scores, const int64_
                 ss[q] = scores[mask[q]];
             }
             /* per-class nms_op: nms_cfg_ no longer holds max_num here (popped before the loop) */
-            int64_t k = nms_op(sb, ss, m, iou_thr, offset, -1, sk);
+            int64_t k = nms_op(sb, ss, m, iou_thr, offset, -1, score_threshold, sk);
             for (int64_t q = 0; q < k; ++q) total[mask[sk[q]]] = 1;
         }
         /* keep = total_mask.nonzero(); scores[keep].sort(descending=True)  (canonical: stable) */
@@ -314,6 +337,11 @@ int64_t oracle_batched_nms(const float* boxes, const float* scores, const int64_
     return nk;
 }
 
+int64_t oracle_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, float iou_thr,
+                           int offset, int split_thr, int class_agnostic, int max_num, float* dets, int64_t* keep) {
+    return oracle_batched_nms2(boxes, scores, idxs, n, iou_thr, offset, split_thr, class_agnostic, max_num, 0.f, dets, keep);
+}
+
 /*
  * multiclass_nms (bbox_nms.py:7-93).
  *   multi_bboxes (n,4) [boxes_per_class==0] or (n, 4*C); multi_scores (n, C+1), last column = background
@@ -321,10 +349,10 @@ int64_t oracle_batched_nms(const float* boxes, const float* scores, const int64_
  *   outputs (capacity n*C): dets[k][5], labels[k], inds[k] = the `keep` the reference returns with
  *   return_inds=True (index into the thresholded candidate list), flat[k] = row*C + class of each detection.
  */
-int64_t oracle_multiclass_nms(const float* multi_bboxes, int per_class_boxes, const float* multi_scores, int64_t n,
-                              int C, float score_thr, float iou_thr, int offset, int split_thr, int class_agnostic,
-                              int nms_max_num, int max_num, const float* score_factors, float* dets,
-                              int64_t* labels, int64_t* inds, int64_t* flat, int64_t* num_candidates) {
+int64_t oracle_multiclass_nms2(const float* multi_bboxes, int per_class_boxes, const float* multi_scores, int64_t n,
+                               int C, float score_thr, float iou_thr, int offset, int split_thr, int class_agnostic,
+                               int nms_max_num, int max_num, float nms_score_threshold, const float* score_factors,
+                               float* dets, int64_t* labels, int64_t* inds, int64_t* flat, int64_t* num_candidates) {
     int64_t total = n * (int64_t)C, m = 0;
     float* bb = (float*)malloc(sizeof(float) * 4 * (size_t)(total > 0 ? total : 1));
     float* sc = (float*)malloc(sizeof(float) * (size_t)(total > 0 ? total : 1));
@@ -348,7 +376,8 @@ int64_t oracle_multiclass_nms(const float* multi_bboxes, int per_class_boxes, co
     if (m > 0) {
         int64_t* keep = (int64_t*)malloc(sizeof(int64_t) * (size_t)m);
         float* d = (float*)malloc(sizeof(float) * 5 * (size_t)m);
-        nk = oracle_batched_nms(bb, sc, lb, m, iou_thr, offset, split_thr, class_agnostic, nms_max_num, d, keep);
+        nk = oracle_batched_nms2(bb, sc, lb, m, iou_thr, offset, split_thr, class_agnostic, nms_max_num,
+                                 nms_score_threshold, d, keep);
         if (max_num > 0 && nk > max_num) nk = max_num;
         for (int64_t q = 0; q < nk; ++q) {
             memcpy(dets + 5 * q, d + 5 * q, sizeof(float) * 5);
@@ -364,6 +393,15 @@ int64_t oracle_multiclass_nms(const float* multi_bboxes, int per_class_boxes, co
     free(lb);
     free(fl);
     return nk;
+}
+
+int64_t oracle_multiclass_nms(const float* multi_bboxes, int per_class_boxes, const float* multi_scores, int64_t n,
+                              int C, float score_thr, float iou_thr, int offset, int split_thr, int class_agnostic,
+                              int nms_max_num, int max_num, const float* score_factors, float* dets,
+                              int64_t* labels, int64_t* inds, int64_t* flat, int64_t* num_candidates) {
+    return oracle_multiclass_nms2(multi_bboxes, per_class_boxes, multi_scores, n, C, score_thr, iou_thr, offset, split_thr,
+                                  class_agnostic, nms_max_num, max_num, 0.f, score_factors, dets, labels, inds, flat,
+                                  num_candidates);
 }
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -553,9 +591,9 @@ static int64_t get_bboxes_single(const yolopp_params* p, const float* const* lev
     int64_t* lab = (int64_t*)malloc(sizeof(int64_t) * (size_t)(total > 0 ? total : 1));
     int64_t* flat = (int64_t*)malloc(sizeof(int64_t) * (size_t)(total > 0 ? total : 1));
     int64_t ncand = 0;
-    int64_t nk = oracle_multiclass_nms(box, 0, ms, R2, C, p->score_thr, p->iou_thr, p->nms_offset, p->split_thr,
-                                       p->nms_class_agnostic, p->nms_max_num, p->max_per_img, factors, d, lab, NULL,
-                                       flat, &ncand);
+    int64_t nk = oracle_multiclass_nms2(box, 0, ms, R2, C, p->score_thr, p->iou_thr, p->nms_offset, p->split_thr,
+                                        p->nms_class_agnostic, p->nms_max_num, p->max_per_img, p->nms_score_thr, factors, d,
+                                        lab, NULL, flat, &ncand);
     if (nk > cap) nk = -1;
     for (int64_t q = 0; q < nk; ++q) {
         memcpy(out_dets + 5 * q, d + 5 * q, sizeof(float) * 5);

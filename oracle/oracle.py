@@ -39,9 +39,9 @@ def lib():
         L.oracle_grid_anchors.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]
         L.oracle_nms.restype = c_int64
         L.oracle_nms.argtypes = [c_void_p, c_void_p, c_int64, c_float, c_int, c_void_p]
-        L.oracle_batched_nms.restype = c_int64
-        L.oracle_batched_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_int, c_int, c_int,
-                                         c_void_p, c_void_p]
+        L.oracle_batched_nms2.restype = c_int64
+        L.oracle_batched_nms2.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int, c_int, c_int, c_int,
+                                          c_float, c_void_p, c_void_p]
         L.oracle_multiclass_nms.restype = c_int64
         L.oracle_multiclass_nms.argtypes = [c_void_p, c_int, c_void_p, c_int64, c_int, c_float, c_float, c_int, c_int,
                                             c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -102,14 +102,15 @@ def nms(boxes, scores, iou_thr, offset=0):
     return keep[:k].copy()
 
 
-def batched_nms(boxes, scores, idxs, iou_thr, offset=0, split_thr=10000, class_agnostic=False, max_num=-1):
+def batched_nms(boxes, scores, idxs, iou_thr, offset=0, split_thr=10000, class_agnostic=False, max_num=-1,
+                score_threshold=0.0):
     b, s = _f32(boxes).reshape(-1, 4), _f32(scores).reshape(-1)
     i = None if idxs is None else np.ascontiguousarray(idxs, dtype=np.int64)
     n = s.size
     dets = np.empty((max(n, 1), 5), np.float32)
     keep = np.empty(max(n, 1), np.int64)
-    k = lib().oracle_batched_nms(_ptr(b), _ptr(s), _ptr(i), n, float(iou_thr), int(offset), int(split_thr),
-                                 int(bool(class_agnostic)), int(max_num), _ptr(dets), _ptr(keep))
+    k = lib().oracle_batched_nms2(_ptr(b), _ptr(s), _ptr(i), n, float(iou_thr), int(offset), int(split_thr),
+                                  int(bool(class_agnostic)), int(max_num), float(score_threshold), _ptr(dets), _ptr(keep))
     return dets[:k].copy(), keep[:k].copy()
 
 

@@ -62,6 +62,11 @@ CASES = {
     'csp_force_global': _csp(160, 2, 'dense', 32, C=20, nms_pre=500,
                              nms=dict(type='nms', iou_threshold=0.5, split_thr=1000000)),
     'csp_keep_all': _csp(64, 2, 'dense', 33, C=3, nms_pre=100, max_per_img=-1, out_capacity=400),
+    # nms_cfg.score_threshold (mmcv NMSop prefilter), both batched_nms regimes
+    'csp_nms_score_thr': _csp(128, 2, 'dense', 34, C=6, nms_pre=300,
+                              nms=dict(type='nms', iou_threshold=0.5, score_threshold=0.55)),
+    'csp_nms_score_thr_split': _csp(128, 2, 'dense', 35, C=6, nms_pre=300,
+                                    nms=dict(type='nms', iou_threshold=0.5, score_threshold=0.62, split_thr=100)),
     # YOLOv3 convention (BASELINE.json config 4 (ii))
     'v3_416_sparse': _v3(416, 2, 'sparse', 41),
     'v3_416_dense': _v3(416, 2, 'dense', 42),
@@ -89,7 +94,7 @@ PKL_CASE = dict(mode=capi.MODE_V3, batch=1, sizes=[(32, 32), (16, 16), (8, 8)], 
 GOLDEN_CASES = ['csp608_sparse', 'csp608_dense', 'csp608_dense_thr07', 'csp608_sparse_thr002', 'csp320_nopre_sparse', 'csp_odd', 'csp416_rescale',
                 'csp_saturated', 'tencent_agnostic', 'csp_nms_agnostic', 'csp_nms_offset1', 'csp_nms_maxnum',
                 'csp_force_global', 'v3_416_sparse', 'v3_416_dense', 'v3_320_mid', 'v3_rescale', 'csp640_sparse',
-                'csp_empty', 'v3_640_sparse', 'csp1280_sparse']
+                'csp_empty', 'v3_640_sparse', 'csp1280_sparse', 'csp_nms_score_thr', 'csp_nms_score_thr_split']
 
 
 def asis_rel_err(ref_dets, got_dets):

@@ -37,8 +37,8 @@ def test_planning_calls_need_no_device():
     assert 20e6 < ws < 200e6
     info = capi.describe(p)
     assert info.anchors_per_image == 22743 and info.rows_per_image == 1000 and info.num_attrib == 85
-    assert info.tma_level_mask == 0b111          # 76^2 / 38^2: plain TMA tiles; 19^2 (plane stride not 16-byte
-                                                 # aligned): quad-row TMA tiles — every level is streamed
+    assert info.tma_level_mask == 0b111          # 76^2 / 38^2: TMA tiles; 19^2 (plane stride not 16-byte aligned):
+                                                 # gather tiles of the same persistent kernel
     assert info.tma_bytes_per_image + info.ldg_bytes_per_image == 7732620  # 4*3*85*7581
     assert info.kernel_launches == 3             # select, persistent decode (TMA + gather tiles), per-image NMS
     assert info.ldg_blocks == 0 and info.ldg_bytes_per_image == 0
@@ -80,7 +80,8 @@ def test_host_api_mirrors_reference_validation():
     import yolopp
     from yolopp.heads import parse_nms_cfg
     assert parse_nms_cfg(dict(type='nms', iou_threshold=0.65)) == dict(
-        iou_thr=0.65, nms_offset=0, split_thr=10000, nms_class_agnostic=False, nms_max_num=-1)
+        iou_thr=0.65, nms_offset=0, split_thr=10000, nms_class_agnostic=False, nms_max_num=-1, nms_score_thr=0.0)
+    assert parse_nms_cfg(dict(type='nms', iou_threshold=0.5, score_threshold=0.25))['nms_score_thr'] == 0.25
     with pytest.raises(NotImplementedError):
         parse_nms_cfg(dict(type='soft_nms', iou_threshold=0.5))
     with pytest.raises(TypeError):

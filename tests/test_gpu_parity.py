@@ -303,6 +303,26 @@ def test_batched_nms_matches_oracle(n, ncls, split_thr, max_num, agnostic, offse
     np.testing.assert_array_equal(_u32(dets.cpu().numpy()), _u32(od))
 
 
+@pytest.mark.parametrize('n,ncls,split_thr,thr', [(800, 5, 10000, 0.4), (800, 5, 100, 0.4), (500, 1, 10000, 0.999), (3000, 20, 10000, 0.7)])
+def test_batched_nms_score_threshold(n, ncls, split_thr, thr):
+    """nms_cfg.score_threshold (mmcv NMSop.forward prefilter): only boxes with score > threshold enter the greedy
+    pass; both regimes."""
+    import yolopp
+    rng = np.random.RandomState(n + ncls + split_thr)
+    boxes = _rand_boxes(rng, n)
+    scores = rng.rand(n).astype(np.float32)
+    idxs = rng.randint(0, ncls, n).astype(np.int64)
+    cfg = dict(type='nms', iou_threshold=0.5, split_thr=split_thr, score_threshold=thr)
+    dets, keep = yolopp.batched_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(),
+                                    torch.from_numpy(idxs).cuda(), cfg)
+    od, ok = oracle.batched_nms(boxes, scores, idxs, 0.5, split_thr=split_thr, score_threshold=thr)
+    np.testing.assert_array_equal(keep.cpu().numpy(), ok)
+    np.testing.assert_array_equal(_u32(dets.cpu().numpy()), _u32(od))
+    d2, i2 = yolopp.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.5, score_threshold=thr)
+    _, ok2 = oracle.batched_nms(boxes, scores, None, 0.5, class_agnostic=True, score_threshold=thr)
+    np.testing.assert_array_equal(i2.cpu().numpy(), ok2)
+
+
 def test_nms_matches_oracle_and_torchvision():
     import yolopp
     rng = np.random.RandomState(5)

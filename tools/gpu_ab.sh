@@ -8,7 +8,7 @@ import json,sys; d=json.load(open(sys.argv[1])); print(sys.argv[2], round(d['val
 for rep in 1 2; do
   for lib in tools/var/lib_*.so; do
     n=$(basename $lib .so)
-    YOLOPP_LIB=/root/repo/$lib timeout 120 python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_${n}_$TAG.json 2>/dev/null; show gpurun_out/bench_${n}_$TAG.json $n
+    YOLOPP_LIB=$PWD/$lib timeout 120 python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_${n}_$TAG.json 2>/dev/null; show gpurun_out/bench_${n}_$TAG.json $n
   done
   timeout 120 python bench.py --steps 200 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_tree_$TAG.json 2>/dev/null; show gpurun_out/bench_tree_$TAG.json in-tree
 done

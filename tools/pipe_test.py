@@ -1,6 +1,8 @@
 """Feasibility: steps issued round-robin on D streams (D sessions / workspaces) vs one stream."""
 import sys, time
-sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'mmdet-yolov4_b200'), os.path.join(ROOT, 'tests')]
 import torch, cases, yolopp
 from yolopp.ops import Session
 case = dict(cases.CASES['csp608_sparse'], batch=64)

@@ -1,13 +1,15 @@
 """Phase timeline of the per-image kernels (profiling build tools/libyolopp_prof.so, -DYPP_PROFILE)."""
 import sys, ctypes
-sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'mmdet-yolov4_b200'), os.path.join(ROOT, 'tests')]
 import numpy as np, torch, cases
 from yolopp import _capi
-_capi.LIB_PATH = '/root/repo/tools/libyolopp_prof.so'
+_capi.LIB_PATH = os.path.join(ROOT, 'tools', 'libyolopp_prof.so')
 import yolopp
 from yolopp.ops import Session
 lib = _capi.load_library()
-case = dict(cases.CASES['csp608_sparse'], batch=64)
+case = dict(cases.CASES[sys.argv[1] if len(sys.argv) > 1 else 'csp608_sparse'], batch=int(sys.argv[2]) if len(sys.argv) > 2 else 64)
 p = cases.build_params(case)
 levels = yolopp.synth.synth_levels(p, 11, 'sparse')
 s = Session(p)
@@ -16,7 +18,7 @@ torch.cuda.synchronize()
 buf = np.zeros((2, 256, 16), np.int64)
 lib.yolopp_phase_read.argtypes = [ctypes.c_void_p]
 lib.yolopp_phase_read(buf.ctypes.data_as(ctypes.c_void_p))
-B = 64
+B = case['batch']
 sel = buf[0, :B]; nms = buf[1, :B]
 def stats(name, d):
     print('  %-34s median %7.0f  p10 %7.0f  p90 %7.0f  max %7.0f' % (name, np.median(d), np.percentile(d, 10), np.percentile(d, 90), d.max()))

@@ -2,10 +2,12 @@
 where do the microseconds beyond bytes / bandwidth go — ramp-up, steady state, tail?
     python tools/prof_timeline.py [case] [batch]"""
 import sys, ctypes
-sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'mmdet-yolov4_b200'), os.path.join(ROOT, 'tests')]
 import numpy as np, torch, cases
 from yolopp import _capi
-_capi.LIB_PATH = '/root/repo/tools/libyolopp_prof.so'
+_capi.LIB_PATH = os.environ.get('YPP_PROF_LIB') or os.path.join(ROOT, 'tools', 'libyolopp_prof.so')
 import yolopp
 from yolopp.ops import Session
 lib = _capi.load_library()

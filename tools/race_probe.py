@@ -2,7 +2,9 @@
 Prints one fingerprint per run (so a cold first run, a rare glitch and a steady disagreement can be told apart)
 and, for every run that is not in the majority, the images that differ from the majority result."""
 import sys, hashlib, collections
-sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'mmdet-yolov4_b200'), os.path.join(ROOT, 'tests')]
 import numpy as np, torch, cases, yolopp
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 30

@@ -1,6 +1,8 @@
 """Run-to-run reproducibility of the whole path at full size: python tools/repro.py [batch] [runs]"""
 import sys
-sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'mmdet-yolov4_b200'), os.path.join(ROOT, 'tests')]
 import numpy as np, torch, cases, yolopp
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 R = int(sys.argv[2]) if len(sys.argv) > 2 else 10

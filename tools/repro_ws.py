@@ -1,6 +1,8 @@
 """Which intermediate differs between two runs? Diffs the workspace buffers (rank, row_anchor, row_box, row_stat, mat)."""
 import sys
-sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'mmdet-yolov4_b200'), os.path.join(ROOT, 'tests')]
 import numpy as np, torch, cases, yolopp
 from yolopp.ops import Session
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128

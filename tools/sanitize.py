@@ -1,6 +1,8 @@
 """Small end-to-end runs for compute-sanitizer (memcheck / racecheck / synccheck): every kernel, both decode paths."""
 import sys
-sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'mmdet-yolov4_b200'), os.path.join(ROOT, 'tests')]
 import numpy as np, torch, cases, yolopp
 from oracle import oracle
 names = sys.argv[1:] or ['csp_tiny', 'csp_odd', 'csp608_sparse', 'v3_tiny_nopre', 'tencent_agnostic', 'csp_force_global']

@@ -4,7 +4,9 @@ _get_bboxes_single / multiclass_nms (yolocsp_head.py:225-382, bbox_nms.py:7-93).
 sigmoid, library tie order) and not the product: a number to put next to bench.py's.
     python tools/stock_gpu.py [batch] [steps]"""
 import sys, time
-sys.path[:0] = ['/root/repo', '/root/repo/mmdet-yolov4_b200', '/root/repo/tests']
+import os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'mmdet-yolov4_b200'), os.path.join(ROOT, 'tests')]
 import torch, torchvision
 import cases, yolopp
 
