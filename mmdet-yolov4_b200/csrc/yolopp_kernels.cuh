@@ -267,21 +267,6 @@ struct RowListSource {
     }
     __device__ __forceinline__ int groups() const { return nrows * nsub * 32; }
 };
-// best score of every row that owns a candidate (row_stat.x), key = (~ord(best) << 32) | row
-struct RowBestSource {
-    typedef uint4 Raw;
-    static constexpr int V = 1, U = 4;
-    const uint4* rs;
-    int R;
-    __device__ __forceinline__ Raw load(int g) const { return rs[g]; }
-    __device__ __forceinline__ unsigned exact(const Raw& r, int g, u64 lo, u64 hi) const {
-        const u64 k = ((u64)(~r.x) << 32) | (u64)(uint32_t)g;
-        return (r.z && k >= lo && k <= hi) ? 1u : 0u;
-    }
-    __device__ __forceinline__ u64 key_at(int g, int) const { return ((u64)(~rs[g].x) << 32) | (u64)(uint32_t)g; }
-    __device__ __forceinline__ int groups() const { return R; }
-};
-
 // ------------------------------------------------------------------------------------------------
 // K0: objectness top-k
 // ------------------------------------------------------------------------------------------------
@@ -1814,6 +1799,62 @@ __device__ __noinline__ void nms_group_by_label(const DevParams& P, int b, int n
     }
 }
 
+// Upper key bound of a chunk of the NMS candidate stream: the W-th best ROW maximum is a lower bound of the W-th
+// best candidate score (each of those rows owns a candidate at least that good), so when a chunk must reach
+// cumulative rank W only the rows whose best score reaches that bound can matter, and only their entries at or
+// above it. The bound need not be exact: a 512-bin histogram of the row maxima gives T = lower edge of the bin in
+// which the count from the top reaches W (round 1 sorted the row maxima for this: 20 k cycles per image; this is
+// ~4 k). Lists those rows (unordered) in rowkeys[] and returns their number, or -1 (fewer than W candidate rows /
+// list longer than NMS_KCAP: the caller scans the whole matrix). bmax / bmin = ord of the best / worst candidate
+// score of the image. All threads of the NMS block call.
+__device__ __noinline__ int nms_pick_rows(const DevParams& P, int b, int W, uint32_t bmax, uint32_t bmin, u64* rowkeys,
+                                          TopSelSmem& S, uint32_t* t_ord) {
+    static_assert(NMS_THREADS == 512, "one histogram bin per thread");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint4* rs = P.row_stat + (size_t)b * P.R;
+    const uint32_t range = bmax - bmin;
+    const int shift = range >= 512u ? (32 - __clz(range)) - 9 : 0;
+    S.hist[tid] = 0;
+    if (tid == 0) {
+        S.count = 0;
+        S.kb = -1;
+    }
+    __syncthreads();
+    for (int r = tid; r < P.R; r += NMS_THREADS) {
+        const uint4 st = rs[r];
+        if (st.z) atomicAdd(&S.hist[(bmax - st.x) >> shift], 1);
+    }
+    __syncthreads();
+    const int v = S.hist[tid];
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) S.wsum[warp] = incl;
+    __syncthreads();
+    int excl = incl - v;
+    for (int w = 0; w < warp; ++w) excl += S.wsum[w];
+    if (excl < W && W <= excl + v) S.kb = tid;
+    __syncthreads();
+    const int pb = S.kb;
+    if (pb < 0) return -1;
+    for (int r = tid; r < P.R; r += NMS_THREADS) {
+        const uint4 st = rs[r];
+        if (st.z && (int)((bmax - st.x) >> shift) <= pb) {
+            const int sp = atomicAdd(&S.count, 1);
+            if (sp < NMS_KCAP) rowkeys[sp] = (u64)(uint32_t)r;
+        }
+    }
+    __syncthreads();
+    const int n = S.count;
+    const u64 below = (((u64)pb + 1ull) << shift) - 1ull;  // largest (bmax - ord) inside the pivot bin
+    *t_ord = below >= (u64)bmax ? 0u : bmax - (uint32_t)below;
+    __syncthreads();  // S.count / S.kb are reused by the scan that follows
+    return n <= NMS_KCAP ? n : -1;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K2: per-image NMS over the merged, score-ordered candidate stream
 // ------------------------------------------------------------------------------------------------
@@ -1950,20 +1991,6 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
 
     int processed = 0;
     u64 lo = gmin;
-    // Upper key bounds for the chunks: the W-th best ROW maximum is a lower bound of the W-th best candidate
-    // score (each of those rows owns a candidate at least that good), so when a chunk must reach cumulative
-    // rank W every key above rowkeys[W-1] is rejected by the 32-bit window instead of going through the
-    // histogram. The (up to NMS_KCAP) best rows are selected and sorted once.
-    int nrows_sorted = 0;
-    if (!generic) {
-        RowBestSource rsrc;
-        rsrc.rs = P.row_stat + (size_t)b * P.R;
-        rsrc.R = P.R;
-        const int mrows = P.R < NMS_KCAP ? P.R : NMS_KCAP;
-        nrows_sorted = select_sorted_prefix(rsrc, gmin & 0xFFFFFFFF00000000ull, gmax, mrows, rowkeys, ktmp, NMS_KCAP, S);
-        nrows_sorted = nrows_sorted < mrows ? nrows_sorted : mrows;
-        __syncthreads();
-    }
     // the first chunk only needs a little more than `cap` candidates; later chunks (heavy suppression) are full
     int chunk = cap + (cap >> 2) + 64;
     chunk = chunk < NMS_CH ? chunk : NMS_CH;
@@ -1976,21 +2003,30 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         const int want = min(chunk, ntot - processed);
         chunk = NMS_CH;
         const int wc = processed + want;  // cumulative rank this chunk must reach
-        const u64 hi = wc <= nrows_sorted ? (rowkeys[wc - 1] | 0xFFFFFFFFull) : gmax;
+        u64 hi = gmax;
+        int nrows = -1;
+        if (!generic && nonneg) {
+            uint32_t t_ord = 0u;
+            nrows = nms_pick_rows(P, b, wc, s_red[0], ~s_red[1], rowkeys, S, &t_ord);
+            if (nrows >= 0) {
+                const u64 hi_t = ((u64)(~t_ord) << 32) | 0xFFFFFFFFull;
+                hi = hi_t < gmax ? hi_t : gmax;
+            }
+        }
         int got;
-        if (wc <= nrows_sorted && nonneg) {
-            // only the wc best rows can hold one of the wc best candidates: scan just their matrix rows
+        if (nrows >= 0) {
+            // only the listed rows can hold one of the wc best candidates: scan just their matrix rows
             RowListSource rl;
             rl.m = mat;
             rl.rows = rowkeys;
-            rl.nrows = wc;
+            rl.nrows = nrows;
             rl.C = C;
             rl.nsub = (C + 127) / 128;
             rl.vec4 = ((C & 3) == 0);
             rl.win.set(lo, hi);
             int staged = -1;
             if (P.nms_stage_rows > 0)
-                staged = nms_stage_scan(P, mat, rowkeys, wc, lo, hi, keys, NMS_KCAP, nms_smem + P.nms_stage_off, &s_stash);
+                staged = nms_stage_scan(P, mat, rowkeys, nrows, lo, hi, keys, NMS_KCAP, nms_smem + P.nms_stage_off, &s_stash);
             if (staged >= 0 && staged <= NMS_KCAP) {
                 StashSource none;
                 got = select_sorted_prefix(none, lo, hi, want, keys, ktmp, NMS_KCAP, S, staged);

@@ -21,6 +21,9 @@ CASES = {
     # BASELINE.json configs 1-3 at reduced batch
     'csp608_sparse': _csp(608, 2, 'sparse', 11),
     'csp608_dense': _csp(608, 2, 'dense', 12),
+    # the same setting with TRUE Gaussian tails (objectness logits beyond +2 occur; host-generated inputs)
+    'csp608_gauss': _csp(608, 2, 'gauss', 36),
+    'v3_416_gauss': _v3(416, 2, 'gauss', 37),
     # single-problem regime of batched_nms (n < split_thr), mostly separable by class
     'csp608_dense_thr07': _csp(608, 2, 'dense', 13, score_thr=0.7),
     'csp608_sparse_thr002': _csp(608, 2, 'sparse', 13, score_thr=0.02),
@@ -94,7 +97,7 @@ PKL_CASE = dict(mode=capi.MODE_V3, batch=1, sizes=[(32, 32), (16, 16), (8, 8)], 
 GOLDEN_CASES = ['csp608_sparse', 'csp608_dense', 'csp608_dense_thr07', 'csp608_sparse_thr002', 'csp320_nopre_sparse', 'csp_odd', 'csp416_rescale',
                 'csp_saturated', 'tencent_agnostic', 'csp_nms_agnostic', 'csp_nms_offset1', 'csp_nms_maxnum',
                 'csp_force_global', 'v3_416_sparse', 'v3_416_dense', 'v3_320_mid', 'v3_rescale', 'csp640_sparse',
-                'csp_empty', 'v3_640_sparse', 'csp1280_sparse', 'csp_nms_score_thr', 'csp_nms_score_thr_split']
+                'csp_empty', 'v3_640_sparse', 'csp1280_sparse', 'csp_nms_score_thr', 'csp_nms_score_thr_split', 'csp608_gauss', 'v3_416_gauss']
 
 
 def asis_rel_err(ref_dets, got_dets):
@@ -129,3 +132,11 @@ def asis_strict_rel_err(ref_dets, got_dets):
 # value (documented in INTEGRATION.md §3a): one corner of one box at 1280^2 is -0.39 = 34.1 - 34.5, a 2-ulp-of-34
 # absolute difference (7.6e-6) between torch's SIMD sigmoid and the canonical polynomial is 1.94e-5 of the corner.
 STRICT_OUTLIERS = {'csp1280_sparse': 2.0e-5}
+
+
+def device_levels(case, p, device='cuda'):
+    """The case's head tensors on the device: the device generator, or (host-generated distributions) an upload."""
+    import torch
+    if case['dist'] == 'gauss':
+        return [torch.from_numpy(x).to(device) for x in host_levels(case, p)]
+    return ysynth.synth_levels(p, case['seed'], case['dist'], device=device)

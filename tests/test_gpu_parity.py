@@ -26,7 +26,7 @@ def run_cuda(case, params=None, levels=None):
     import yolopp
     p = params or cases.build_params(case)
     if levels is None:
-        levels = yolopp.synth.synth_levels(p, case['seed'], case['dist'])
+        levels = cases.device_levels(case, p)
     sf = cases.scale_factors(case)
     sf_t = torch.from_numpy(sf).cuda() if sf is not None else None
     out = yolopp.get_bboxes_raw(p, levels, sf_t)

@@ -74,6 +74,8 @@ def host_levels(case, params=None):
     bits as the device generator). Test / CPU-baseline infrastructure: imports oracle/."""
     from oracle import oracle
     p = params or build_params(case)
+    if case['dist'] == 'gauss':
+        return gauss_levels(case, p)
     mean, std = ysynth.dist_stats(case['dist'])
     na = p.num_attrib
     m = np.array([mean[0]] * 4 + [mean[1]] + [mean[2]] * (na - 5), np.float32)
@@ -83,4 +85,21 @@ def host_levels(case, params=None):
         hw = p.height[l] * p.width[l]
         x = oracle.synth_level(p.batch, p.num_anchors, na, hw, m, s, ysynth.level_seed(case['seed'], l))
         out.append(x.reshape(p.level_shape(l)))
+    return out
+
+
+def gauss_levels(case, p):
+    """SURVEY.md §8(d)'s "COCO-like sparse" distribution with TRUE Gaussian tails (the bit-reproducible device
+    generator is Irwin-Hall(4), support +-3.46 sigma): box logits N(0,1), objectness N(-5, 2^2), class logits
+    N(-4.9, 1.5^2), from numpy's MT19937 (deterministic across platforms) — generated on the host and uploaded."""
+    rng = np.random.RandomState(case['seed'])
+    na = p.num_attrib
+    mean = np.array([0.0] * 4 + [-5.0] + [-4.9] * (na - 5), np.float32)
+    std = np.array([1.0] * 4 + [2.0] + [1.5] * (na - 5), np.float32)
+    out = []
+    for l in range(p.num_levels):
+        B, _, H, W = p.level_shape(l)
+        z = rng.standard_normal((B, p.num_anchors, na, H * W)).astype(np.float32)
+        x = z * std[None, None, :, None] + mean[None, None, :, None]
+        out.append(np.ascontiguousarray(x.reshape(p.level_shape(l)), np.float32))
     return out
