@@ -95,7 +95,8 @@ typedef struct yolopp_params {
     int32_t max_per_img;   /* cfg.max_per_img (<=0: keep all) */
     int32_t rescale;       /* divide boxes by scale_factor[b][0..3] before NMS */
     /* capacity knobs (0 = worst case) */
-    int32_t out_capacity;  /* rows of the per-image output block; 0 -> max_per_img (must be > 0 then) */
+    int32_t out_capacity;  /* rows of the per-image output block; 0 -> max_per_img (must be > 0 then). With max_per_img <= 0
+                              ("keep all") a status of YOLOPP_E_OVERFLOW reports images with more survivors than this */
     /* scheduling hint (no effect on results): how many batches the caller keeps in flight on different streams.
        <= 1: the batch runs alone -> lowest latency schedule; > 1: schedule that lets neighbouring batches overlap */
     int32_t batches_in_flight;
@@ -235,14 +236,15 @@ int yolopp_coder_decode(int mode, const float* bboxes, const float* pred, float 
  * result in (score desc, index asc) order, first max_num kept. score_threshold > 0: mmcv's NMSop prefilter
  * (only boxes with score > score_threshold enter the greedy pass).
  *   boxes  DEVICE [n][4] fp32 (16-byte aligned), scores DEVICE [n], idxs DEVICE [n] int64 in [0, num_labels) or NULL
- *   dets   DEVICE [cap][5], keep DEVICE [cap] int64 (indices into the inputs), cap = min(4096, max_num if
- *          0 < max_num < n else n)  — the kept list lives in shared memory, so max_num must be <= 4096
- *   num_keep DEVICE int32[2]: [0] = number kept, [1] = 0 or YOLOPP_E_OVERFLOW (no max_num given and more than
- *          4096 boxes survive)
+ *   dets   DEVICE [cap][5], keep DEVICE [cap] int64 (indices into the inputs), cap = max_num if 0 < max_num < n else n
+ *   num_keep DEVICE int32[2]: [0] = number kept, [1] = status (0)
+ *   workspace: only needed when cap > 4096 (the kept list then lives there instead of shared memory):
+ *          >= yolopp_nms_workspace_bytes(n, 0) bytes, 256-byte aligned; may be NULL otherwise
  */
 int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, int32_t num_labels,
                        float iou_thr, float score_threshold, int nms_offset, int split_thr, int class_agnostic,
-                       int max_num, float* dets, int64_t* keep, int32_t* num_keep, void* stream);
+                       int max_num, float* dets, int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                       void* stream);
 
 /*
  * multiclass_nms (mmdet/core/post_processing/bbox_nms.py:7-93) on device, for the other heads that share the
@@ -252,7 +254,7 @@ int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* i
  *   multi_scores DEVICE [n][C+1] (last column = background, ignored); score_factors DEVICE [n] or NULL
  *   dets DEVICE [cap][5], labels DEVICE [cap] int64, flat_inds DEVICE [cap] int64 (row*C + class; may be NULL),
  *   num_keep DEVICE int32[2] ([0] count, [1] 0 or YOLOPP_E_OVERFLOW), num_candidates DEVICE [1] (may be NULL);
- *   cap = min(4096, effective max_num or n*C)
+ *   cap = effective max_num when 0 < it < n*C, else n*C
  *   workspace >= yolopp_nms_workspace_bytes(n, C), 256-byte aligned
  */
 size_t yolopp_nms_workspace_bytes(int64_t n, int32_t num_classes);

@@ -49,7 +49,7 @@ static size_t nms_add_stage(ypp::DevParams& d, size_t smem) {
 struct Plan {
     DevParams d;
     size_t off_counters, counters_bytes;
-    size_t off_ckey, off_rank, off_row_anchor, off_row_box, off_row_stat, off_mat;
+    size_t off_ckey, off_rank, off_row_anchor, off_row_box, off_row_stat, off_mat, off_kept, kept_stride;
     size_t total;
     size_t dec_smem, sel_smem, nms_smem;
     int dec_ctas_per_sm;
@@ -154,10 +154,13 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     if (p->nms_max_num > 0) m_eff = (m_eff > 0 && m_eff < p->nms_max_num) ? m_eff : p->nms_max_num;
     d.m_eff = m_eff;
     d.out_cap = p->out_capacity > 0 ? p->out_capacity : p->max_per_img;
-    CHECK_ARG(d.out_cap >= 1 && d.out_cap <= NMS_MAX_KEEP);
-    CHECK_ARG(m_eff <= NMS_MAX_KEEP);
-    // boxes the NMS pass may keep: max_num when given, else one more than fits (to flag the overflow)
+    CHECK_ARG(d.out_cap >= 1 && d.out_cap <= YOLOPP_MAX_ROWS);
+    CHECK_ARG(m_eff <= YOLOPP_MAX_ROWS);
+    // boxes the NMS pass may keep: max_num when given, else one more than fits (to flag the overflow). Up to
+    // NMS_MAX_KEEP the kept list lives in shared memory, beyond that in the workspace.
     d.keep_cap = m_eff > 0 ? m_eff : d.out_cap + 1;
+    const int cap_s = d.keep_cap > NMS_MAX_KEEP ? 0 : d.keep_cap;
+    plan->kept_stride = d.keep_cap > NMS_MAX_KEEP ? align_up((size_t)d.keep_cap * 36, 256) : 0;
     CHECK_ARG((long long)d.R * d.C < (1ll << 31));
     int max_k = 0;
     for (int s = 0; s < d.nsegs; ++s)
@@ -187,7 +190,7 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
         }
     }
     CHECK_ARG(plan->sel_smem <= SMEM_LIMIT);
-    plan->nms_smem = (size_t)NMS_KCAP * 8 * 2 + (size_t)d.keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)d.keep_cap * 28 +
+    plan->nms_smem = (size_t)NMS_KCAP * 8 * 2 + (size_t)cap_s * 8 + (size_t)NMS_CH * 24 + (size_t)cap_s * 28 +
                      (size_t)d.C * 4;
     plan->nms_smem = align_up(plan->nms_smem, 16);
     d.nms_rowkeys_off = (int)plan->nms_smem;
@@ -286,6 +289,8 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
     off += align_up(B * R * 16, 256);
     plan->off_mat = off;
     off += align_up(B * R * Cc * 4, 256);
+    plan->off_kept = off;
+    off += B * plan->kept_stride;
     plan->total = off;
     return true;
 }
@@ -300,6 +305,8 @@ void bind_workspace(Plan* plan, void* ws) {
     d.row_box = (float4*)(w + plan->off_row_box);
     d.row_stat = (uint4*)(w + plan->off_row_stat);
     d.mat = (uint32_t*)(w + plan->off_mat);
+    d.nms_kept = plan->kept_stride ? w + plan->off_kept : nullptr;
+    d.nms_kept_stride = (long long)plan->kept_stride;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -810,6 +817,7 @@ int yolopp_phase_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, 
 // standalone NMS entry points: the per-image NMS kernel with B = 1
 // ---------------------------------------------------------------------------------------------------
 static size_t nms_only_smem(int keep_cap, int nlab, int* rowkeys_off) {
+    if (keep_cap > NMS_MAX_KEEP) keep_cap = 0;  // kept list in the workspace
     size_t sm = (size_t)NMS_KCAP * 8 * 2 + (size_t)keep_cap * 8 + (size_t)NMS_CH * 24 + (size_t)keep_cap * 28 + (size_t)nlab * 4;
     sm = align_up(sm, 16);
     *rowkeys_off = (int)sm;
@@ -826,15 +834,21 @@ static int launch_nms_only(DevParams& d, int nlab, cudaStream_t stream) {
     return cuda_rc(cudaGetLastError());
 }
 
+static size_t nms_kept_bytes(long long cap) { return cap > NMS_MAX_KEEP ? align_up((size_t)cap * 36, 256) : 0; }
+
 size_t yolopp_nms_workspace_bytes(int64_t n, int32_t num_classes) {
     if (n < 0 || num_classes < 0) return 0;
-    // multiclass_nms: score matrix + per-row statistics; batched_nms / nms (num_classes == 0): nothing
-    return num_classes == 0 ? 256 : align_up((size_t)n * num_classes * 4, 256) + align_up((size_t)n * 16, 256) + 256;
+    // multiclass_nms: score matrix + per-row statistics; batched_nms / nms (num_classes == 0): nothing — plus, in both,
+    // the kept list when more than 4096 boxes may be kept (worst case: every candidate)
+    const long long cand = num_classes == 0 ? n : n * num_classes;
+    const size_t base = num_classes == 0 ? 256 : align_up((size_t)n * num_classes * 4, 256) + align_up((size_t)n * 16, 256) + 256;
+    return base + nms_kept_bytes(cand);
 }
 
 int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* idxs, int64_t n, int32_t num_labels,
                        float iou_thr, float score_threshold, int nms_offset, int split_thr, int class_agnostic,
-                       int max_num, float* dets, int64_t* keep, int32_t* num_keep, void* stream_) {
+                       int max_num, float* dets, int64_t* keep, int32_t* num_keep, void* workspace, size_t workspace_bytes,
+                       void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n < 0 || n >= (1ll << 31) || !num_keep || (nms_offset != 0 && nms_offset != 1)) return YOLOPP_E_INVALID;
     const DeviceInfo di = device_info();
@@ -843,13 +857,15 @@ int yolopp_batched_nms(const float* boxes, const float* scores, const int64_t* i
     if (!boxes || !scores || !dets || !keep || (((uintptr_t)boxes) & 15)) return YOLOPP_E_INVALID;
     const int nlab = idxs ? num_labels : 1;
     if (nlab < 1 || nlab > YOLOPP_MAX_CLASSES) return YOLOPP_E_INVALID;
-    long long cap = (max_num > 0 && max_num < n) ? max_num : n;
-    if (max_num > NMS_MAX_KEEP) return YOLOPP_E_INVALID;  // kept list lives in shared memory
-    if (cap > NMS_MAX_KEEP) cap = NMS_MAX_KEEP;           // "keep all": overflow is reported in num_keep[1]
+    const long long cap = (max_num > 0 && max_num < n) ? max_num : n;
+    if (nms_kept_bytes(cap) && (!workspace || workspace_bytes < nms_kept_bytes(cap) || (((uintptr_t)workspace) & 255)))
+        return YOLOPP_E_WORKSPACE;  // more than 4096 boxes may be kept: the kept list lives in the workspace
     cudaError_t e0 = cudaMemsetAsync(num_keep, 0, 2 * sizeof(int32_t), stream);
     if (e0 != cudaSuccess) return cuda_rc(e0);
     DevParams d;
     memset(&d, 0, sizeof(d));
+    d.nms_kept = nms_kept_bytes(cap) ? (unsigned char*)workspace : nullptr;
+    d.nms_kept_stride = (long long)nms_kept_bytes(cap);
     d.B = 1;
     d.R = (int)n;
     d.C = 1;
@@ -896,14 +912,13 @@ int yolopp_multiclass_nms(const float* multi_bboxes, int boxes_per_class, const 
     if (max_num > 0) m_eff = max_num;
     if (nms_max_num > 0) m_eff = (m_eff > 0 && m_eff < nms_max_num) ? m_eff : nms_max_num;
     const long long total = n * num_classes;
-    long long cap = (m_eff > 0 && m_eff < total) ? m_eff : total;
-    if (m_eff > NMS_MAX_KEEP) return YOLOPP_E_INVALID;
-    if (cap > NMS_MAX_KEEP) cap = NMS_MAX_KEEP;  // "keep all": overflow is reported in num_keep[1]
+    const long long cap = (m_eff > 0 && m_eff < total) ? m_eff : total;
     cudaError_t e0 = cudaMemsetAsync(num_keep, 0, 2 * sizeof(int32_t), stream);
     if (e0 != cudaSuccess) return cuda_rc(e0);
     unsigned char* w = (unsigned char*)workspace;
     uint32_t* mat = (uint32_t*)w;
     uint4* row_stat = (uint4*)(w + align_up((size_t)total * 4, 256));
+    unsigned char* kept = w + align_up((size_t)total * 4, 256) + align_up((size_t)n * 16, 256) + 256;  // (after the stats)
     multiclass_prep_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(multi_scores, score_factors, (const float4*)multi_bboxes,
                                                                         boxes_per_class ? 1 : 0, (int)n, num_classes,
                                                                         score_thr, mat, row_stat);
@@ -911,6 +926,8 @@ int yolopp_multiclass_nms(const float* multi_bboxes, int boxes_per_class, const 
     if (e != cudaSuccess) return cuda_rc(e);
     DevParams d;
     memset(&d, 0, sizeof(d));
+    d.nms_kept = nms_kept_bytes(cap) ? kept : nullptr;
+    d.nms_kept_stride = (long long)nms_kept_bytes(cap);
     d.B = 1;
     d.R = (int)n;
     d.C = num_classes;

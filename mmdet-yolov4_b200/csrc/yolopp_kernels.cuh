@@ -112,6 +112,8 @@ struct DevParams {
     const float* g_scores;     // generic: [n]
     const long long* g_labels; // generic: [n] or null (one class)
     long long* o_keep;         // kept candidate (flat) indices, in output order; may be null
+    unsigned char* nms_kept;   // kept list in global memory, [B][nms_kept_stride] bytes (keep_cap > NMS_MAX_KEEP), else null
+    long long nms_kept_stride;
     // outputs
     float* o_dets;
     long long* o_labels;
@@ -1783,19 +1785,28 @@ __device__ __noinline__ void nms_group_by_label(const DevParams& P, int b, int n
         if (lane == 31) offs[C] = incl;  // == nk
     }
     __syncthreads();
-    for (int i = tid; i < nk; i += NMS_THREADS) {
-        const int c = kcl[i];
-        int pos = cnt[c];
-        for (int j = 0; j < i; ++j) pos += (kcl[j] == c) ? 1 : 0;  // rows are few (<= max_per_img)
-        const u64 key = kkey[i];
-        const uint32_t flat = key_flat(key);
-        const float4 bx = row_box[P.boxes_per_class ? flat : flat / (uint32_t)C];
-        float* d = P.o_cls_dets + ((size_t)b * P.out_cap + pos) * 5;
-        d[0] = bx.x;
-        d[1] = bx.y;
-        d[2] = bx.z;
-        d[3] = bx.w;
-        d[4] = key_score(key);
+    // stable placement, one chunk of NMS_THREADS rows at a time: position = running base of the class + rank among
+    // the chunk's earlier rows of that class; then the bases advance by the chunk's class counts
+    for (int s0 = 0; s0 < nk; s0 += NMS_THREADS) {
+        const int i = s0 + tid;
+        int c = -1;
+        if (i < nk) {
+            c = kcl[i];
+            int pos = cnt[c];
+            for (int j = s0; j < i; ++j) pos += (kcl[j] == c) ? 1 : 0;
+            const u64 key = kkey[i];
+            const uint32_t flat = key_flat(key);
+            const float4 bx = row_box[P.boxes_per_class ? flat : flat / (uint32_t)C];
+            float* d = P.o_cls_dets + ((size_t)b * P.out_cap + pos) * 5;
+            d[0] = bx.x;
+            d[1] = bx.y;
+            d[2] = bx.z;
+            d[3] = bx.w;
+            d[4] = key_score(key);
+        }
+        __syncthreads();
+        if (c >= 0) atomicAdd(&cnt[c], 1);
+        __syncthreads();
     }
 }
 
@@ -1873,23 +1884,33 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     __shared__ int s_nk, s_stash;
     __shared__ uint32_t s_red[4];
     const int cap = P.keep_cap;
+    // The kept list (key, offset box, area, class, chain link per kept box) lives in shared memory up to NMS_MAX_KEEP
+    // boxes; beyond that ("keep all" with many survivors: max_per_img = -1, RPN-sized standalone NMS) it lives in
+    // the caller's workspace — same code, the pointers just lead to global memory (L2 resident).
+    const bool kept_global = P.nms_kept != nullptr;
+    const int cap_s = kept_global ? 0 : cap;
     u64* keys = reinterpret_cast<u64*>(nms_smem);                 // [NMS_KCAP] sorted chunk
     u64* ktmp = keys + NMS_KCAP;                                   // [NMS_KCAP] scratch of the select
-    u64* kkey = ktmp + NMS_KCAP;                                   // [cap]
-    float* cx1 = reinterpret_cast<float*>(kkey + cap);             // [NMS_CH] x 5
+    u64* kkey = ktmp + NMS_KCAP;                                   // [cap_s]
+    float* cx1 = reinterpret_cast<float*>(kkey + cap_s);           // [NMS_CH] x 5
     float* cy1 = cx1 + NMS_CH;
     float* cx2 = cy1 + NMS_CH;
     float* cy2 = cx2 + NMS_CH;
     float* car = cy2 + NMS_CH;
     int* ccl = reinterpret_cast<int*>(car + NMS_CH);               // [NMS_CH]
-    float* kx1 = reinterpret_cast<float*>(ccl + NMS_CH);           // [cap] x 5
+    float* kx1 = reinterpret_cast<float*>(ccl + NMS_CH);           // [cap_s] x 5
+    int* chead = reinterpret_cast<int*>(kx1 + 7 * (size_t)cap_s);  // [C]   latest kept box of each class (-1: none)
+    if (kept_global) {
+        unsigned char* gk = P.nms_kept + (size_t)blockIdx.x * (size_t)P.nms_kept_stride;
+        kkey = reinterpret_cast<u64*>(gk);
+        kx1 = reinterpret_cast<float*>(kkey + cap);
+    }
     float* ky1 = kx1 + cap;
     float* kx2 = ky1 + cap;
     float* ky2 = kx2 + cap;
     float* kar = ky2 + cap;
     int* kcl = reinterpret_cast<int*>(kar + cap);                  // [cap]
     int* knext = kcl + cap;                                        // [cap] previous kept box of the same class
-    int* chead = knext + cap;                                      // [C]   latest kept box of each class (-1: none)
     u64* rowkeys = reinterpret_cast<u64*>(nms_smem + P.nms_rowkeys_off);  // [NMS_KCAP] best rows, sorted
 
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;

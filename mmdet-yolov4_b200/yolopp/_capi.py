@@ -246,7 +246,8 @@ def load_library(path=None):
     lib.yolopp_nms_workspace_bytes.argtypes = [c_int64, c_int32]
     lib.yolopp_batched_nms.restype = ctypes.c_int
     lib.yolopp_batched_nms.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_float, c_float, ctypes.c_int,
-                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_size_t, c_void_p]
     lib.yolopp_multiclass_nms.restype = ctypes.c_int
     lib.yolopp_multiclass_nms.argtypes = [c_void_p, ctypes.c_int, c_void_p, c_int64, c_int32, c_float, c_void_p, c_float,
                                           c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,

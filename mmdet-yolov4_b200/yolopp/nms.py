@@ -5,7 +5,7 @@
     nms              mmcv.ops.nms.nms
 
 Same argument meaning and return types; results follow the canonical tie order (score desc, index asc).
-Not supported (raise): nms types other than 'nms', numpy inputs, more than 4096 kept boxes.
+Not supported (raise): nms types other than 'nms', numpy inputs.
 CUDA tensors only — there is no CPU fallback.
 """
 import ctypes
@@ -47,18 +47,23 @@ def _run_batched(boxes, scores, idxs, iou_thr, offset, split_thr, class_agnostic
         num_labels = int(lab.max().item()) + 1  # mmcv's batched_nms synchronises too (boxes.max(), torch.unique)
         if int(lab.min().item()) < 0:
             raise ValueError('negative class index')
-    cap = min(max_num if 0 < max_num < n else n, 4096)
+    cap = max_num if 0 < max_num < n else n
     dets = torch.empty((max(cap, 1), 5), dtype=torch.float32, device=boxes.device)
     keep = torch.empty((max(cap, 1), ), dtype=torch.int64, device=boxes.device)
     cnt = torch.zeros((2, ), dtype=torch.int32, device=boxes.device)
     with torch.cuda.device(boxes.device):
+        ws_bytes = lib.yolopp_nms_workspace_bytes(n, 0) if cap > 4096 else 0  # kept list beyond the smem capacity
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=boxes.device) if ws_bytes else None
         rc = lib.yolopp_batched_nms(_p(b), _p(s), _p(lab), n, num_labels, float(iou_thr), float(score_threshold),
                                     int(offset), int(split_thr),
-                                    int(bool(class_agnostic)), int(max_num), _p(dets), _p(keep), _p(cnt), _stream())
+                                    int(bool(class_agnostic)), int(max_num), _p(dets), _p(keep), _p(cnt), _p(ws),
+                                    ws.numel() if ws is not None else 0, _stream())
+        if ws is not None:
+            ws.record_stream(torch.cuda.current_stream())
     _capi.check(rc, 'yolopp_batched_nms')
     k, status = (int(v) for v in cnt.tolist())
     if status:
-        raise RuntimeError('yolopp_batched_nms: more than 4096 boxes survive and no max_num was given')
+        raise RuntimeError(f'yolopp_batched_nms: status {status}')
     return dets[:k].to(boxes.dtype), keep[:k]
 
 
@@ -97,7 +102,7 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, s
     if cfg['nms_max_num'] > 0:
         m_eff = min(m_eff, cfg['nms_max_num']) if m_eff > 0 else cfg['nms_max_num']
     total = n * C
-    cap = min(m_eff if 0 < m_eff < total else total, 4096)
+    cap = m_eff if 0 < m_eff < total else total
     dets = torch.empty((max(cap, 1), 5), dtype=torch.float32, device=dev)
     labels = torch.empty((max(cap, 1), ), dtype=torch.int64, device=dev)
     flat = torch.empty((max(cap, 1), ), dtype=torch.int64, device=dev)
@@ -113,7 +118,7 @@ def multiclass_nms(multi_bboxes, multi_scores, score_thr, nms_cfg, max_num=-1, s
     _capi.check(rc, 'yolopp_multiclass_nms')
     k, status, ncand = (int(v) for v in cnt.tolist())
     if status:
-        raise RuntimeError('yolopp_multiclass_nms: more than 4096 boxes survive and no max_num was given')
+        raise RuntimeError(f'yolopp_multiclass_nms: status {status}')
     if ncand == 0:
         # the reference returns the (0, 4) boxes tensor here (bbox_nms.py:75-82)
         out = (mb.new_zeros((0, 4)).to(multi_bboxes.dtype), labels[:0])

@@ -65,6 +65,9 @@ CASES = {
     'csp_force_global': _csp(160, 2, 'dense', 32, C=20, nms_pre=500,
                              nms=dict(type='nms', iou_threshold=0.5, split_thr=1000000)),
     'csp_keep_all': _csp(64, 2, 'dense', 33, C=3, nms_pre=100, max_per_img=-1, out_capacity=400),
+    # "keep all" with more than 4096 survivors per image: the kept list moves from shared memory to the workspace
+    'csp_keep_many': _csp(128, 2, 'dense', 38, C=20, nms_pre=-1, score_thr=0.05, max_per_img=-1, out_capacity=20160,
+                          nms=dict(type='nms', iou_threshold=0.9)),
     # nms_cfg.score_threshold (mmcv NMSop prefilter), both batched_nms regimes
     'csp_nms_score_thr': _csp(128, 2, 'dense', 34, C=6, nms_pre=300,
                               nms=dict(type='nms', iou_threshold=0.5, score_threshold=0.55)),

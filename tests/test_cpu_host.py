@@ -55,7 +55,7 @@ def test_planning_calls_need_no_device():
 @pytest.mark.parametrize('mutate', [
     lambda p: setattr(p, 'abi_version', 99), lambda p: setattr(p, 'mode', 5), lambda p: setattr(p, 'batch', 0),
     lambda p: setattr(p, 'num_levels', 9), lambda p: setattr(p, 'num_anchors', 0), lambda p: setattr(p, 'num_classes', 5000),
-    lambda p: setattr(p, 'nms_offset', 2), lambda p: setattr(p, 'layout', 2), lambda p: setattr(p, 'max_per_img', 5000),
+    lambda p: setattr(p, 'nms_offset', 2), lambda p: setattr(p, 'layout', 2), lambda p: setattr(p, 'max_per_img', 1 << 21),
     lambda p: (setattr(p, 'max_per_img', -1), setattr(p, 'out_capacity', 0)),
 ])
 def test_invalid_params_are_rejected(mutate):

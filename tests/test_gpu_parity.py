@@ -359,19 +359,31 @@ def test_multiclass_nms_matches_oracle(n, C, per_class, factors, thr, max_num):
     np.testing.assert_array_equal(_u32(dets.cpu().numpy()), _u32(od))
 
 
-def test_keep_all_overflow_is_reported_not_truncated():
-    """No max_num and more than 4096 survivors: the ops raise instead of silently truncating."""
+def test_keep_all_beyond_the_smem_kept_list():
+    """No max_num and more than 4096 survivors (RPN-sized standalone NMS): the kept list lives in the workspace;
+    nothing is truncated."""
     import yolopp
     rng = np.random.RandomState(9)
     n = 6000
     boxes = np.concatenate([np.arange(n, dtype=np.float32)[:, None] * 10 + np.zeros((n, 2), np.float32),
                             np.arange(n, dtype=np.float32)[:, None] * 10 + 5 + np.zeros((n, 2), np.float32)], 1)
     scores = rng.rand(n).astype(np.float32)
-    with pytest.raises(RuntimeError):
-        yolopp.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.5)
+    dets, inds = yolopp.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.5)
+    want = oracle.nms(boxes, scores, 0.5)
+    assert inds.numel() == 6000 == len(want)
+    np.testing.assert_array_equal(inds.cpu().numpy(), want)
     dets, inds = yolopp.nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(), 0.5, max_num=4096)
-    assert inds.numel() == 4096
-    np.testing.assert_array_equal(inds.cpu().numpy(), oracle.nms(boxes, scores, 0.5)[:4096])
+    np.testing.assert_array_equal(inds.cpu().numpy(), want[:4096])
+    # RPN-like: 12000 overlapping boxes, 5 levels as classes, keep all (rpn_head.py:247 then dets[:max_per_img])
+    boxes = _rand_boxes(rng, 12000, span=800., wh=200.)
+    scores = rng.rand(12000).astype(np.float32)
+    idxs = rng.randint(0, 5, 12000).astype(np.int64)
+    dets, keep = yolopp.batched_nms(torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda(),
+                                    torch.from_numpy(idxs).cuda(), dict(type='nms', iou_threshold=0.7))
+    od, ok = oracle.batched_nms(boxes, scores, idxs, 0.7)
+    assert len(ok) > 4096
+    np.testing.assert_array_equal(keep.cpu().numpy(), ok)
+    np.testing.assert_array_equal(_u32(dets.cpu().numpy()), _u32(od))
 
 
 def test_get_results_host_and_bbox2result():
