@@ -23,9 +23,15 @@ namespace {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Staging ring of the NMS kernel's candidate scan: NMS_STAGES buffers of whole score-matrix rows (rows must be
-// 16-byte multiples for the asynchronous copies; classes <= 128 so that one lane owns one 16-byte chunk of a row).
-// The NMS CTA owns its SM anyway (512 threads x 128 registers), so the ring may take what the other buffers leave.
+constexpr size_t SMEM_LIMIT_TOTAL = 232448;  // static + dynamic shared memory a CTA may use on sm_100 (227 KB opt-in)
+#ifndef YPP_NMS_STATIC_SMEM
+#define YPP_NMS_STATIC_SMEM 10496  // >= the per-image kernels' static shared memory (ptxas -v; checked at start-up)
+#endif
+constexpr size_t SMEM_LIMIT = SMEM_LIMIT_TOTAL - YPP_NMS_STATIC_SMEM;  // dynamic part
+
+// Staging buffer of the NMS kernel's candidate scan: whole score-matrix rows, one bulk copy each (rows must be
+// 16-byte multiples; classes <= 128). The NMS CTA owns its SM anyway (512 threads x 128 registers), so the buffer takes
+// what the other arrays leave — the more rows fit, the more often the scan is a single DRAM round trip.
 static size_t nms_add_stage(ypp::DevParams& d, size_t smem) {
     d.nms_stage_off = 0;
     d.nms_stage_rows = 0;
@@ -34,16 +40,13 @@ static size_t nms_add_stage(ypp::DevParams& d, size_t smem) {
 #endif
     if (d.C % 4 != 0 || d.C > 128 || d.generic) return smem;
     smem = (smem + 127) & ~(size_t)127;
-#ifndef YPP_NMS_STAGE_KB
-#define YPP_NMS_STAGE_KB 120  // measured (608^2 b64): 60 KB 53.6 us, 90 KB 52.1 us, 120 KB 51.6 us per NMS launch
-#endif
-    int rows = (int)((YPP_NMS_STAGE_KB * 1024) / ypp::NMS_STAGES / ((size_t)d.C * 4));
-    rows &= ~15;  // whole rounds of the 16 warps
-    if (rows > 256) rows = 256;
-    if (rows < 16 || smem + (size_t)ypp::NMS_STAGES * rows * d.C * 4 > 212 * 1024) return smem;
+    if (smem >= SMEM_LIMIT) return smem;
+    int rows = (int)((SMEM_LIMIT - smem) / ((size_t)d.C * 4));
+    if (rows > 1024) rows = 1024;
+    if (rows < 16) return smem;
     d.nms_stage_off = (int)smem;
     d.nms_stage_rows = rows;
-    return smem + (size_t)ypp::NMS_STAGES * rows * d.C * 4;
+    return smem + (size_t)rows * d.C * 4;
 }
 
 struct Plan {
@@ -60,9 +63,6 @@ struct Plan {
     do {                \
         if (!(cond)) return false; \
     } while (0)
-
-constexpr size_t SMEM_LIMIT = 232448 - 10448;  // dynamic shared memory a CTA may use on sm_100: the 227 KB opt-in limit
-                                               // minus the per-image kernels' static shared memory (10 448 B)
 
 // Validates the params and lays the workspace out. Level pointers are filled in by the caller.
 bool make_plan(const yolopp_params* p, Plan* plan) {
@@ -358,6 +358,7 @@ DeviceInfo device_info() {
         cudaFuncAttributes fa;
         cudaError_t e2 = cudaFuncGetAttributes(&fa, fn);
         if (e2 != cudaSuccess) return e2;
+        if (fa.sharedSizeBytes > (size_t)YPP_NMS_STATIC_SMEM) return cudaErrorInvalidConfiguration;  // SMEM_LIMIT assumes it
         return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     };
     cudaError_t e = opt_in((const void*)select_kernel);
@@ -810,6 +811,7 @@ int yolopp_prof_read(long long* host, int n) {
 int yolopp_prof_cta_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_prof_cta, sizeof(long long) * 1024 * 8); }
 int yolopp_ssp_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_ssp, sizeof(long long) * 2 * 64 * 4 * 10); }
 int yolopp_ssp2_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_ssp2, sizeof(long long) * 2 * 64 * 4 * 4); }
+int yolopp_sub_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_sub, sizeof(long long) * 256 * 32); }
 int yolopp_phase_read(long long* host) { return (int)cudaMemcpyFromSymbol(host, ypp::g_phase, sizeof(long long) * 2 * 256 * 16); }
 #endif
 

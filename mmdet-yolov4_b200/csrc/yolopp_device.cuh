@@ -235,6 +235,60 @@ __device__ __forceinline__ void bitonic_sort(u64* s, int p2) {
     __syncthreads();
 }
 
+// Ascending bitonic sort of (key, 16-bit payload) pairs with the data in REGISTERS, one pair per thread: every
+// exchange at distance < 32 is a warp shuffle, only the exchanges at distance >= 32 go through shared memory (two
+// buffers used alternately: one block barrier per such step). The per-image kernels are bound by instruction issue
+// (16 warps on one SM), so what counts is instructions per step: ~12 here against ~80 for a sort that walks shared
+// memory. p2 = power of two, 32 <= p2 <= blockDim.x; key[0..p2) / pay[0..p2) in, sorted out; tk / tp = scratch of
+// the same size; the caller has synchronised the block after filling key / pay; all threads call.
+__device__ __noinline__ void bitonic_sort_kv(u64* __restrict__ key, unsigned short* __restrict__ pay, u64* __restrict__ tk,
+                                             unsigned short* __restrict__ tp, int p2) {
+    const int e = threadIdx.x, lane = e & 31;
+    const bool active = e < p2;  // whole warps
+    u64 k = active ? key[e] : ~0ull;
+    unsigned v = active ? pay[e] : 0u;
+    int flip = 0;
+#pragma unroll 1
+    for (int size = 2; size <= p2; size <<= 1) {
+        const bool up = (e & size) == 0;
+        int stride = size >> 1;
+#pragma unroll 1
+        for (; stride >= 32; stride >>= 1) {
+            u64* bk = flip ? key : tk;
+            unsigned short* bp = flip ? pay : tp;
+            flip ^= 1;
+            if (active) {
+                bk[e] = k;
+                bp[e] = (unsigned short)v;
+            }
+            __syncthreads();
+            if (active) {
+                const u64 pk = bk[e ^ stride];
+                const unsigned pv = bp[e ^ stride];
+                const bool take = (k < pk) != (((e & stride) == 0) == up);  // the lower position keeps the smaller key when ascending
+                k = take ? pk : k;
+                v = take ? pv : v;
+            }
+        }
+        if (active) {
+#pragma unroll 1
+            for (; stride > 0; stride >>= 1) {
+                const u64 pk = __shfl_xor_sync(0xffffffffu, k, stride);
+                const unsigned pv = __shfl_xor_sync(0xffffffffu, v, stride);
+                const bool take = (k < pk) != (((lane & stride) == 0) == up);
+                k = take ? pk : k;
+                v = take ? pv : v;
+            }
+        }
+    }
+    __syncthreads();  // (the readers of the last exchange buffer are done)
+    if (active) {
+        key[e] = k;
+        pay[e] = (unsigned short)v;
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;

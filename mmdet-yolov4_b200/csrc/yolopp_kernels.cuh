@@ -72,8 +72,12 @@ struct SegDev {
 // per-CTA phase timestamps of the per-image kernels (profiling build only): [kernel][image][phase]
 __device__ long long g_phase[2][256][16];
 #define YPP_PHASE(k, blk, i) do { if (threadIdx.x == 0 && (blk) < 256) g_phase[k][blk][i] = clock64(); } while (0)
+// finer stamps inside the NMS kernel's first chunk: [image][stamp]
+__device__ long long g_sub[256][32];  // (stamps 0..16 in use)
+#define YPP_SUB(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) g_sub[blockIdx.x][i] = clock64(); } while (0)
 #else
 #define YPP_PHASE(k, blk, i) do { } while (0)
+#define YPP_SUB(i) do { } while (0)
 #endif
 
 struct DevParams {
@@ -1659,58 +1663,56 @@ __global__ void __launch_bounds__(32 * DENSE_WARPS, 6) decode_dense_kernel(const
     if (adm) P.row_stat[(size_t)b * P.R + r] = make_uint4(best, worst, (uint32_t)npass, 0u);
 }
 
-// Candidate scan of the NMS kernel through shared memory: the score-matrix rows of the `nrows` best rows
-// (rows[i], low word = row index) are streamed through a ring of NMS_STAGES staging buffers with 16-byte
-// asynchronous copies (no registers held, all stages in flight: the DRAM latency is paid about once instead of
-// once per load batch), and every entry inside the key window [lo, hi] lands in the stash `out` as a 64-bit key.
-// Warp w owns rows w, w + 16, ... of a stage, one lane per 16-byte chunk of a row (C <= 128, C % 4 == 0).
-// Returns the number of stashed keys (may exceed cap: the caller then falls back to the generic source scan);
-// all threads call.
-constexpr int NMS_STAGES = 3;
-__device__ __noinline__ int nms_stage_scan(const DevParams& P, const uint32_t* mat, const u64* rows, int nrows, u64 lo, u64 hi,
-                                           u64* out, int cap, unsigned char* stage, int* count) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = NMS_THREADS / 32;
+// Candidate scan of the NMS kernel through shared memory: the score-matrix rows of the `nrows` best rows (rows[i],
+// low word = row index) are fetched with ONE bulk copy per row (cp.async.bulk: no registers, no per-chunk copy
+// instructions, every row in flight at once — the DRAM latency is paid once per pass) into a staging buffer of
+// P.nms_stage_rows rows, and every entry inside the key window [lo, hi] lands in the stash `out` as a 64-bit key.
+// Rows are 16-byte multiples (C % 4 == 0). More rows than the buffer holds: further passes. Returns the number of
+// stashed keys (may exceed cap: the caller then falls back to the generic source scan); all threads call.
+// `bar` = the block's staging mbarrier (initialised with count 1), `phase` = its running parity.
+__device__ __noinline__ int nms_bulk_scan(const DevParams& P, const uint32_t* mat, const u64* rows, int nrows, u64 lo, u64 hi,
+                                          u64* out, int cap, unsigned char* stage, int* count, uint64_t* bar, uint32_t& phase) {
+    const int tid = threadIdx.x, lane = tid & 31;
     const int C = P.C, C4 = C >> 2, H = P.nms_stage_rows;
     const uint32_t row_bytes = (uint32_t)C * 4u;
     ScoreWindow win;
     win.set(lo, hi);
-    const int npass = (nrows + H - 1) / H;
     if (tid == 0) *count = 0;
-    auto issue = [&](int pass) {  // every thread copies the chunks it will later test (plus commit)
-        if (pass < npass) {
-            const int r0 = pass * H, n = min(H, nrows - r0);
-            unsigned char* dst = stage + (size_t)(pass % NMS_STAGES) * H * row_bytes;
-            if (lane < C4)
-                for (int i = warp; i < n; i += NW)
-                    cp_async16(dst + (size_t)i * row_bytes + lane * 16, mat + (size_t)(uint32_t)rows[r0 + i] * C + 4 * lane);
-        }
-        cp_async_commit();
-    };
 #ifdef YPP_PROFILE
     long long pt[3] = {0, 0, 0}, pt_t = clock64();
 #define YPP_ACC2(i) do { long long t2 = clock64(); pt[i] += t2 - pt_t; pt_t = t2; } while (0)
 #else
 #define YPP_ACC2(i) do { } while (0)
 #endif
-#pragma unroll
-    for (int s = 0; s < NMS_STAGES; ++s) issue(s);
-    YPP_ACC2(0);
-    for (int pass = 0; pass < npass; ++pass) {
-        const int r0 = pass * H, n = min(H, nrows - r0);
-        const unsigned char* src = stage + (size_t)(pass % NMS_STAGES) * H * row_bytes;
-        cp_async_wait_group<NMS_STAGES - 1>();  // this thread's copies of `pass` have landed; it reads only those
-        if (pass == 0) __syncthreads();         // (*count = 0 above)
+    int npass = 0;
+    for (int r0 = 0; r0 < nrows; r0 += H, ++npass) {
+        const int n = min(H, nrows - r0);
+        if (r0 > 0) fence_proxy_async();  // this thread's generic reads of the buffer -> the async-proxy refill
+        __syncthreads();                  // (first pass: publishes *count = 0)
+        // (complete_tx of a copy may precede the expect_tx: the phase cannot complete before thread 0 has arrived)
+        if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)n * row_bytes);
+        for (int i = tid; i < n; i += NMS_THREADS)
+            bulk_load_1d(stage + (size_t)i * row_bytes, mat + (size_t)(uint32_t)rows[r0 + i] * C, row_bytes, bar);
+        YPP_ACC2(0);
+        mbar_wait(bar, phase);
+        phase ^= 1u;
         YPP_ACC2(1);
-        // survivors of up to 8 rows are flushed together
-        for (int i0 = warp; i0 < n; i0 += NW * 8) {
+        // the buffer is n * C4 consecutive 16-byte groups: thread-contiguous, conflict-free reads; survivors of up to
+        // 8 groups per thread are flushed together (one warp scan + one shared-memory atomic per flush)
+        const uint4* st4 = reinterpret_cast<const uint4*>(stage);
+        const int ng = n * C4;
+        for (int base = 0; base < ng; base += NMS_THREADS * 8) {
             unsigned em = 0u;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                const int i = i0 + q * NW;
-                if (i < n && lane < C4) {
-                    const uint4 w = *reinterpret_cast<const uint4*>(src + (size_t)i * row_bytes + lane * 16);
-                    const uint32_t f0 = win.ends ? (uint32_t)rows[r0 + i] * (uint32_t)C + 4u * lane : 0u;
+                const int g = base + q * NMS_THREADS + tid;
+                if (g < ng) {
+                    const uint4 w = st4[g];
+                    uint32_t f0 = 0u;
+                    if (win.ends) {
+                        const int r = g / C4;
+                        f0 = (uint32_t)rows[r0 + r] * (uint32_t)C + 4u * (uint32_t)(g - r * C4);
+                    }
                     em |= win.test4(w, f0) << (q * 4);
                 }
             }
@@ -1725,20 +1727,18 @@ __device__ __noinline__ int nms_stage_scan(const DevParams& P, const uint32_t* m
                 int sp = 0;
                 if (lane == 31) sp = atomicAdd(count, incl);
                 sp = __shfl_sync(0xffffffffu, sp, 31) + incl - c;
+                // (the stash entry carries the position inside the row list for now: no division, no row lookup here)
                 while (em) {
                     const int pos = __ffs(em) - 1;
                     em &= em - 1;
-                    const int i = i0 + (pos >> 2) * NW, v = pos & 3;
-                    const uint32_t word = *reinterpret_cast<const uint32_t*>(src + (size_t)i * row_bytes + lane * 16 + v * 4);
-                    const uint32_t flat = (uint32_t)rows[r0 + i] * (uint32_t)C + 4u * lane + v;
-                    if (sp < cap) out[sp] = score_key(word, flat);
+                    const int e = 4 * (base + (pos >> 2) * NMS_THREADS + tid) + (pos & 3);
+                    const uint32_t word = reinterpret_cast<const uint32_t*>(stage)[e];
+                    if (sp < cap) out[sp] = score_key(word, (uint32_t)(r0 * C + e));
                     ++sp;
                 }
             }
         }
         YPP_ACC2(2);
-        issue(pass + NMS_STAGES);  // the same thread re-fills exactly the chunks it has just consumed
-        YPP_ACC2(0);
     }
 #ifdef YPP_PROFILE
     if (tid == 0 && blockIdx.x < 256) {
@@ -1748,16 +1748,256 @@ __device__ __noinline__ int nms_stage_scan(const DevParams& P, const uint32_t* m
         g_phase[1][blockIdx.x][15] = npass;
     }
 #endif
-    cp_async_wait_group<0>();
     __syncthreads();
-    return *count;
+    // position inside the row list -> flat candidate index row * C + class, one dense pass over the stash
+    const int total = *count;
+#pragma unroll 1
+    for (int i = tid; i < total && i < cap; i += NMS_THREADS) {
+        const u64 k = out[i];
+        const uint32_t e = (uint32_t)k, r = e / (uint32_t)C;
+        out[i] = (k & 0xFFFFFFFF00000000ull) | (u64)((uint32_t)rows[r] * (uint32_t)C + (e - r * (uint32_t)C));
+    }
+    __syncthreads();
+    return total;
+}
+
+// Greedy NMS of one chunk in the classes-are-independent regime (mmcv batched_nms, n >= split_thr: a kept box only
+// suppresses boxes of its own class): the classes are resolved IN PARALLEL instead of walking the chunk in score
+// order, and the chunk is never sorted as a whole. A candidate's fate depends only on the better-scored candidates of
+// its own class, so the keep flag of every candidate of the chunk is exact; only the kept ones are then sorted by key
+// (score desc, flat asc) and the first (cap - kept so far) of them appended to the kept list.
+//   1. class member lists (counting sort by class, unordered), then each candidate's position inside its class =
+//      number of members with a smaller key -> ordered lists;
+//   2. warp per class, lanes over the class's pairs (a < b in class order): IoU -> 64-bit mask `supby[b]` (bit a: the
+//      member at class position a would suppress b);
+//   3. candidates with an empty mask are kept (unless a box kept from an earlier chunk suppresses them); the
+//      undecided members of a class are walked in order by one thread with bit operations only;
+//   4. the kept candidates are compacted and sorted: (key, index) pairs in registers, one per thread.
+// key[0..m): the chunk's candidates in any order (the complete set of candidates inside a key window), m <= NMS_CH;
+// cx1..ccl: their (offset) boxes / areas / classes in the same order; kx1..knext/chead/kcl/kkey: kept list with
+// per-class chains, nk boxes so far. Returns the new number of kept boxes, or -1 — kept list untouched — when the
+// pass does not apply: a class with more than NMS_CLS_MAX candidates in the chunk, or more than NMS_THREADS kept
+// (the caller then sorts the chunk and runs the group-wise pass). The loops are deliberately not unrolled: the
+// per-image kernels run their code about once and are bound by instruction issue and fetch.
+constexpr int NMS_CLS_MAX = 64;              // candidates of one class (one mask word)
+constexpr int NMS_CLS_LABELS = 128;          // classes the parallel pass has scratch for
+struct NmsClsSmem {
+    int ccnt[NMS_CLS_LABELS];
+    int coff[NMS_CLS_LABELS + 1];
+    int over, nkept;
+    unsigned short ulist[NMS_CH];                     // members of each class, unordered
+    unsigned short clist[NMS_CH];                     // members of each class, in score order
+    unsigned char cpos[NMS_CH];                       // position of candidate i inside its class
+    unsigned char kflag[NMS_CH];                      // result: kept
+    unsigned keptm[NMS_CLS_LABELS][2], unc[NMS_CLS_LABELS][2];  // per class: members kept for sure / undecided (bit = position)
+    unsigned short spay[NMS_THREADS], tpay[NMS_THREADS];       // kept candidates: index (payload of the sort) + scratch
+};
+static_assert(sizeof(NmsClsSmem) <= NMS_KCAP * 8, "lives in the row-list buffer, which is free between two scans");
+__device__ __noinline__ bool nms_iou_gt(const float* x1, const float* y1, const float* x2, const float* y2, const float* ar, int i,
+                                        const Box& bj, float thr, float foff) {
+    Box bi;
+    bi.x1 = x1[i];
+    bi.y1 = y1[i];
+    bi.x2 = x2[i];
+    bi.y2 = y2[i];
+    bi.area = ar[i];
+    return iou_gt(bi, bj, thr, foff);
+}
+__device__ __noinline__ int nms_resolve_classes(int m, int nlab, int nk, int cap, float thr, float foff, const u64* key,
+                                                const float* cx1, const float* cy1, const float* cx2, const float* cy2,
+                                                const float* car, const int* ccl, float* kx1, float* ky1, float* kx2, float* ky2,
+                                                float* kar, int* kcl, u64* kkey, int* knext, int* chead, NmsClsSmem& Q,
+                                                u64* scratch /* 2 * NMS_CH keys */) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    u64* supby = scratch;                 // [NMS_CH]
+    u64* skey = scratch + NMS_CH;         // [NMS_THREADS] kept keys
+    u64* tkey = skey + NMS_THREADS;       // [NMS_THREADS] scratch of the sort
+    static_assert(2 * NMS_THREADS <= NMS_CH, "scratch layout");
+    YPP_SUB(8);
+    // 1a. class sizes
+    if (tid < nlab) Q.ccnt[tid] = 0;
+    if (tid == 0) {
+        Q.over = 0;
+        Q.nkept = 0;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int i = tid; i < m; i += NMS_THREADS) atomicAdd(&Q.ccnt[ccl[i]], 1);
+    __syncthreads();
+    if (tid < 32) {
+        // exclusive scan over the classes (each lane owns a contiguous run), largest class
+        const int per = (nlab + 31) / 32, c0 = lane * per, c1 = min(nlab, c0 + per);
+        int sum = 0, mx = 0;
+#pragma unroll 1
+        for (int c = c0; c < c1; ++c) {
+            const int v = Q.ccnt[c];
+            sum += v;
+            mx = v > mx ? v : mx;
+        }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int run = incl - sum;
+#pragma unroll 1
+        for (int c = c0; c < c1; ++c) {
+            const int v = Q.ccnt[c];
+            Q.coff[c] = run;
+            Q.ccnt[c] = 0;  // becomes the fill cursor
+            run += v;
+        }
+        if (lane == 31) Q.coff[nlab] = incl;
+        if (__reduce_max_sync(0xffffffffu, mx) > NMS_CLS_MAX && lane == 0) Q.over = 1;
+    }
+    __syncthreads();
+    YPP_SUB(9);
+    if (Q.over) return -1;
+    // 1b. member lists (unordered)
+#pragma unroll 1
+    for (int i = tid; i < m; i += NMS_THREADS) {
+        const int c = ccl[i];
+        Q.ulist[Q.coff[c] + atomicAdd(&Q.ccnt[c], 1)] = (unsigned short)i;
+    }
+    if (tid < 2 * nlab) {
+        (&Q.keptm[0][0])[tid] = 0u;
+        (&Q.unc[0][0])[tid] = 0u;
+    }
+    __syncthreads();
+    YPP_SUB(10);
+    // 1c. position inside the class = members with a smaller key (keys are unique) -> ordered lists
+#pragma unroll 1
+    for (int i = tid; i < m; i += NMS_THREADS) {
+        const int c = ccl[i], o0 = Q.coff[c], n = Q.coff[c + 1] - o0;
+        const u64 mine = key[i];
+        int p = 0;
+#pragma unroll 1
+        for (int t = 0; t < n; ++t) p += key[Q.ulist[o0 + t]] < mine ? 1 : 0;
+        Q.cpos[i] = (unsigned char)p;
+        Q.clist[o0 + p] = (unsigned short)i;
+        supby[i] = 0ull;
+    }
+    __syncthreads();
+    YPP_SUB(11);
+    // 2. suppression masks: warp per class, lanes over the class's pairs, so the work is balanced whatever the
+    // class sizes are
+    uint32_t* sup32 = reinterpret_cast<uint32_t*>(supby);
+#pragma unroll 1
+    for (int c = tid >> 5; c < nlab; c += NMS_THREADS / 32) {
+        const int o0 = Q.coff[c], n = Q.coff[c + 1] - o0, npairs = (n * (n - 1)) >> 1;
+#pragma unroll 1
+        for (int e = lane; e < npairs; e += 32) {
+            int pb = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)e)) * 0.5f);  // e = pb (pb - 1) / 2 + pa, pa < pb
+            while (((pb * (pb - 1)) >> 1) > e) --pb;
+            while ((((pb + 1) * pb) >> 1) <= e) ++pb;
+            const int pa = e - ((pb * (pb - 1)) >> 1);
+            const int i = (int)Q.clist[o0 + pa], j = (int)Q.clist[o0 + pb];
+            Box bj;
+            bj.x1 = cx1[j];
+            bj.y1 = cy1[j];
+            bj.x2 = cx2[j];
+            bj.y2 = cy2[j];
+            bj.area = car[j];
+            if (nms_iou_gt(cx1, cy1, cx2, cy2, car, i, bj, thr, foff)) atomicOr(&sup32[2 * j + (pa >> 5)], 1u << (pa & 31));
+        }
+    }
+    __syncthreads();
+    YPP_SUB(12);
+    // 3a. candidates nobody can suppress are kept (if alive), the rest wait for their class's pass
+#pragma unroll 1
+    for (int j = tid; j < m; j += NMS_THREADS) {
+        const int c = ccl[j], p = (int)Q.cpos[j];
+        bool dead = false;
+        if (nk > 0) {
+            Box bj;
+            bj.x1 = cx1[j];
+            bj.y1 = cy1[j];
+            bj.x2 = cx2[j];
+            bj.y2 = cy2[j];
+            bj.area = car[j];
+#pragma unroll 1
+            for (int kk = chead[c]; kk >= 0 && !dead; kk = knext[kk]) dead = nms_iou_gt(kx1, ky1, kx2, ky2, kar, kk, bj, thr, foff);
+        }
+        const bool sure = !dead && supby[j] == 0ull;
+        Q.kflag[j] = sure ? 1 : 0;
+        if (!dead) atomicOr(sure ? &Q.keptm[c][p >> 5] : &Q.unc[c][p >> 5], 1u << (p & 31));
+    }
+    __syncthreads();
+    // 3b. greedy pass per class over the undecided members, in score order: bit operations only
+    if (tid < nlab) {
+        u64 todo = ((u64)Q.unc[tid][1] << 32) | (u64)Q.unc[tid][0];
+        if (todo) {
+            const int o0 = Q.coff[tid];
+            u64 kept = ((u64)Q.keptm[tid][1] << 32) | (u64)Q.keptm[tid][0];
+#pragma unroll 1
+            while (todo) {
+                const int p = __ffsll((long long)todo) - 1;
+                todo &= todo - 1ull;
+                const int j = (int)Q.clist[o0 + p];
+                if ((supby[j] & kept) == 0ull) {
+                    kept |= 1ull << p;
+                    Q.kflag[j] = 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    YPP_SUB(13);
+    // 4. kept candidates -> (key, index) pairs, compacted (any order), sorted by key
+#pragma unroll 1
+    for (int i0 = 0; i0 < m; i0 += NMS_THREADS) {  // (uniform trip count)
+        const int i = i0 + tid;
+        const bool kf = i < m && Q.kflag[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, kf);
+        int base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&Q.nkept, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (kf) {
+            const int t = base + __popc(bal & ((1u << lane) - 1u));
+            if (t < NMS_THREADS) {
+                skey[t] = key[i];
+                Q.spay[t] = (unsigned short)i;
+            }
+        }
+    }
+    __syncthreads();
+    const int K = Q.nkept;
+    if (K > NMS_THREADS) return -1;
+    const int p2 = next_pow2(K < 32 ? 32 : K);
+    if (tid >= K && tid < p2) {
+        skey[tid] = ~0ull;
+        Q.spay[tid] = 0;
+    }
+    __syncthreads();
+    YPP_SUB(14);
+    bitonic_sort_kv(skey, Q.spay, tkey, Q.tpay, p2);
+    YPP_SUB(15);
+    // the first (cap - nk) of them join the kept list, in score order
+    const int take = K < cap - nk ? K : cap - nk;
+    if (tid < take) {
+        const int gj = (int)Q.spay[tid], kidx = nk + tid;
+        kx1[kidx] = cx1[gj];
+        ky1[kidx] = cy1[gj];
+        kx2[kidx] = cx2[gj];
+        ky2[kidx] = cy2[gj];
+        kar[kidx] = car[gj];
+        kcl[kidx] = ccl[gj];
+        kkey[kidx] = skey[tid];
+        knext[kidx] = atomicExch(&chead[ccl[gj]], kidx);  // class chain (order irrelevant)
+    }
+    __syncthreads();
+    YPP_SUB(16);
+    return nk + take;
 }
 
 // bbox2result (mmdet/core/bbox/transforms.py:110-116): `bboxes[labels == i, :]` for every class, i.e. a STABLE
-// counting sort of the <= max_per_img output rows by label. Done on the device so that the host gets one block it
-// can slice into num_classes views. All threads of the NMS block call; `cnt` = C ints of scratch.
-__device__ __noinline__ void nms_group_by_label(const DevParams& P, int b, int nk, const int* kcl, const u64* kkey, int* cnt,
-                                                const float4* row_box) {
+// counting sort of the <= max_per_img output rows by label, done on the device so that the host gets one block it
+// can slice into num_classes views. This part: per-class counts of the nk output rows -> exclusive offsets, written
+// to o_cls_offsets[b][0..C] and left in cnt[0..C) (C ints of scratch). The rows themselves are placed by the output
+// loop: position = offset of the class + number of kept boxes of that class with a smaller output index, counted
+// along the class chain of the kept list. All threads of the NMS block call.
+__device__ __noinline__ void nms_label_offsets(const DevParams& P, int b, int nk, const int* kcl, int* cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, C = P.C;
     for (int c = tid; c < C; c += NMS_THREADS) cnt[c] = 0;
     __syncthreads();
@@ -1785,29 +2025,6 @@ __device__ __noinline__ void nms_group_by_label(const DevParams& P, int b, int n
         if (lane == 31) offs[C] = incl;  // == nk
     }
     __syncthreads();
-    // stable placement, one chunk of NMS_THREADS rows at a time: position = running base of the class + rank among
-    // the chunk's earlier rows of that class; then the bases advance by the chunk's class counts
-    for (int s0 = 0; s0 < nk; s0 += NMS_THREADS) {
-        const int i = s0 + tid;
-        int c = -1;
-        if (i < nk) {
-            c = kcl[i];
-            int pos = cnt[c];
-            for (int j = s0; j < i; ++j) pos += (kcl[j] == c) ? 1 : 0;
-            const u64 key = kkey[i];
-            const uint32_t flat = key_flat(key);
-            const float4 bx = row_box[P.boxes_per_class ? flat : flat / (uint32_t)C];
-            float* d = P.o_cls_dets + ((size_t)b * P.out_cap + pos) * 5;
-            d[0] = bx.x;
-            d[1] = bx.y;
-            d[2] = bx.z;
-            d[3] = bx.w;
-            d[4] = key_score(key);
-        }
-        __syncthreads();
-        if (c >= 0) atomicAdd(&cnt[c], 1);
-        __syncthreads();
-    }
 }
 
 // Upper key bound of a chunk of the NMS candidate stream: the W-th best ROW maximum is a lower bound of the W-th
@@ -1911,7 +2128,8 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     float* kar = ky2 + cap;
     int* kcl = reinterpret_cast<int*>(kar + cap);                  // [cap]
     int* knext = kcl + cap;                                        // [cap] previous kept box of the same class
-    u64* rowkeys = reinterpret_cast<u64*>(nms_smem + P.nms_rowkeys_off);  // [NMS_KCAP] best rows, sorted
+    u64* rowkeys = reinterpret_cast<u64*>(nms_smem + P.nms_rowkeys_off);  // [NMS_KCAP] rows of the candidate scan
+    NmsClsSmem& Q = *reinterpret_cast<NmsClsSmem*>(rowkeys);              // (scratch of the class-parallel pass, between scans)
 
     const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = P.C;
@@ -1927,7 +2145,11 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
 #ifdef YPP_PROFILE
     if (threadIdx.x == 0) { S.prof_kernel = 1; S.prof_call = 0; }
 #endif
+    uint64_t* stage_bar = reinterpret_cast<uint64_t*>(&S.bar);  // bulk copies of the candidate scan
+    uint32_t stage_phase = 0u;
     if (tid == 0) {
+        mbar_init(stage_bar, 1);
+        fence_mbar_init();
         s_nk = 0;
         s_sup = 0ull;
         s_red[0] = 0u;
@@ -1979,7 +2201,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     if (tid == 0 && P.o_ncand) P.o_ncand[b] = ntot;
     if (ntot == 0) {
         if (tid == 0) P.o_count[b] = 0;
-        if (P.o_cls_offsets && !generic) nms_group_by_label(P, b, 0, kcl, kkey, chead, row_box);  // all groups empty
+        if (P.o_cls_offsets && !generic) nms_label_offsets(P, b, 0, kcl, reinterpret_cast<int*>(ktmp));  // all groups empty
         return;
     }
     const u64 gmin = (u64)(~s_red[0]) << 32;
@@ -1991,7 +2213,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         const u64 lim = (u64)(~f2ord(P.nms_score_thr)) << 32;
         if (lim == 0ull || lim - 1ull < gmin) {
             if (tid == 0) P.o_count[b] = 0;
-            if (P.o_cls_offsets && !generic) nms_group_by_label(P, b, 0, kcl, kkey, chead, row_box);
+            if (P.o_cls_offsets && !generic) nms_label_offsets(P, b, 0, kcl, reinterpret_cast<int*>(ktmp));
             return;
         }
         gmax = gmax < lim - 1ull ? gmax : lim - 1ull;
@@ -2015,6 +2237,15 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     // the first chunk only needs a little more than `cap` candidates; later chunks (heavy suppression) are full
     int chunk = cap + (cap >> 2) + 64;
     chunk = chunk < NMS_CH ? chunk : NMS_CH;
+    // ... and its rows should fit the staging buffer in one pass (the pivot bin adds a few rows beyond `chunk`)
+    if (P.nms_stage_rows - 24 >= cap + 32 && chunk > P.nms_stage_rows - 24) chunk = P.nms_stage_rows - 24;
+    // classes-in-parallel pass: available when the classes are independent and the scratch covers the label range. It
+    // takes a whole stash of at most NMS_THREADS candidates (one per thread). The stash of a scan that must reach
+    // rank W holds every entry of the W best rows above the W-th best row maximum — typically ~2 W candidates — so the
+    // first chunk then asks for fewer rows; a stash that still comes out larger goes the sorted, group-wise way.
+    const bool cls_parallel = per_class && !generic && nlab <= NMS_CLS_LABELS && P.nms_stage_rows > 0;
+    const int chunk_sorted = chunk;
+    if (cls_parallel && cap >= 64 && cap <= (NMS_THREADS * 3) / 4) chunk = (cap * 3) / 4;
     YPP_PHASE(1, b, 2);
 #ifdef YPP_PROFILE
     int prof_chunks = 0, prof_groups = 0;
@@ -2022,36 +2253,89 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
 #endif
     while (processed < ntot && s_nk < cap) {
         const int want = min(chunk, ntot - processed);
+        const int want_sorted = processed == 0 ? min(chunk_sorted, ntot) : want;  // (the stash usually holds more than `want`)
         chunk = NMS_CH;
         const int wc = processed + want;  // cumulative rank this chunk must reach
         u64 hi = gmax;
         int nrows = -1;
         if (!generic && nonneg) {
             uint32_t t_ord = 0u;
+            YPP_SUB(0);
             nrows = nms_pick_rows(P, b, wc, s_red[0], ~s_red[1], rowkeys, S, &t_ord);
+            YPP_SUB(1);
             if (nrows >= 0) {
                 const u64 hi_t = ((u64)(~t_ord) << 32) | 0xFFFFFFFFull;
                 hi = hi_t < gmax ? hi_t : gmax;
             }
         }
+        // boxes of the chunk's candidates keys[0..n): boxes + idxs.to(boxes) * (max_coordinate + 1), areas, classes
+        auto stage_boxes = [&](int n) {
+#pragma unroll 1
+            for (int i = tid; i < n; i += NMS_THREADS) {
+                const uint32_t flat = key_flat(keys[i]);
+                const int r = (int)(flat / (uint32_t)C);
+                const int c = generic ? (P.g_labels ? (int)P.g_labels[flat] : 0) : (int)(flat - (uint32_t)r * (uint32_t)C);
+                const float4 bx = row_box[P.boxes_per_class ? flat : (uint32_t)r];
+                float x1 = bx.x, y1 = bx.y, x2 = bx.z, y2 = bx.w;
+                if (use_off) {
+                    const float off = fmul((float)c, mp1);
+                    x1 = fadd(x1, off);
+                    y1 = fadd(y1, off);
+                    x2 = fadd(x2, off);
+                    y2 = fadd(y2, off);
+                }
+                cx1[i] = x1;
+                cy1[i] = y1;
+                cx2[i] = x2;
+                cy2[i] = y2;
+                car[i] = box_area(x1, y1, x2, y2, foff);
+                ccl[i] = c;
+            }
+            __syncthreads();
+        };
         int got;
         if (nrows >= 0) {
             // only the listed rows can hold one of the wc best candidates: scan just their matrix rows
-            RowListSource rl;
-            rl.m = mat;
-            rl.rows = rowkeys;
-            rl.nrows = nrows;
-            rl.C = C;
-            rl.nsub = (C + 127) / 128;
-            rl.vec4 = ((C & 3) == 0);
-            rl.win.set(lo, hi);
             int staged = -1;
             if (P.nms_stage_rows > 0)
-                staged = nms_stage_scan(P, mat, rowkeys, nrows, lo, hi, keys, NMS_KCAP, nms_smem + P.nms_stage_off, &s_stash);
+                staged = nms_bulk_scan(P, mat, rowkeys, nrows, lo, hi, keys, NMS_KCAP, nms_smem + P.nms_stage_off, &s_stash,
+                                       stage_bar, stage_phase);
+            YPP_SUB(2);
+            if (cls_parallel && staged > 0 && staged <= NMS_THREADS) {
+                // the stash IS the complete set of candidates inside the window [lo, hi] — a prefix of the global order
+                // that reaches rank wc: resolve its classes in parallel, unsorted
+                stage_boxes(staged);
+                YPP_SUB(3);
+                const int nk1 = nms_resolve_classes(staged, nlab, s_nk, cap, thr, foff, keys, cx1, cy1, cx2, cy2, car, ccl, kx1, ky1,
+                                                    kx2, ky2, kar, kcl, kkey, knext, chead, Q, ktmp);
+                if (nk1 >= 0) {
+#ifdef YPP_PROFILE
+                    if (prof_chunks == 0) {
+                        YPP_PHASE(1, b, 3);
+                        YPP_PHASE(1, b, 4);
+                    }
+                    ++prof_chunks;
+#endif
+                    if (tid == 0) s_nk = nk1;
+                    processed += staged;
+                    if (hi == ~0ull) processed = ntot;
+                    lo = hi + 1ull;
+                    __syncthreads();
+                    continue;
+                }
+            }
             if (staged >= 0 && staged <= NMS_KCAP) {
                 StashSource none;
-                got = select_sorted_prefix(none, lo, hi, want, keys, ktmp, NMS_KCAP, S, staged);
+                got = select_sorted_prefix(none, lo, hi, want_sorted, keys, ktmp, NMS_KCAP, S, staged);
             } else {
+                RowListSource rl;
+                rl.m = mat;
+                rl.rows = rowkeys;
+                rl.nrows = nrows;
+                rl.C = C;
+                rl.nsub = (C + 127) / 128;
+                rl.vec4 = ((C & 3) == 0);
+                rl.win.set(lo, hi);
                 __syncthreads();
                 got = select_sorted_prefix(rl, lo, hi, want, keys, ktmp, NMS_KCAP, S);
             }
@@ -2065,27 +2349,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         ++prof_chunks;
 #endif
         if (m == 0) break;
-        for (int i = tid; i < m; i += NMS_THREADS) {
-            const uint32_t flat = key_flat(keys[i]);
-            const int r = (int)(flat / (uint32_t)C);
-            const int c = generic ? (P.g_labels ? (int)P.g_labels[flat] : 0) : (int)(flat - (uint32_t)r * (uint32_t)C);
-            const float4 bx = row_box[P.boxes_per_class ? flat : (uint32_t)r];
-            float x1 = bx.x, y1 = bx.y, x2 = bx.z, y2 = bx.w;
-            if (use_off) {  // boxes + idxs.to(boxes) * (max_coordinate + 1)
-                const float off = fmul((float)c, mp1);
-                x1 = fadd(x1, off);
-                y1 = fadd(y1, off);
-                x2 = fadd(x2, off);
-                y2 = fadd(y2, off);
-            }
-            cx1[i] = x1;
-            cy1[i] = y1;
-            cx2[i] = x2;
-            cy2[i] = y2;
-            car[i] = box_area(x1, y1, x2, y2, foff);
-            ccl[i] = c;
-        }
-        __syncthreads();
+        stage_boxes(m);
 #ifdef YPP_PROFILE
         if (prof_chunks == 1) YPP_PHASE(1, b, 4);
 #endif
@@ -2255,28 +2519,42 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         nk = P.out_cap;
         if (tid == 0 && P.o_status) atomicMax(P.o_status, 3);  // YOLOPP_E_OVERFLOW
     }
+    const bool grouped = P.o_cls_offsets && !generic;
+    int* gcnt = reinterpret_cast<int*>(ktmp);  // (the select scratch is free by now: C <= 4096 ints)
+    if (grouped) {
+        __syncthreads();
+        nms_label_offsets(P, b, nk, kcl, gcnt);
+    }
     for (int i = tid; i < nk; i += NMS_THREADS) {
         const u64 key = kkey[i];
         const uint32_t flat = key_flat(key);
         const int r = (int)(flat / (uint32_t)C);
         const int c = generic ? kcl[i] : (int)(flat - (uint32_t)r * (uint32_t)C);
         const float4 bx = row_box[P.boxes_per_class ? flat : (uint32_t)r];
+        const float sc = key_score(key);
         float* d = P.o_dets + ((size_t)b * P.out_cap + i) * 5;
         d[0] = bx.x;
         d[1] = bx.y;
         d[2] = bx.z;
         d[3] = bx.w;
-        d[4] = key_score(key);
+        d[4] = sc;
         if (P.o_labels) P.o_labels[(size_t)b * P.out_cap + i] = (long long)c;
         if (P.o_keep) P.o_keep[(size_t)b * P.out_cap + i] = (long long)flat;
         if (P.o_anchors) P.o_anchors[(size_t)b * P.out_cap + i] = P.row_anchor[(size_t)b * P.R + r];
         if (P.o_rows) P.o_rows[(size_t)b * P.out_cap + i] = r;
+        if (grouped) {
+            // stable position inside the label's group: kept boxes of the class with a smaller output index
+            int pos = gcnt[c];
+            for (int k = chead[c]; k >= 0; k = knext[k]) pos += (k < i) ? 1 : 0;
+            float* g = P.o_cls_dets + ((size_t)b * P.out_cap + pos) * 5;
+            g[0] = bx.x;
+            g[1] = bx.y;
+            g[2] = bx.z;
+            g[3] = bx.w;
+            g[4] = sc;
+        }
     }
     if (tid == 0) P.o_count[b] = nk;
-    if (P.o_cls_offsets && !generic) {
-        __syncthreads();
-        nms_group_by_label(P, b, nk, kcl, kkey, chead, row_box);
-    }
     YPP_PHASE(1, b, 6);
 }
 

@@ -44,6 +44,16 @@ stats('chunks', nms[:, 7]); stats('groups', nms[:, 8]); stats('candidates', nms[
 per_group = (nms[:, 5] - nms[:, 4]) / np.maximum(nms[:, 8], 1)
 stats('cycles per group', per_group)
 stats('  A + B1 per group', nms[:, 10] / np.maximum(nms[:, 8], 1)); stats('  B2 + append per group', nms[:, 11] / np.maximum(nms[:, 8], 1))
+sub = np.zeros((256, 32), np.int64)
+if hasattr(lib, 'yolopp_sub_read'):
+    lib.yolopp_sub_read.argtypes = [ctypes.c_void_p]
+    lib.yolopp_sub_read(sub.ctypes.data_as(ctypes.c_void_p))
+    sub = sub[:B]
+    print('nms first chunk, finer stamps (cycles, median):')
+    for a, z, n in ((0, 1, 'pick rows'), (1, 2, 'bulk scan'), (2, 3, 'stage boxes'), (8, 9, 'classes: sizes + offsets'),
+                    (9, 10, 'classes: member lists'), (10, 11, 'classes: rank inside class'), (11, 12, 'classes: pair masks'),
+                    (12, 13, 'classes: decide'), (13, 14, 'kept: compact'), (14, 15, 'kept: sort'), (15, 16, 'kept: append')):
+        if sub[:, z].max() > 0 and sub[:, a].max() > 0: print('    %-36s %7.0f' % (n, np.median(sub[:, z] - sub[:, a])))
 ssp = np.zeros((2, 64, 4, 10), np.int64)
 lib.yolopp_ssp_read.argtypes = [ctypes.c_void_p]
 lib.yolopp_ssp_read(ssp.ctypes.data_as(ctypes.c_void_p))
