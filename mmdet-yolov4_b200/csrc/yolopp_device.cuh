@@ -135,9 +135,12 @@ __device__ u64 radix_select(Fetch fetch, int n_slots, bool has_lo, u64 lo, int m
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
     u64 prefix = 0, pmask = 0;
     int need = m;
+#pragma unroll 1
     for (int shift = 56; shift >= 0; shift -= 8) {
+#pragma unroll 1
         for (int i = tid; i < 256; i += nth) S.hist[i] = 0;
         __syncthreads();
+#pragma unroll 1
         for (int base = 0; base < n_slots; base += nth) {
             int i = base + tid;
             u64 key = 0;
@@ -194,6 +197,7 @@ __device__ int gather_le(Fetch fetch, int n_slots, bool has_lo, u64 lo, u64 T, u
     const int tid = threadIdx.x, nth = blockDim.x, lane = tid & 31;
     if (tid == 0) S.count = 0;
     __syncthreads();
+#pragma unroll 1
     for (int base = 0; base < n_slots; base += nth) {
         int i = base + tid;
         u64 key = 0;
@@ -217,9 +221,12 @@ __device__ int gather_le(Fetch fetch, int n_slots, bool has_lo, u64 lo, u64 T, u
 // In-place ascending bitonic sort of s[0..p2), p2 a power of two. All threads of the block call it.
 __device__ __forceinline__ void bitonic_sort(u64* s, int p2) {
     const int tid = threadIdx.x, nth = blockDim.x;
+#pragma unroll 1
     for (int size = 2; size <= p2; size <<= 1) {
+#pragma unroll 1
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             __syncthreads();
+#pragma unroll 1
             for (int i = tid; i < (p2 >> 1); i += nth) {
                 int pos = 2 * i - (i & (stride - 1));
                 int j = pos + stride;
@@ -291,6 +298,7 @@ __device__ __noinline__ void bitonic_sort_kv(u64* __restrict__ key, unsigned sho
 
 __device__ __forceinline__ int next_pow2(int v) {
     int p = 1;
+#pragma unroll 1
     while (p < v) p <<= 1;
     return p;
 }
@@ -383,6 +391,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
     }
     const u64 base = lo_incl >> shift;
     YPP_SSP(0);
+#pragma unroll 1
     for (int i = tid; i < TS_BINS; i += nth) S.hist[i] = 0;
     if (tid == 0) S.count = prefilled < 0 ? 0 : prefilled;  // prefilled: the caller already put the eligible keys in `out`
     __syncthreads();
@@ -399,6 +408,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
 #else
 #define YPP_ACC(i) do { } while (0)
 #endif
+#pragma unroll 1
     for (int b0 = 0; b0 < n_groups && prefilled < 0; b0 += nth * U) {
         Raw raw[U];
 #pragma unroll
@@ -426,6 +436,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
             if (lane == 31) sp = atomicAdd(&S.count, incl);
             sp = __shfl_sync(0xffffffffu, sp, 31) + incl - c;
             YPP_ACC(1);
+#pragma unroll 1
             while (emask) {
                 const int pos = __ffs(emask) - 1;
                 emask &= emask - 1;
@@ -447,9 +458,11 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
     const int n_stash = S.count;
     const bool stash_ok = n_stash <= cap;
     if (stash_ok) {
+#pragma unroll 1
         for (int i = tid; i < n_stash; i += nth) atomicAdd(&S.hist[(int)((out[i] >> shift) - base)], 1);
     } else {
         // too many eligible keys for the stash (no tight bound was available): histogram straight from the source
+#pragma unroll 1
         for (int b0 = 0; b0 < n_groups; b0 += nth * U) {
             Raw raw[U];
 #pragma unroll
@@ -463,6 +476,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
                 const int gi = b0 + q * nth + tid;
                 if (gi < n_groups) emask |= src.exact(raw[q], gi, lo_incl, hi_incl) << (q * V);
             }
+#pragma unroll 1
             while (emask) {
                 const int pos = __ffs(emask) - 1;
                 emask &= emask - 1;
@@ -491,6 +505,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
     if (tid == 0) S.kb = -1;
     __syncthreads();
     int woff = 0, total = 0;
+#pragma unroll 1
     for (int w = 0; w < nw; ++w) {
         int v = S.wsum[w];
         if (w < warp) woff += v;
@@ -522,6 +537,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
         // scatter: hist[bucket] is the running cursor of the bucket, keys land grouped by bucket in tmp
         if (stash_ok) {
             // every survivor of the first pass sits in `out`: no second trip to global memory
+#pragma unroll 1
             for (int i = tid; i < n_stash; i += nth) {
                 const u64 k = out[i];
                 const int bk = (int)((k >> shift) - base);
@@ -529,6 +545,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
             }
             __syncthreads();  // `out` is rewritten by the ranking step below
         } else {
+#pragma unroll 1
             for (int b0 = 0; b0 < n_groups; b0 += nth * U) {
                 Raw raw[U];
 #pragma unroll
@@ -542,6 +559,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
                     const int gi = b0 + q * nth + tid;
                     if (gi < n_groups) emask |= src.exact(raw[q], gi, lo_incl, hi_incl) << (q * V);
                 }
+#pragma unroll 1
                 while (emask) {
                     const int pos = __ffs(emask) - 1;
                     emask &= emask - 1;
@@ -555,11 +573,13 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
         YPP_SSP(5);
         cnt = above + bsize;
         // rank inside the bucket: after the scatter hist[bk] is the END of bucket bk, hist[bk-1] its start
+#pragma unroll 1
         for (int pos = tid; pos < cnt; pos += nth) {
             const u64 key = tmp[pos];
             const int bk = (int)((key >> shift) - base);
             const int st = bk ? S.hist[bk - 1] : 0, en = S.hist[bk];
             int rnk = st;
+#pragma unroll 1
             for (int q = st; q < en; ++q) rnk += (tmp[q] < key) ? 1 : 0;
             out[rnk] = key;
         }
@@ -577,6 +597,7 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
         u64 T = radix_select(f1, n_groups * Source::V, has_lo, lo_incl - 1, m, S.rs);
         cnt = gather_le(f1, n_groups * Source::V, has_lo, lo_incl - 1, T, out, cap, S.rs);
         const int p2 = next_pow2(cnt);
+#pragma unroll 1
         for (int i = cnt + tid; i < p2; i += nth) out[i] = ~0ull;
         __syncthreads();
         bitonic_sort(out, p2);

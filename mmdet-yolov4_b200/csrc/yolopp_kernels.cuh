@@ -278,12 +278,14 @@ struct RowListSource {
 // ------------------------------------------------------------------------------------------------
 // (level, anchor, position) of plane-major slot m of a segment; false for the alignment padding between levels
 __device__ __forceinline__ bool seg_slot(const DevParams& P, const SegDev& sg, int m, int& l, int& a, int& hw) {
+#pragma unroll 1
     for (int li = sg.num_levels - 1; li >= 0; --li) {
         const LevelDev& lv = P.lv[sg.first_level + li];
         if (m >= lv.m_off) {
             int e = m - lv.m_off;
             if (e >= P.A * lv.HW) return false;
             int aa = 0;
+#pragma unroll 1
             while (e >= lv.HW) {
                 e -= lv.HW;
                 ++aa;
@@ -308,9 +310,11 @@ __device__ __forceinline__ const float* obj_addr(const DevParams& P, const Level
 __device__ __forceinline__ void select_write(const DevParams& P, const SegDev& sg, int b, const u64* sel, int k, int row0 = 0) {
     uint32_t* rank = P.rank + (size_t)b * P.M_pad;
     const int first = sg.first_level, nl = sg.num_levels, A = P.A;
+#pragma unroll 1
     for (int i = threadIdx.x; i < k; i += SEL_THREADS) {
         const int n = (int)(uint32_t)sel[i];
         int l = first;
+#pragma unroll 1
         for (int q = nl - 1; q >= 0; --q)
             if (n >= P.lv[first + q].n_off) {
                 l = first + q;
@@ -354,6 +358,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     const bool staged = stride == 1;
     int ns = staged ? M : 0;  // staged slots (streamed: counted while the sample is issued)
     uint32_t* rank = P.rank + (size_t)b * P.M_pad + sg.m_begin;
+#pragma unroll 1
     for (int i = tid; i < TS_BINS; i += SEL_THREADS) S.hist[i] = 0;
     if (tid == 0) S.count = 0;
     uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
@@ -364,6 +369,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
             mbar_init(bar, 1);
             fence_mbar_init();
             uint32_t bulk_bytes = 0;
+#pragma unroll 1
             for (int li = 0; li < sg.num_levels; ++li) {
                 const LevelDev& lv = P.lv[sg.first_level + li];
                 if (!P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && (((lv.m_off - sg.m_begin) & 3) == 0))
@@ -372,6 +378,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
             mbar_arrive_expect_tx(bar, bulk_bytes);
         }
         __syncthreads();
+#pragma unroll 1
         for (int li = 0; li < sg.num_levels; ++li) {
             const LevelDev& lv = P.lv[sg.first_level + li];
             const float* lbase = lv.ptr + (size_t)b * P.A * P.NA * lv.HW;
@@ -379,11 +386,14 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
             const bool bulk = !P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && ((s0 & 3) == 0);
             if (bulk) {
                 if (warp == 0)
+#pragma unroll 1
                     for (int a = lane; a < P.A; a += 32)
                         bulk_load_1d(ox + s0 + a * lv.HW, lbase + ((size_t)a * P.NA + 4) * lv.HW, (uint32_t)lv.HW * 4u, bar);
             } else {
+#pragma unroll 1
                 for (int e = tid; e < AHW; e += SEL_THREADS) {
                     int a = 0, hw = e;
+#pragma unroll 1
                     while (hw >= lv.HW) {
                         hw -= lv.HW;
                         ++a;
@@ -401,17 +411,21 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
         // sample 1 in `stride` logits of every plane: four consecutive logits every 4 * stride (16-byte copies) where
         // the plane is 16-byte aligned, single logits every `stride` otherwise. `ns` = samples staged.
         ns = 0;
+#pragma unroll 1
         for (int li = 0; li < sg.num_levels; ++li) {
             const LevelDev& lv = P.lv[sg.first_level + li];
             const bool vec = !P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0);
+#pragma unroll 1
             for (int a = 0; a < P.A; ++a) {
                 if (vec) {
                     const float* plane = obj_addr(P, lv, b, a, 0);
                     const int n4 = lv.HW / (4 * stride);
+#pragma unroll 1
                     for (int i = tid; i < n4; i += SEL_THREADS) cp_async16(ox + ns + 4 * i, plane + (size_t)4 * stride * i);
                     ns += 4 * n4;
                 } else {
                     const int n1 = lv.HW / stride, n1p = (n1 + 3) & ~3;  // (running offset stays 16-byte aligned)
+#pragma unroll 1
                     for (int i = tid; i < n1; i += SEL_THREADS) cp_async4(ox + ns + i, obj_addr(P, lv, b, a, i * stride));
                     if (tid < n1p - n1) ox[ns + n1 + tid] = 0xFFFFFFFFu;  // padding: becomes ord 0, never counted
                     ns += n1p;
@@ -424,6 +438,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     __syncthreads();
     YPP_PHASE(0, b, 6);
     uint32_t omin = 0xFFFFFFFFu, omax = 0u;
+#pragma unroll 1
     for (int m = tid; m < ns; m += SEL_THREADS) {
         const uint32_t raw = ox[m];
         const uint32_t o = raw == 0xFFFFFFFFu ? 0u : f2ord(__uint_as_float(raw));
@@ -452,6 +467,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     // sampled histogram of (omax - o): bin 0 holds the best logits (staged: 1-in-8 of the slots; streamed: the
     // whole sample)
     const int hstep = staged ? 8 : 1;
+#pragma unroll 1
     for (int m = tid * hstep; m < ns; m += SEL_THREADS * hstep) {
         const uint32_t o = ox[m];
         if (o) atomicAdd(&S.hist[(omax - o) >> shift], 1);
@@ -498,6 +514,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     if (staged) {
         static_assert(SEL_THREADS * 32 >= 32768, "one survivor bit per staged slot of a thread");
         unsigned em = 0u;
+#pragma unroll 1
         for (int m = tid, j = 0; m < M; m += SEL_THREADS, ++j) {
             const uint32_t o = ox[m];
             em |= ((o && o >= cut_ord) ? 1u : 0u) << j;
@@ -512,6 +529,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
         int sp = 0;
         if (lane == 31 && incl) sp = atomicAdd(&S.count, incl);
         sp = __shfl_sync(0xffffffffu, sp, 31) + incl - c;
+#pragma unroll 1
         while (em) {
             const int j = __ffs(em) - 1;
             em &= em - 1;
@@ -522,16 +540,19 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
         // one pass over the whole segment in global memory: 16-byte loads (4 x 4 logits in flight per thread) where
         // the planes are 16-byte aligned, 8 scalar loads in flight otherwise. Survivors are rare (~1.4 k of the
         // segment): each takes its stash slot with one shared-memory atomic.
+#pragma unroll 1
         for (int li = 0; li < sg.num_levels; ++li) {
             const LevelDev& lv = P.lv[sg.first_level + li];
             const int s0 = lv.m_off - sg.m_begin;
             const bool vec = !P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0);
+#pragma unroll 1
             for (int a = 0; a < P.A; ++a) {
                 if (vec) {
                     constexpr int U = 4;
                     const float4* plane4 = reinterpret_cast<const float4*>(obj_addr(P, lv, b, a, 0));
                     uint4* rank4 = reinterpret_cast<uint4*>(rank + s0 + a * lv.HW);  // (m_begin, m_off, HW: multiples of 4)
                     const int n4 = lv.HW >> 2;
+#pragma unroll 1
                     for (int i0 = 0; i0 < n4; i0 += SEL_THREADS * U) {
                         float4 v[U];
 #pragma unroll
@@ -556,6 +577,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
                     }
                 } else {
                     constexpr int U = 8;
+#pragma unroll 1
                     for (int h0 = 0; h0 < lv.HW; h0 += SEL_THREADS * U) {
                         float v[U];
 #pragma unroll
@@ -586,6 +608,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     if (n_stash < sg.k || n_stash > kcap) return false;
     // keys of the stash + their exact range
     uint32_t hmin = 0xFFFFFFFFu, hmax = 0u;
+#pragma unroll 1
     for (int i = tid; i < n_stash; i += SEL_THREADS) {
         const int m = (int)slots[i];
         int l = 0, a = 0, hw = 0;
@@ -654,11 +677,14 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
     // pass 0: objectness of every anchor of the segment -> composite key; rank map cleared; key range.
     // Loads are issued in batches of 8 per thread so that one DRAM round trip covers 8 anchors.
     u64 kmin = ~0ull, kmax = 0ull;
+#pragma unroll 1
     for (int li = 0; li < sg.num_levels; ++li) {
         const LevelDev& lv = P.lv[sg.first_level + li];
         constexpr int U = 8;
+#pragma unroll 1
         for (int a = 0; a < P.A; ++a) {
             const int m0 = lv.m_off + a * lv.HW;
+#pragma unroll 1
             for (int h0 = 0; h0 < lv.HW; h0 += SEL_THREADS * U) {
                 float v[U];
 #pragma unroll
@@ -698,6 +724,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_kernel(const __grid_con
         const int chunk = P.sel_kcap / 2;
         u64 lo = gmin;
         int done = 0;
+#pragma unroll 1
         while (done < sg.k) {
             const int want = min(chunk, sg.k - done);
             const int cnt = select_sorted_prefix(src, lo, gmax, want, sel, sel + P.sel_kcap, P.sel_kcap, S);
@@ -1685,12 +1712,14 @@ __device__ __noinline__ int nms_bulk_scan(const DevParams& P, const uint32_t* ma
 #define YPP_ACC2(i) do { } while (0)
 #endif
     int npass = 0;
+#pragma unroll 1
     for (int r0 = 0; r0 < nrows; r0 += H, ++npass) {
         const int n = min(H, nrows - r0);
         if (r0 > 0) fence_proxy_async();  // this thread's generic reads of the buffer -> the async-proxy refill
         __syncthreads();                  // (first pass: publishes *count = 0)
         // (complete_tx of a copy may precede the expect_tx: the phase cannot complete before thread 0 has arrived)
         if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)n * row_bytes);
+#pragma unroll 1
         for (int i = tid; i < n; i += NMS_THREADS)
             bulk_load_1d(stage + (size_t)i * row_bytes, mat + (size_t)(uint32_t)rows[r0 + i] * C, row_bytes, bar);
         YPP_ACC2(0);
@@ -1701,6 +1730,7 @@ __device__ __noinline__ int nms_bulk_scan(const DevParams& P, const uint32_t* ma
         // 8 groups per thread are flushed together (one warp scan + one shared-memory atomic per flush)
         const uint4* st4 = reinterpret_cast<const uint4*>(stage);
         const int ng = n * C4;
+#pragma unroll 1
         for (int base = 0; base < ng; base += NMS_THREADS * 8) {
             unsigned em = 0u;
 #pragma unroll
@@ -1728,6 +1758,7 @@ __device__ __noinline__ int nms_bulk_scan(const DevParams& P, const uint32_t* ma
                 if (lane == 31) sp = atomicAdd(count, incl);
                 sp = __shfl_sync(0xffffffffu, sp, 31) + incl - c;
                 // (the stash entry carries the position inside the row list for now: no division, no row lookup here)
+#pragma unroll 1
                 while (em) {
                     const int pos = __ffs(em) - 1;
                     em &= em - 1;
@@ -1889,7 +1920,9 @@ __device__ __noinline__ int nms_resolve_classes(int m, int nlab, int nk, int cap
 #pragma unroll 1
         for (int e = lane; e < npairs; e += 32) {
             int pb = (int)((1.0f + sqrtf(1.0f + 8.0f * (float)e)) * 0.5f);  // e = pb (pb - 1) / 2 + pa, pa < pb
+#pragma unroll 1
             while (((pb * (pb - 1)) >> 1) > e) --pb;
+#pragma unroll 1
             while ((((pb + 1) * pb) >> 1) <= e) ++pb;
             const int pa = e - ((pb * (pb - 1)) >> 1);
             const int i = (int)Q.clist[o0 + pa], j = (int)Q.clist[o0 + pb];
@@ -1999,14 +2032,17 @@ __device__ __noinline__ int nms_resolve_classes(int m, int nlab, int nk, int cap
 // along the class chain of the kept list. All threads of the NMS block call.
 __device__ __noinline__ void nms_label_offsets(const DevParams& P, int b, int nk, const int* kcl, int* cnt) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, C = P.C;
+#pragma unroll 1
     for (int c = tid; c < C; c += NMS_THREADS) cnt[c] = 0;
     __syncthreads();
+#pragma unroll 1
     for (int i = tid; i < nk; i += NMS_THREADS) atomicAdd(&cnt[kcl[i]], 1);
     __syncthreads();
     if (warp == 0) {
         // exclusive scan over the classes: each lane owns a contiguous run
         const int per = (C + 31) / 32, c0 = lane * per, c1 = min(C, c0 + per);
         int sum = 0;
+#pragma unroll 1
         for (int c = c0; c < c1; ++c) sum += cnt[c];
         int incl = sum;
 #pragma unroll
@@ -2016,6 +2052,7 @@ __device__ __noinline__ void nms_label_offsets(const DevParams& P, int b, int nk
         }
         int run = incl - sum;
         int* offs = P.o_cls_offsets + (size_t)b * (C + 1);
+#pragma unroll 1
         for (int c = c0; c < c1; ++c) {
             const int v = cnt[c];
             cnt[c] = run;
@@ -2048,6 +2085,7 @@ __device__ __noinline__ int nms_pick_rows(const DevParams& P, int b, int W, uint
         S.kb = -1;
     }
     __syncthreads();
+#pragma unroll 1
     for (int r = tid; r < P.R; r += NMS_THREADS) {
         const uint4 st = rs[r];
         if (st.z) atomicAdd(&S.hist[(bmax - st.x) >> shift], 1);
@@ -2063,11 +2101,13 @@ __device__ __noinline__ int nms_pick_rows(const DevParams& P, int b, int W, uint
     if (lane == 31) S.wsum[warp] = incl;
     __syncthreads();
     int excl = incl - v;
+#pragma unroll 1
     for (int w = 0; w < warp; ++w) excl += S.wsum[w];
     if (excl < W && W <= excl + v) S.kb = tid;
     __syncthreads();
     const int pb = S.kb;
     if (pb < 0) return -1;
+#pragma unroll 1
     for (int r = tid; r < P.R; r += NMS_THREADS) {
         const uint4 st = rs[r];
         if (st.z && (int)((bmax - st.x) >> shift) <= pb) {
@@ -2162,6 +2202,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         uint32_t best = 0u, worst = 0u, mx = 0u, cnt = 0u;
         if (!generic) {
             const uint4* rs = P.row_stat + (size_t)b * P.R;
+#pragma unroll 1
             for (int r = tid; r < P.R; r += NMS_THREADS) {
                 const uint4 st = rs[r];
                 if (st.z) {
@@ -2175,6 +2216,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
             }
         } else {
             // every input box is a candidate: key range over all scores, boxes.max() over all boxes
+#pragma unroll 1
             for (int i = tid; i < slots; i += NMS_THREADS) {
                 const uint32_t o = f2ord(__uint_as_float(mat[i]));
                 best = o > best ? o : best;
@@ -2220,6 +2262,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     }
     const uint32_t img_max_ord = s_red[2];
     const bool per_class = !(ntot < P.split_thr);  // regime of mmcv batched_nms
+#pragma unroll 1
     for (int c = tid; c < nlab; c += NMS_THREADS) chead[c] = -1;
     const bool use_off = !P.nms_agnostic;
     const float mp1 = fadd(ord2f(img_max_ord), 1.0f);  // max_coordinate + 1
@@ -2251,6 +2294,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     int prof_chunks = 0, prof_groups = 0;
     long long prof_ab1 = 0, prof_b2 = 0;
 #endif
+#pragma unroll 1
     while (processed < ntot && s_nk < cap) {
         const int want = min(chunk, ntot - processed);
         const int want_sorted = processed == 0 ? min(chunk_sorted, ntot) : want;  // (the stash usually holds more than `want`)
@@ -2353,6 +2397,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
 #ifdef YPP_PROFILE
         if (prof_chunks == 1) YPP_PHASE(1, b, 4);
 #endif
+#pragma unroll 1
         for (int s0 = 0; s0 < m; s0 += NMS_G) {
             const int nk = s_nk;
             if (nk >= cap) break;
@@ -2373,6 +2418,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
                         bj.x2 = cx2[j];
                         bj.y2 = cy2[j];
                         bj.area = car[j];
+#pragma unroll 1
                         for (int k = chead[ccl[j]]; k >= 0 && !sup; k = knext[k]) {
                             Box bk;
                             bk.x1 = kx1[k];
@@ -2397,6 +2443,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
                 bj.y2 = valid ? cy2[j] : 0.f;
                 bj.area = valid ? car[j] : 0.f;
                 bool sup = false;
+#pragma unroll 1
                 for (int k = tid >> 6; k < nk; k += NMS_THREADS / NMS_G) {
                     Box bk;
                     bk.x1 = kx1[k];
@@ -2410,6 +2457,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
                 if (lane == 0 && bal) atomicOr(&s_sup, (u64)bal << ((warp & 1) * 32));
             }
             // ---- phase B1: suppression rows inside the group, row i = bits j > i that box i would suppress
+#pragma unroll 1
             for (int i = warp; i < NMS_G; i += NMS_THREADS / 32) {
                 const int gi = s0 + i;
                 u64 row = 0ull;
@@ -2459,6 +2507,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
                 u64 nz = ((u64)__ballot_sync(0xffffffffu, (mb & alive) != 0ull) << 32) |
                          (u64)__ballot_sync(0xffffffffu, (ma & alive) != 0ull);
                 nz &= alive;
+#pragma unroll 1
                 while (nz) {
                     const int i = __ffsll((long long)nz) - 1;
                     nz &= nz - 1ull;
@@ -2469,6 +2518,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
                 }
                 u64 keptm = alive;
                 // only the first `room` kept boxes can enter the first `cap` kept (later ones never affect earlier)
+#pragma unroll 1
                 for (int kc = __popcll(keptm); kc > room; --kc) keptm &= ~(1ull << (63 - __clzll((long long)keptm)));
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -2525,6 +2575,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         __syncthreads();
         nms_label_offsets(P, b, nk, kcl, gcnt);
     }
+#pragma unroll 1
     for (int i = tid; i < nk; i += NMS_THREADS) {
         const u64 key = kkey[i];
         const uint32_t flat = key_flat(key);
@@ -2545,6 +2596,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
         if (grouped) {
             // stable position inside the label's group: kept boxes of the class with a smaller output index
             int pos = gcnt[c];
+#pragma unroll 1
             for (int k = chead[c]; k >= 0; k = knext[k]) pos += (k < i) ? 1 : 0;
             float* g = P.o_cls_dets + ((size_t)b * P.out_cap + pos) * 5;
             g[0] = bx.x;
