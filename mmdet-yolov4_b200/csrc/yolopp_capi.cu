@@ -25,7 +25,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 constexpr size_t SMEM_LIMIT_TOTAL = 232448;  // static + dynamic shared memory a CTA may use on sm_100 (227 KB opt-in)
 #ifndef YPP_NMS_STATIC_SMEM
-#define YPP_NMS_STATIC_SMEM 10496  // >= the per-image kernels' static shared memory (ptxas -v; checked at start-up)
+#define YPP_NMS_STATIC_SMEM 10752  // >= the per-image kernels' static shared memory (ptxas -v; checked at start-up)
 #endif
 constexpr size_t SMEM_LIMIT = SMEM_LIMIT_TOTAL - YPP_NMS_STATIC_SMEM;  // dynamic part
 
@@ -383,6 +383,7 @@ struct yolopp_plan {
     Plan plan;
     TmapPack maps;
     int dec_grid;
+    int nms_grid;    // CTAs of the NMS kernel: one per image, or one per YPP_NMS_IMAGES_PER_CTA images for batches in flight
     int stop_after;  // 0: whole path, 1: after the top-k, 2: after the decode (stage entries)
     cudaGraphExec_t exec;  // plan handles only: the call's launches as one executable graph (null: launch directly)
 };
@@ -430,8 +431,19 @@ int prepare(const yolopp_params* p, const float* const* level_ptrs, const float*
     // and the per-image kernels of the neighbouring batches move onto the freed SMs while the rest of the decode
     // kernel still streams.
     int dec_grid = di.sms * plan.dec_ctas_per_sm;
+#ifdef YPP_EXPERIMENT_KNOBS
+    if (getenv("YPP_DEC_GRID")) dec_grid = atoi(getenv("YPP_DEC_GRID"));
+#endif
     if (dec_grid > d.tma_tiles) dec_grid = d.tma_tiles;
     pl->dec_grid = dec_grid;
+#ifndef YPP_NMS_IMAGES_PER_CTA
+#define YPP_NMS_IMAGES_PER_CTA 1  // measured (608^2 b64, 6 batches in flight): 1 -> 579 k, 2 -> 583 k, 4 -> 575 k img/s: no gain
+#endif
+    {
+        const char* env = getenv("YPP_NMS_IPC");  // (experiment knob)
+        const int ipc = env ? atoi(env) : YPP_NMS_IMAGES_PER_CTA;
+        pl->nms_grid = (p->batches_in_flight > 1 && ipc > 1) ? (d.B + ipc - 1) / ipc : d.B;
+    }
     d.dec_first = 0;
     if (d.tma_tiles > 0) {
         d.dec_first = p->batches_in_flight > 1 ? (unsigned)d.tma_tiles
@@ -489,7 +501,13 @@ int launch(const yolopp_plan* pl, cudaStream_t stream, void* const* events, int 
         }                                                                                   \
     } while (0)
     YPP_MARK();  // 0: start of select
-    if (d.ntopk > 0) {
+#ifdef YPP_EXPERIMENT_KNOBS
+    const char* skip_env = getenv("YPP_SKIP");  // timing experiments only: bit 0 = no top-k, bit 1 = no NMS (stale results)
+    const int skip = skip_env ? atoi(skip_env) : 0;
+#else
+    const int skip = 0;
+#endif
+    if (d.ntopk > 0 && !(skip & 1)) {
         // (block (0, 0) also clears the status word and initialises the decode kernel's tile counter)
         select_kernel<<<dim3(d.ntopk, d.B), SEL_THREADS, plan.sel_smem, stream>>>(d);
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
@@ -539,8 +557,10 @@ int launch(const yolopp_plan* pl, cudaStream_t stream, void* const* events, int 
     }
     if (pl->stop_after == 2) return YOLOPP_OK;
     YPP_MARK();  // 3: start of the per-image NMS
-    nms_image_kernel<<<d.B, NMS_THREADS, plan.nms_smem, stream>>>(d);
-    if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    if (!(skip & 2)) {
+        nms_image_kernel<<<pl->nms_grid, NMS_THREADS, plan.nms_smem, stream>>>(d);
+        if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
+    }
     YPP_MARK();  // 4: end
 #undef YPP_MARK
     return YOLOPP_OK;

@@ -75,9 +75,11 @@ __device__ long long g_phase[2][256][16];
 // finer stamps inside the NMS kernel's first chunk: [image][stamp]
 __device__ long long g_sub[256][32];  // (stamps 0..16 in use)
 #define YPP_SUB(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) g_sub[blockIdx.x][i] = clock64(); } while (0)
+#define YPP_SUBY(i) do { if (threadIdx.x == 0 && blockIdx.y < 256) g_sub[blockIdx.y][i] = clock64(); } while (0)
 #else
 #define YPP_PHASE(k, blk, i) do { } while (0)
 #define YPP_SUB(i) do { } while (0)
+#define YPP_SUBY(i) do { } while (0)
 #endif
 
 struct DevParams {
@@ -362,6 +364,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     for (int i = tid; i < TS_BINS; i += SEL_THREADS) S.hist[i] = 0;
     if (tid == 0) S.count = 0;
     uint64_t* bar = reinterpret_cast<uint64_t*>(&S.bar);
+    YPP_SUBY(20);
     if (staged) {
         // stage the logits (slot order = plane-major order of the segment): one bulk copy per objectness plane
         // where planes are 16-byte aligned (issued by warp 0, one plane per lane), 4-byte async copies otherwise
@@ -377,7 +380,9 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
             }
             mbar_arrive_expect_tx(bar, bulk_bytes);
         }
+        YPP_SUBY(21);
         __syncthreads();
+        YPP_SUBY(22);
 #pragma unroll 1
         for (int li = 0; li < sg.num_levels; ++li) {
             const LevelDev& lv = P.lv[sg.first_level + li];
@@ -403,6 +408,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
             }
             const int pad0 = s0 + AHW, pad1 = li + 1 < sg.num_levels ? P.lv[sg.first_level + li + 1].m_off - sg.m_begin : M;
             if (tid < pad1 - pad0) ox[pad0 + tid] = 0xFFFFFFFFu;  // alignment padding: becomes ord 0, never eligible
+            YPP_SUBY(23 + li);
         }
         YPP_PHASE(0, b, 5);
         cp_async_wait_all();
@@ -1715,7 +1721,7 @@ __device__ __noinline__ int nms_bulk_scan(const DevParams& P, const uint32_t* ma
 #pragma unroll 1
     for (int r0 = 0; r0 < nrows; r0 += H, ++npass) {
         const int n = min(H, nrows - r0);
-        if (r0 > 0) fence_proxy_async();  // this thread's generic reads of the buffer -> the async-proxy refill
+        fence_proxy_async();  // this thread's generic reads of the buffer (earlier pass / image) -> the async-proxy refill
         __syncthreads();                  // (first pass: publishes *count = 0)
         // (complete_tx of a copy may precede the expect_tx: the phase cannot complete before thread 0 has arrived)
         if (tid == 0) mbar_arrive_expect_tx(bar, (uint32_t)n * row_bytes);
@@ -2134,8 +2140,8 @@ __device__ __noinline__ int nms_pick_rows(const DevParams& P, int b, int W, uint
 //                   still on the offset boxes.
 // In both regimes the result order is (score desc, flat index asc) and only the first max_num are returned,
 // so candidates are visited in that global order and the pass stops once `cap` boxes are kept.
-__global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_constant__ DevParams P) {
-    extern __shared__ __align__(16) unsigned char nms_smem[];
+__device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, unsigned char* nms_smem, uint64_t* stage_bar,
+                                               uint32_t& stage_phase) {
     __shared__ TopSelSmem S;
     __shared__ u64 s_sup, s_masks[NMS_G];
     __shared__ int s_nk, s_stash;
@@ -2158,7 +2164,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     float* kx1 = reinterpret_cast<float*>(ccl + NMS_CH);           // [cap_s] x 5
     int* chead = reinterpret_cast<int*>(kx1 + 7 * (size_t)cap_s);  // [C]   latest kept box of each class (-1: none)
     if (kept_global) {
-        unsigned char* gk = P.nms_kept + (size_t)blockIdx.x * (size_t)P.nms_kept_stride;
+        unsigned char* gk = P.nms_kept + (size_t)b * (size_t)P.nms_kept_stride;
         kkey = reinterpret_cast<u64*>(gk);
         kx1 = reinterpret_cast<float*>(kkey + cap);
     }
@@ -2171,7 +2177,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     u64* rowkeys = reinterpret_cast<u64*>(nms_smem + P.nms_rowkeys_off);  // [NMS_KCAP] rows of the candidate scan
     NmsClsSmem& Q = *reinterpret_cast<NmsClsSmem*>(rowkeys);              // (scratch of the class-parallel pass, between scans)
 
-    const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int C = P.C;
     const int slots = P.R * C;
     const bool generic = P.generic != 0;
@@ -2185,11 +2191,7 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
 #ifdef YPP_PROFILE
     if (threadIdx.x == 0) { S.prof_kernel = 1; S.prof_call = 0; }
 #endif
-    uint64_t* stage_bar = reinterpret_cast<uint64_t*>(&S.bar);  // bulk copies of the candidate scan
-    uint32_t stage_phase = 0u;
     if (tid == 0) {
-        mbar_init(stage_bar, 1);
-        fence_mbar_init();
         s_nk = 0;
         s_sup = 0ull;
         s_red[0] = 0u;
@@ -2608,6 +2610,26 @@ __global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_
     }
     if (tid == 0) P.o_count[b] = nk;
     YPP_PHASE(1, b, 6);
+}
+
+// One CTA per image — or, when the grid is smaller than the batch (batches in flight on several streams: what counts
+// there is SM-time, not latency), a CTA takes several images one after the other: the later ones find the kernel's
+// code in the instruction caches, which is most of what a per-image pass waits for.
+__global__ void __launch_bounds__(NMS_THREADS, 1) nms_image_kernel(const __grid_constant__ DevParams P) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    __shared__ unsigned long long s_stage_bar;  // bulk copies of the candidate scan
+    uint64_t* stage_bar = reinterpret_cast<uint64_t*>(&s_stage_bar);
+    uint32_t stage_phase = 0u;
+    if (threadIdx.x == 0) {
+        mbar_init(stage_bar, 1);
+        fence_mbar_init();
+    }
+    // (the body's first block barrier publishes the initialised mbarrier)
+#pragma unroll 1
+    for (int b = blockIdx.x; b < P.B; b += gridDim.x) {
+        nms_image_body(P, b, nms_smem, stage_bar, stage_phase);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
