@@ -411,6 +411,16 @@ int prepare(const yolopp_params* p, const float* const* level_ptrs, const float*
         // a tensor map needs a 16-byte aligned base: otherwise the level's tiles are gathered
         if (d.lv[l].use_tma && ((uintptr_t)level_ptrs[l] & 15) != 0) d.lv[l].use_tma = 2;
     }
+    // top-k staging: which levels' objectness planes can be bulk-copied (16-byte aligned source and destination)
+    for (int sgi = 0; sgi < d.nsegs; ++sgi) {
+        SegDev& sg = d.seg[sgi];
+        sg.sel_bulk_bytes = 0;
+        for (int q = 0; q < sg.num_levels; ++q) {
+            LevelDev& lv = d.lv[sg.first_level + q];
+            lv.sel_bulk = (!d.nhwc && (lv.HW & 3) == 0 && ((uintptr_t)lv.ptr & 15) == 0 && ((lv.m_off - sg.m_begin) & 3) == 0) ? 1 : 0;
+            if (lv.sel_bulk) sg.sel_bulk_bytes += (unsigned)(d.A * lv.HW) * 4u;
+        }
+    }
     bind_workspace(&plan, workspace);
     d.scale = scale_factors;
     if (out) {

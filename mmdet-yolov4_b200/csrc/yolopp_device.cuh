@@ -504,12 +504,18 @@ __device__ __noinline__ int select_sorted_prefix(const Source& src_ref, u64 lo_i
     if (lane == 31) S.wsum[warp] = incl;
     if (tid == 0) S.kb = -1;
     __syncthreads();
-    int woff = 0, total = 0;
-#pragma unroll 1
-    for (int w = 0; w < nw; ++w) {
-        int v = S.wsum[w];
-        if (w < warp) woff += v;
-        total += v;
+    // offset of this warp / total: every warp scans the (<= 32) warp sums itself
+    int woff, total;
+    {
+        const int wv = lane < nw ? S.wsum[lane] : 0;
+        int wi = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        total = __shfl_sync(0xffffffffu, wi, 31);
+        woff = __shfl_sync(0xffffffffu, wi - wv, warp);
     }
     if (m > total) m = total;
     if (total == 0) return 0;

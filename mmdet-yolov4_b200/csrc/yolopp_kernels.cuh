@@ -50,6 +50,7 @@ struct LevelDev {
                   // (unaligned plane stride: the tensor is viewed as rows of FOUR planes, whose stride always is a
                   // multiple of 16 bytes), 2 = gather tiles (no tensor map possible); 0: decode_ldg / decode_dense kernel
     int dense;    // use_tma == 0 only: 1 = most anchors are admitted -> decode_dense_kernel (thread per position)
+    int sel_bulk; // top-k staging: the level's objectness planes are 16-byte aligned on both sides -> one bulk copy per plane
     int qrows;    // use_tma == 3: rows of the quad-row view = floor(B * A * NA / 4)
     int tile0;    // first tile id of this level in its kernel's tile enumeration
     int tpp;      // tiles per plane
@@ -66,6 +67,7 @@ struct SegDev {
     int row_off;  // first row of the segment
     int has_topk;
     int m_begin, m_end;  // plane-major index range of the segment
+    unsigned sel_bulk_bytes;  // top-k staging: bytes the bulk copies of one image bring in (levels with sel_bulk)
 };
 
 #ifdef YPP_PROFILE
@@ -368,17 +370,12 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     if (staged) {
         // stage the logits (slot order = plane-major order of the segment): one bulk copy per objectness plane
         // where planes are 16-byte aligned (issued by warp 0, one plane per lane), 4-byte async copies otherwise
+        // (which levels qualify and how many bytes that makes is worked out on the host: the start of this kernel is
+        // a serial stretch of cold code, every instruction taken out of it counts)
         if (tid == 0) {
             mbar_init(bar, 1);
             fence_mbar_init();
-            uint32_t bulk_bytes = 0;
-#pragma unroll 1
-            for (int li = 0; li < sg.num_levels; ++li) {
-                const LevelDev& lv = P.lv[sg.first_level + li];
-                if (!P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && (((lv.m_off - sg.m_begin) & 3) == 0))
-                    bulk_bytes += (uint32_t)(P.A * lv.HW) * 4u;
-            }
-            mbar_arrive_expect_tx(bar, bulk_bytes);
+            mbar_arrive_expect_tx(bar, sg.sel_bulk_bytes);
         }
         YPP_SUBY(21);
         __syncthreads();
@@ -388,8 +385,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
             const LevelDev& lv = P.lv[sg.first_level + li];
             const float* lbase = lv.ptr + (size_t)b * P.A * P.NA * lv.HW;
             const int AHW = P.A * lv.HW, s0 = lv.m_off - sg.m_begin;
-            const bool bulk = !P.nhwc && ((lv.HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(lv.ptr) & 15) == 0) && ((s0 & 3) == 0);
-            if (bulk) {
+            if (lv.sel_bulk) {
                 if (warp == 0)
 #pragma unroll 1
                     for (int a = lane; a < P.A; a += 32)
@@ -443,13 +439,18 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     }
     __syncthreads();
     YPP_PHASE(0, b, 6);
+    // The staging buffer keeps the RAW logits (0xFFFFFFFF = alignment padding -> ord 0, never eligible); the order-
+    // preserving integers are formed on the fly. Range and histogram come from the same sample (staged: 1 in 8 slots;
+    // streamed: everything that was staged) — logits outside the sample's range are simply above / below every bin.
+    auto ord_at = [&](int m) -> uint32_t {
+        const uint32_t raw = ox[m];
+        return raw == 0xFFFFFFFFu ? 0u : f2ord(__uint_as_float(raw));
+    };
+    const int hstep = staged ? 8 : 1;
     uint32_t omin = 0xFFFFFFFFu, omax = 0u;
 #pragma unroll 1
-    for (int m = tid; m < ns; m += SEL_THREADS) {
-        const uint32_t raw = ox[m];
-        const uint32_t o = raw == 0xFFFFFFFFu ? 0u : f2ord(__uint_as_float(raw));
-        ox[m] = o;
-        if (staged && !P.nhwc) rank[m] = RANK_INVALID;
+    for (int m = tid * hstep; m < ns; m += SEL_THREADS * hstep) {
+        const uint32_t o = ord_at(m);
         omin = (o && o < omin) ? o : omin;
         omax = o > omax ? o : omax;
     }
@@ -472,10 +473,9 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     const int shift = range >= (uint32_t)TS_BINS ? (32 - __clz(range)) - 11 : 0;
     // sampled histogram of (omax - o): bin 0 holds the best logits (staged: 1-in-8 of the slots; streamed: the
     // whole sample)
-    const int hstep = staged ? 8 : 1;
 #pragma unroll 1
     for (int m = tid * hstep; m < ns; m += SEL_THREADS * hstep) {
-        const uint32_t o = ox[m];
+        const uint32_t o = ord_at(m);
         if (o) atomicAdd(&S.hist[(omax - o) >> shift], 1);
     }
     __syncthreads();
@@ -522,8 +522,9 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
         unsigned em = 0u;
 #pragma unroll 1
         for (int m = tid, j = 0; m < M; m += SEL_THREADS, ++j) {
-            const uint32_t o = ox[m];
+            const uint32_t o = ord_at(m);
             em |= ((o && o >= cut_ord) ? 1u : 0u) << j;
+            if (!P.nhwc) rank[m] = RANK_INVALID;  // (the rank map is cleared on the way)
         }
         const int c = __popc(em);
         int incl = c;
@@ -619,7 +620,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
         const int m = (int)slots[i];
         int l = 0, a = 0, hw = 0;
         seg_slot(P, sg, m + sg.m_begin, l, a, hw);
-        const uint32_t o = staged ? ox[m] : f2ord(__ldg(obj_addr(P, P.lv[l], b, a, hw)));
+        const uint32_t o = staged ? ord_at(m) : f2ord(__ldg(obj_addr(P, P.lv[l], b, a, hw)));
         const float conf = c_sigmoid(ord2f(o));
         const uint32_t h = ~f2ord(conf);
         sel[i] = ((u64)h << 32) | (u64)(uint32_t)(P.lv[l].n_off + hw * P.A + a);
@@ -644,7 +645,7 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
     // every logit outside the stash is below the cut: its confidence is at most conf(cut) (+ rounding noise)
     const uint32_t conf_cut = f2ord(c_sigmoid(ord2f(cut_ord)));
     const uint32_t conf_k = ~(uint32_t)(sel[sg.k - 1] >> 32);
-    const bool excluded = staged ? (cut < range) : (n_stash < sg.N);
+    const bool excluded = n_stash < sg.N;  // (the range is the sample's: logits below it are outside the stash whatever the cut)
     if (excluded && !(conf_k >= conf_cut + 16u)) return false;
     select_write(P, sg, b, sel, sg.k);
     return true;
