@@ -380,17 +380,27 @@ __device__ __noinline__ bool select_fast(const DevParams& P, const SegDev& sg, i
         YPP_SUBY(21);
         __syncthreads();
         YPP_SUBY(22);
+        if (warp == 0) {
+            // bulk copies: one lane per (level, anchor) plane, all issued at once
+#pragma unroll 1
+            for (int q = lane; q < sg.num_levels * P.A; q += 32) {
+                int li = 0, a = q;
+#pragma unroll 1
+                while (a >= P.A) {
+                    a -= P.A;
+                    ++li;
+                }
+                const LevelDev& lv = P.lv[sg.first_level + li];
+                if (lv.sel_bulk)
+                    bulk_load_1d(ox + (lv.m_off - sg.m_begin) + a * lv.HW,
+                                 lv.ptr + ((size_t)(b * P.A + a) * P.NA + 4) * lv.HW, (uint32_t)lv.HW * 4u, bar);
+            }
+        }
 #pragma unroll 1
         for (int li = 0; li < sg.num_levels; ++li) {
             const LevelDev& lv = P.lv[sg.first_level + li];
-            const float* lbase = lv.ptr + (size_t)b * P.A * P.NA * lv.HW;
             const int AHW = P.A * lv.HW, s0 = lv.m_off - sg.m_begin;
-            if (lv.sel_bulk) {
-                if (warp == 0)
-#pragma unroll 1
-                    for (int a = lane; a < P.A; a += 32)
-                        bulk_load_1d(ox + s0 + a * lv.HW, lbase + ((size_t)a * P.NA + 4) * lv.HW, (uint32_t)lv.HW * 4u, bar);
-            } else {
+            if (!lv.sel_bulk) {
 #pragma unroll 1
                 for (int e = tid; e < AHW; e += SEL_THREADS) {
                     int a = 0, hw = e;
@@ -1702,7 +1712,8 @@ __global__ void __launch_bounds__(32 * DENSE_WARPS, 6) decode_dense_kernel(const
 // instructions, every row in flight at once — the DRAM latency is paid once per pass) into a staging buffer of
 // P.nms_stage_rows rows, and every entry inside the key window [lo, hi] lands in the stash `out` as a 64-bit key.
 // Rows are 16-byte multiples (C % 4 == 0). More rows than the buffer holds: further passes. Returns the number of
-// stashed keys (may exceed cap: the caller then falls back to the generic source scan); all threads call.
+// stashed keys (may exceed cap: the caller then falls back to the generic source scan); their low words hold the position
+// inside the row list (see nms_stash_to_flat). All threads call.
 // `bar` = the block's staging mbarrier (initialised with count 1), `phase` = its running parity.
 __device__ __noinline__ int nms_bulk_scan(const DevParams& P, const uint32_t* mat, const u64* rows, int nrows, u64 lo, u64 hi,
                                           u64* out, int cap, unsigned char* stage, int* count, uint64_t* bar, uint32_t& phase) {
@@ -1787,16 +1798,19 @@ __device__ __noinline__ int nms_bulk_scan(const DevParams& P, const uint32_t* ma
     }
 #endif
     __syncthreads();
-    // position inside the row list -> flat candidate index row * C + class, one dense pass over the stash
-    const int total = *count;
+    return *count;
+}
+
+// The stash of nms_bulk_scan carries, in the low word of each key, the candidate's position inside the row list
+// (list index * C + class): this turns it into the flat candidate index row * C + class. All threads call.
+__device__ __forceinline__ void nms_stash_to_flat(u64* keys, int n, const u64* rows, int C) {
 #pragma unroll 1
-    for (int i = tid; i < total && i < cap; i += NMS_THREADS) {
-        const u64 k = out[i];
+    for (int i = threadIdx.x; i < n; i += NMS_THREADS) {
+        const u64 k = keys[i];
         const uint32_t e = (uint32_t)k, r = e / (uint32_t)C;
-        out[i] = (k & 0xFFFFFFFF00000000ull) | (u64)((uint32_t)rows[r] * (uint32_t)C + (e - r * (uint32_t)C));
+        keys[i] = (k & 0xFFFFFFFF00000000ull) | (u64)((uint32_t)rows[r] * (uint32_t)C + (e - r * (uint32_t)C));
     }
     __syncthreads();
-    return total;
 }
 
 // Greedy NMS of one chunk in the classes-are-independent regime (mmcv batched_nms, n >= split_thr: a kept box only
@@ -2080,7 +2094,7 @@ __device__ __noinline__ void nms_label_offsets(const DevParams& P, int b, int nk
 // list longer than NMS_KCAP: the caller scans the whole matrix). bmax / bmin = ord of the best / worst candidate
 // score of the image. All threads of the NMS block call.
 __device__ __noinline__ int nms_pick_rows(const DevParams& P, int b, int W, uint32_t bmax, uint32_t bmin, u64* rowkeys,
-                                          TopSelSmem& S, uint32_t* t_ord) {
+                                          TopSelSmem& S, uint32_t* t_ord, const uint32_t* rmax) {
     static_assert(NMS_THREADS == 512, "one histogram bin per thread");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint4* rs = P.row_stat + (size_t)b * P.R;
@@ -2092,10 +2106,17 @@ __device__ __noinline__ int nms_pick_rows(const DevParams& P, int b, int W, uint
         S.kb = -1;
     }
     __syncthreads();
+    // rmax: the rows' best scores as the reduction pass left them in shared memory (0: no candidate), or null
 #pragma unroll 1
     for (int r = tid; r < P.R; r += NMS_THREADS) {
-        const uint4 st = rs[r];
-        if (st.z) atomicAdd(&S.hist[(bmax - st.x) >> shift], 1);
+        uint32_t x;
+        if (rmax) {
+            x = rmax[r];
+        } else {
+            const uint4 st = rs[r];
+            x = st.z ? st.x : 0u;
+        }
+        if (x) atomicAdd(&S.hist[(bmax - x) >> shift], 1);
     }
     __syncthreads();
     const int v = S.hist[tid];
@@ -2108,16 +2129,31 @@ __device__ __noinline__ int nms_pick_rows(const DevParams& P, int b, int W, uint
     if (lane == 31) S.wsum[warp] = incl;
     __syncthreads();
     int excl = incl - v;
-#pragma unroll 1
-    for (int w = 0; w < warp; ++w) excl += S.wsum[w];
+    {
+        // bins of the warps before this one: every warp scans the 16 warp sums itself
+        const int wv = lane < NMS_THREADS / 32 ? S.wsum[lane] : 0;
+        int wi = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        excl += __shfl_sync(0xffffffffu, wi - wv, warp);
+    }
     if (excl < W && W <= excl + v) S.kb = tid;
     __syncthreads();
     const int pb = S.kb;
     if (pb < 0) return -1;
 #pragma unroll 1
     for (int r = tid; r < P.R; r += NMS_THREADS) {
-        const uint4 st = rs[r];
-        if (st.z && (int)((bmax - st.x) >> shift) <= pb) {
+        uint32_t x;
+        if (rmax) {
+            x = rmax[r];
+        } else {
+            const uint4 st = rs[r];
+            x = st.z ? st.x : 0u;
+        }
+        if (x && (int)((bmax - x) >> shift) <= pb) {
             const int sp = atomicAdd(&S.count, 1);
             if (sp < NMS_KCAP) rowkeys[sp] = (u64)(uint32_t)r;
         }
@@ -2185,6 +2221,8 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
     const uint32_t* mat = generic ? reinterpret_cast<const uint32_t*>(P.g_scores) : P.mat + (size_t)b * slots;
     const float4* row_box = P.row_box + (size_t)b * P.R;
     const int nlab = generic ? P.num_labels : C;
+    // the rows' best scores, kept for the first row pick (the select scratch is free until then)
+    uint32_t* rmax = (!generic && P.R <= 2 * NMS_KCAP) ? reinterpret_cast<uint32_t*>(ktmp) : nullptr;
 
     // candidate count, score range and boxes.max() of the image: reduction over the per-row statistics that the
     // decode kernels stored
@@ -2208,6 +2246,7 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
 #pragma unroll 1
             for (int r = tid; r < P.R; r += NMS_THREADS) {
                 const uint4 st = rs[r];
+                if (rmax) rmax[r] = st.z ? st.x : 0u;
                 if (st.z) {
                     best = st.x > best ? st.x : best;
                     worst = st.y > worst ? st.y : worst;
@@ -2308,7 +2347,8 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
         if (!generic && nonneg) {
             uint32_t t_ord = 0u;
             YPP_SUB(0);
-            nrows = nms_pick_rows(P, b, wc, s_red[0], ~s_red[1], rowkeys, S, &t_ord);
+            nrows = nms_pick_rows(P, b, wc, s_red[0], ~s_red[1], rowkeys, S, &t_ord, rmax);
+            rmax = nullptr;  // (the scratch is reused from here on)
             YPP_SUB(1);
             if (nrows >= 0) {
                 const u64 hi_t = ((u64)(~t_ord) << 32) | 0xFFFFFFFFull;
@@ -2316,12 +2356,19 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
             }
         }
         // boxes of the chunk's candidates keys[0..n): boxes + idxs.to(boxes) * (max_coordinate + 1), areas, classes
-        auto stage_boxes = [&](int n) {
+        // (from_list: the keys still carry positions inside the row list — see nms_stash_to_flat — and become flat here)
+        auto stage_boxes = [&](int n, bool from_list) {
 #pragma unroll 1
             for (int i = tid; i < n; i += NMS_THREADS) {
-                const uint32_t flat = key_flat(keys[i]);
-                const int r = (int)(flat / (uint32_t)C);
-                const int c = generic ? (P.g_labels ? (int)P.g_labels[flat] : 0) : (int)(flat - (uint32_t)r * (uint32_t)C);
+                uint32_t flat = key_flat(keys[i]);
+                int r = (int)(flat / (uint32_t)C);
+                const int c0 = (int)(flat - (uint32_t)r * (uint32_t)C);
+                if (from_list) {
+                    r = (int)(uint32_t)rowkeys[r];
+                    flat = (uint32_t)r * (uint32_t)C + (uint32_t)c0;
+                    keys[i] = (keys[i] & 0xFFFFFFFF00000000ull) | (u64)flat;
+                }
+                const int c = generic ? (P.g_labels ? (int)P.g_labels[flat] : 0) : c0;
                 const float4 bx = row_box[P.boxes_per_class ? flat : (uint32_t)r];
                 float x1 = bx.x, y1 = bx.y, x2 = bx.z, y2 = bx.w;
                 if (use_off) {
@@ -2344,6 +2391,7 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
         if (nrows >= 0) {
             // only the listed rows can hold one of the wc best candidates: scan just their matrix rows
             int staged = -1;
+            bool keys_flat = false;  // the stash keys carry flat indices already (else: positions inside the row list)
             if (P.nms_stage_rows > 0)
                 staged = nms_bulk_scan(P, mat, rowkeys, nrows, lo, hi, keys, NMS_KCAP, nms_smem + P.nms_stage_off, &s_stash,
                                        stage_bar, stage_phase);
@@ -2351,7 +2399,8 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
             if (cls_parallel && staged > 0 && staged <= NMS_THREADS) {
                 // the stash IS the complete set of candidates inside the window [lo, hi] — a prefix of the global order
                 // that reaches rank wc: resolve its classes in parallel, unsorted
-                stage_boxes(staged);
+                stage_boxes(staged, true);
+                keys_flat = true;
                 YPP_SUB(3);
                 const int nk1 = nms_resolve_classes(staged, nlab, s_nk, cap, thr, foff, keys, cx1, cy1, cx2, cy2, car, ccl, kx1, ky1,
                                                     kx2, ky2, kar, kcl, kkey, knext, chead, Q, ktmp);
@@ -2372,6 +2421,7 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
                 }
             }
             if (staged >= 0 && staged <= NMS_KCAP) {
+                if (!keys_flat) nms_stash_to_flat(keys, staged, rowkeys, C);
                 StashSource none;
                 got = select_sorted_prefix(none, lo, hi, want_sorted, keys, ktmp, NMS_KCAP, S, staged);
             } else {
@@ -2396,7 +2446,7 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
         ++prof_chunks;
 #endif
         if (m == 0) break;
-        stage_boxes(m);
+        stage_boxes(m, false);
 #ifdef YPP_PROFILE
         if (prof_chunks == 1) YPP_PHASE(1, b, 4);
 #endif
