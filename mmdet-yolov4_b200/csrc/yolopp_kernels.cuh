@@ -78,10 +78,12 @@ __device__ long long g_phase[2][256][16];
 __device__ long long g_sub[256][32];  // (stamps 0..16 in use)
 #define YPP_SUB(i) do { if (threadIdx.x == 0 && blockIdx.x < 256) g_sub[blockIdx.x][i] = clock64(); } while (0)
 #define YPP_SUBY(i) do { if (threadIdx.x == 0 && blockIdx.y < 256) g_sub[blockIdx.y][i] = clock64(); } while (0)
+#define YPP_SUBV(i, v) do { if (threadIdx.x == 0 && blockIdx.x < 256) g_sub[blockIdx.x][i] = (long long)(v); } while (0)
 #else
 #define YPP_PHASE(k, blk, i) do { } while (0)
 #define YPP_SUB(i) do { } while (0)
 #define YPP_SUBY(i) do { } while (0)
+#define YPP_SUBV(i, v) do { } while (0)
 #endif
 
 struct DevParams {
@@ -1859,7 +1861,7 @@ __device__ __noinline__ int nms_resolve_classes(int m, int nlab, int nk, int cap
                                                 const float* cx1, const float* cy1, const float* cx2, const float* cy2,
                                                 const float* car, const int* ccl, float* kx1, float* ky1, float* kx2, float* ky2,
                                                 float* kar, int* kcl, u64* kkey, int* knext, int* chead, NmsClsSmem& Q,
-                                                u64* scratch /* 2 * NMS_CH keys */) {
+                                                u64* scratch /* 2 * NMS_CH keys */, u64 lo, u64 hi, TopSelSmem& S) {
     const int tid = threadIdx.x, lane = tid & 31;
     u64* supby = scratch;                 // [NMS_CH]
     u64* skey = scratch + NMS_CH;         // [NMS_THREADS] kept keys
@@ -1998,11 +2000,63 @@ __device__ __noinline__ int nms_resolve_classes(int m, int nlab, int nk, int cap
     }
     __syncthreads();
     YPP_SUB(13);
-    // 4. kept candidates -> (key, index) pairs, compacted (any order), sorted by key
+    // 4. kept candidates -> (key, index) pairs, compacted (any order), sorted by key. Only the first (cap - nk) in
+    // key order are needed: when more than NMS_THREADS candidates were kept (the sort takes one per thread), a
+    // 512-bin histogram over the chunk's score window first drops the ones that cannot be among them.
+    const int room = cap - nk;
+    const int tid_w = tid >> 5;
 #pragma unroll 1
     for (int i0 = 0; i0 < m; i0 += NMS_THREADS) {  // (uniform trip count)
         const int i = i0 + tid;
-        const bool kf = i < m && Q.kflag[i];
+        const unsigned bal = __ballot_sync(0xffffffffu, i < m && Q.kflag[i]);
+        if (lane == 0 && bal) atomicAdd(&Q.nkept, __popc(bal));
+    }
+    __syncthreads();
+    const int K0 = Q.nkept;
+    const uint32_t w_lo = (uint32_t)(lo >> 32), w_range = (uint32_t)(hi >> 32) - w_lo;
+    const int shift = w_range >= 512u ? (32 - __clz(w_range)) - 9 : 0;
+    int pb = 0x7FFFFFFF;  // last histogram bin that is kept
+    if (K0 > NMS_THREADS) {
+        static_assert(NMS_THREADS == 512, "one histogram bin per thread");
+        S.hist[tid] = 0;
+        if (tid == 0) S.kb = -1;
+        __syncthreads();
+#pragma unroll 1
+        for (int i = tid; i < m; i += NMS_THREADS)
+            if (Q.kflag[i]) atomicAdd(&S.hist[((uint32_t)(key[i] >> 32) - w_lo) >> shift], 1);
+        __syncthreads();
+        const int v = S.hist[tid];
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) S.wsum[tid_w] = incl;
+        __syncthreads();
+        {
+            const int wv = lane < NMS_THREADS / 32 ? S.wsum[lane] : 0;
+            int wi = wv;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            incl += __shfl_sync(0xffffffffu, wi - wv, tid_w);
+        }
+        // the first bin where the count from the best score down reaches `room`; everything up to it must fit the sort
+        if (incl - v < room && room <= incl) S.kb = incl <= NMS_THREADS ? tid : -2;
+        __syncthreads();
+        pb = S.kb;
+        __syncthreads();
+        if (pb < 0) return -1;  // (-2: too many kept candidates share the pivot bin)
+    }
+    if (tid == 0) Q.nkept = 0;
+    __syncthreads();
+#pragma unroll 1
+    for (int i0 = 0; i0 < m; i0 += NMS_THREADS) {  // (uniform trip count)
+        const int i = i0 + tid;
+        const bool kf = i < m && Q.kflag[i] && (int)(((uint32_t)(key[i] >> 32) - w_lo) >> shift) <= pb;
         const unsigned bal = __ballot_sync(0xffffffffu, kf);
         int base = 0;
         if (lane == 0 && bal) base = atomicAdd(&Q.nkept, __popc(bal));
@@ -2028,7 +2082,7 @@ __device__ __noinline__ int nms_resolve_classes(int m, int nlab, int nk, int cap
     bitonic_sort_kv(skey, Q.spay, tkey, Q.tpay, p2);
     YPP_SUB(15);
     // the first (cap - nk) of them join the kept list, in score order
-    const int take = K < cap - nk ? K : cap - nk;
+    const int take = K < room ? K : room;
     if (tid < take) {
         const int gj = (int)Q.spay[tid], kidx = nk + tid;
         kx1[kidx] = cx1[gj];
@@ -2325,12 +2379,18 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
     // ... and its rows should fit the staging buffer in one pass (the pivot bin adds a few rows beyond `chunk`)
     if (P.nms_stage_rows - 24 >= cap + 32 && chunk > P.nms_stage_rows - 24) chunk = P.nms_stage_rows - 24;
     // classes-in-parallel pass: available when the classes are independent and the scratch covers the label range. It
-    // takes a whole stash of at most NMS_THREADS candidates (one per thread). The stash of a scan that must reach
-    // rank W holds every entry of the W best rows above the W-th best row maximum — typically ~2 W candidates — so the
-    // first chunk then asks for fewer rows; a stash that still comes out larger goes the sorted, group-wise way.
+    // takes a whole stash of at most NMS_CH candidates. The stash of a scan that must reach rank W holds every entry of
+    // the W best rows above the W-th best row maximum — measured 1.2 W .. 1.5 W candidates — so the first chunk asks
+    // for a little under max_num rows (what is missing after it — suppression, or a stash at the low end — is made up by a
+    // further, smaller chunk); a stash that comes out too large goes the sorted, group-wise way.
     const bool cls_parallel = per_class && !generic && nlab <= NMS_CLS_LABELS && P.nms_stage_rows > 0;
     const int chunk_sorted = chunk;
-    if (cls_parallel && cap >= 64 && cap <= (NMS_THREADS * 3) / 4) chunk = (cap * 3) / 4;
+#ifndef YPP_NMS_W_NUM
+#define YPP_NMS_W_NUM 19 // rows of the first chunk = max_num * 19 / 20 (measured, 64 images each: 608^2 stash 1.5 - 1.65 W,
+#define YPP_NMS_W_DEN 20 // 1280^2 1.15 - 1.4 W, YOLOv3 640^2 1.12 - 1.45 W; at 8 / 10 and 17 / 20 some images of the last two needed a
+                         // second chunk: 35 -> 56 us per launch)
+#endif
+    if (cls_parallel && cap <= NMS_THREADS) chunk = cap < 36 ? 32 : (cap * YPP_NMS_W_NUM) / YPP_NMS_W_DEN;
     YPP_PHASE(1, b, 2);
 #ifdef YPP_PROFILE
     int prof_chunks = 0, prof_groups = 0;
@@ -2338,9 +2398,16 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
 #endif
 #pragma unroll 1
     while (processed < ntot && s_nk < cap) {
+        if (processed > 0) {
+            chunk = NMS_CH;
+            if (cls_parallel) {
+                // further chunks of the class-parallel pass: twice what is still missing (at least 128 rows)
+                const int miss = 2 * (cap - s_nk) + 64;
+                chunk = miss < 128 ? 128 : (miss > NMS_THREADS ? NMS_THREADS : miss);
+            }
+        }
         const int want = min(chunk, ntot - processed);
         const int want_sorted = processed == 0 ? min(chunk_sorted, ntot) : want;  // (the stash usually holds more than `want`)
-        chunk = NMS_CH;
         const int wc = processed + want;  // cumulative rank this chunk must reach
         u64 hi = gmax;
         int nrows = -1;
@@ -2396,14 +2463,20 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
                 staged = nms_bulk_scan(P, mat, rowkeys, nrows, lo, hi, keys, NMS_KCAP, nms_smem + P.nms_stage_off, &s_stash,
                                        stage_bar, stage_phase);
             YPP_SUB(2);
-            if (cls_parallel && staged > 0 && staged <= NMS_THREADS) {
+            if (cls_parallel && staged > 0 && staged <= NMS_CH) {
                 // the stash IS the complete set of candidates inside the window [lo, hi] — a prefix of the global order
                 // that reaches rank wc: resolve its classes in parallel, unsorted
                 stage_boxes(staged, true);
                 keys_flat = true;
                 YPP_SUB(3);
                 const int nk1 = nms_resolve_classes(staged, nlab, s_nk, cap, thr, foff, keys, cx1, cy1, cx2, cy2, car, ccl, kx1, ky1,
-                                                    kx2, ky2, kar, kcl, kkey, knext, chead, Q, ktmp);
+                                                    kx2, ky2, kar, kcl, kkey, knext, chead, Q, ktmp, lo, hi, S);
+                if (processed == 0) {
+                    YPP_SUBV(26, nrows);
+                    YPP_SUBV(27, staged);
+                    YPP_SUBV(28, Q.nkept);
+                    YPP_SUBV(29, nk1);
+                }
                 if (nk1 >= 0) {
 #ifdef YPP_PROFILE
                     if (prof_chunks == 0) {

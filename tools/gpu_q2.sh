@@ -1,0 +1,21 @@
+#!/bin/bash
+# parity tests + first-chunk statistics of several cases + A/B bench of the headline workload
+TAG=${1:-q2}
+mkdir -p gpurun_out
+true
+true
+bash tools/gpu_ph2.sh $TAG csp608_sparse csp1280_sparse v3_640_sparse csp608_dense v3_416_sparse
+show() { python -c "
+import json,sys
+try:
+    d=json.load(open(sys.argv[1])); r=d['roofline']
+    print(sys.argv[2], round(d['value']), 'img/s', round(d['ms_per_step'],4), 'ms/step lat', round(d.get('latency_ms',0),4), 'frac', round(r['frac'],3), {k: (round(v*1e3,1) if v is not None else None) for k,v in r['stage_ms'].items()}, d.get('verified'))
+except Exception as e: print(sys.argv[2], 'FAILED', e)
+" $1 $2; }
+for lib in tools/var/lib_*.so intree; do
+  n=$(basename $lib .so); if [ $lib = intree ]; then L=""; else L=$PWD/$lib; fi
+  YOLOPP_LIB=$L timeout 120 python bench.py --steps 300 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_${n}_$TAG.json 2>/dev/null; show gpurun_out/bench_${n}_$TAG.json $n
+  for w in yolov3_640_b128_sparse yolov4_1280_b128_sparse; do
+    YOLOPP_LIB=$L timeout 200 python bench.py --workload $w --steps 30 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_${w}_${n}_$TAG.json 2>/dev/null; show gpurun_out/bench_${w}_${n}_$TAG.json $w/$n
+  done
+done

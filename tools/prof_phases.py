@@ -56,6 +56,9 @@ if hasattr(lib, 'yolopp_sub_read'):
         if sub[:, z].max() > 0 and sub[:, a].max() > 0: print('    %-36s %7.0f' % (n, np.median(sub[:, z] - sub[:, a])))
 if sub[:, 20].max() > 0:
     print('select start-up (cycles from kernel stamp 0, median): ' + ', '.join('%s %d' % (n, np.median(sub[:, i] - sel[:, 0])) for i, n in ((20, 'hist cleared'), (21, 'barrier armed'), (22, 'block barrier'), (23, 'level 0 issued'), (24, 'level 1 issued'), (25, 'level 2 issued'))))
+if sub[:, 27].max() > 0:
+    for i, n in ((26, 'rows scanned'), (27, 'stash'), (28, 'kept in the chunk'), (29, 'kept after the chunk')):
+        print('    first chunk: %-24s median %5d  min %5d  max %5d' % (n, np.median(sub[:, i]), sub[:, i].min(), sub[:, i].max()))
 ssp = np.zeros((2, 64, 4, 10), np.int64)
 lib.yolopp_ssp_read.argtypes = [ctypes.c_void_p]
 lib.yolopp_ssp_read(ssp.ctypes.data_as(ctypes.c_void_p))
