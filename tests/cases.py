@@ -8,13 +8,14 @@ import numpy as np
 from yolopp import _capi as capi
 from yolopp import synth as ysynth  # noqa: F401
 from workloads import (V4_SIZES, V3_SIZES, COCO_NMS, csp_case as _csp, v3_case as _v3, build_params, ref_cfg,  # noqa: F401
-                       scale_factors, host_levels)
+                       scale_factors, host_levels, HOST_DISTS)
 
 TENCENT_SIZES = [[(8, 8)], [(16, 16)], [(32, 32)], [(64, 64)]]
 
 
 SAT = ((0.0, 0.0, 0.0), (30.0, 30.0, 30.0))        # saturated logits: sigmoid hits 0/1 exactly -> many exact ties
 MIDSPARSE = ((0.0, -3.0, -3.0), (1.0, 2.0, 2.0))
+OVERLAP = ((0.0, 0.0, 0.0), (0.25, 1.5, 1.0))       # box logits close to 0: neighbouring anchors predict overlapping boxes
 
 # name -> case. Sizes are chosen so that the CPU oracle finishes each in seconds.
 CASES = {
@@ -86,6 +87,23 @@ CASES = {
     'v3_640_sparse': _v3(640, 2, 'sparse', 47),
     # BASELINE.json config 5: 1280^2 (100 800 anchors per image: the objectness top-k runs its exact path)
     'csp1280_sparse': _csp(1280, 2, 'sparse', 48),
+    # classes-independent regime of batched_nms WITH suppression (the synthetic COCO-like inputs above suppress almost
+    # nothing: random boxes of the same class rarely overlap): tight box logits + a low IoU threshold make neighbouring
+    # anchors of a class collide, so the class-parallel NMS pass has masks to resolve, boxes kept by earlier chunks to
+    # honour (heavy: the first chunk yields far fewer than max_per_img) and classes of very different sizes
+    'csp_overlap_split': _csp(256, 2, OVERLAP, 51, C=24, nms_pre=600, nms=dict(type='nms', iou_threshold=0.45, split_thr=100)),
+    # detector-like inputs ('blobs': a few objects per image -> clusters of overlapping boxes of one class)
+    'csp_blobs': _csp(416, 2, 'blobs', 52, C=20, nms_pre=1000, max_per_img=100, objects=14,
+                      nms=dict(type='nms', iou_threshold=0.65, split_thr=1000)),
+    'csp_blobs_heavy': _csp(416, 2, 'blobs', 53, C=40, nms_pre=1000, max_per_img=300, objects=30,
+                            nms=dict(type='nms', iou_threshold=0.3, split_thr=1000)),
+    'csp608_blobs': _csp(608, 2, 'blobs', 55, objects=40),
+    # many objects of similar strength: class sizes stay small (the class-parallel pass runs) and most of the best
+    # candidates are suppressed (several chunks, boxes kept by earlier chunks suppress later ones)
+    'csp608_crowd': _csp(608, 2, 'blobs', 56, objects=160, amp=(6.0, 7.0), extent=(0.02, 0.06),
+                         nms=dict(type='nms', iou_threshold=0.45)),
+    'v3_crowd': _v3(416, 2, 'blobs', 57, C=80, objects=120, amp=(6.0, 7.0), extent=(0.02, 0.06)),
+    'v3_blobs': _v3(416, 2, 'blobs', 54, C=20, objects=20, nms=dict(type='nms', iou_threshold=0.45, split_thr=1000)),
 }
 
 # The reference's own ready-made deterministic input: tests/test_onnx/data/yolov3_head_get_bboxes.pkl with the head
@@ -100,7 +118,8 @@ PKL_CASE = dict(mode=capi.MODE_V3, batch=1, sizes=[(32, 32), (16, 16), (8, 8)], 
 GOLDEN_CASES = ['csp608_sparse', 'csp608_dense', 'csp608_dense_thr07', 'csp608_sparse_thr002', 'csp320_nopre_sparse', 'csp_odd', 'csp416_rescale',
                 'csp_saturated', 'tencent_agnostic', 'csp_nms_agnostic', 'csp_nms_offset1', 'csp_nms_maxnum',
                 'csp_force_global', 'v3_416_sparse', 'v3_416_dense', 'v3_320_mid', 'v3_rescale', 'csp640_sparse',
-                'csp_empty', 'v3_640_sparse', 'csp1280_sparse', 'csp_nms_score_thr', 'csp_nms_score_thr_split', 'csp608_gauss', 'v3_416_gauss']
+                'csp_empty', 'v3_640_sparse', 'csp1280_sparse', 'csp_nms_score_thr', 'csp_nms_score_thr_split', 'csp608_gauss', 'v3_416_gauss',
+                'csp_overlap_split', 'csp_blobs', 'csp_blobs_heavy', 'csp608_blobs', 'v3_blobs', 'csp608_crowd', 'v3_crowd']
 
 
 def asis_rel_err(ref_dets, got_dets):
@@ -140,6 +159,6 @@ STRICT_OUTLIERS = {'csp1280_sparse': 2.0e-5}
 def device_levels(case, p, device='cuda'):
     """The case's head tensors on the device: the device generator, or (host-generated distributions) an upload."""
     import torch
-    if case['dist'] == 'gauss':
+    if case['dist'] in HOST_DISTS:
         return [torch.from_numpy(x).to(device) for x in host_levels(case, p)]
     return ysynth.synth_levels(p, case['seed'], case['dist'], device=device)

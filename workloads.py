@@ -76,6 +76,8 @@ def host_levels(case, params=None):
     p = params or build_params(case)
     if case['dist'] == 'gauss':
         return gauss_levels(case, p)
+    if case['dist'] == 'blobs':
+        return blob_levels(case, p)
     mean, std = ysynth.dist_stats(case['dist'])
     na = p.num_attrib
     m = np.array([mean[0]] * 4 + [mean[1]] + [mean[2]] * (na - 5), np.float32)
@@ -85,6 +87,44 @@ def host_levels(case, params=None):
         hw = p.height[l] * p.width[l]
         x = oracle.synth_level(p.batch, p.num_anchors, na, hw, m, s, ysynth.level_seed(case['seed'], l))
         out.append(x.reshape(p.level_shape(l)))
+    return out
+
+
+HOST_DISTS = ('gauss', 'blobs')  # generated on the host and uploaded (everything else: the device generator)
+
+
+def blob_levels(case, p):
+    """Detector-like head tensors: a few "objects" per image (centre, extent, class); cells near an object get a high
+    objectness logit and a high logit for the object's class on every level and anchor, box logits stay near 0 — so
+    the best-scored candidates come in clusters of heavily overlapping boxes of the SAME class, which is what NMS
+    exists for (the i.i.d. distributions suppress next to nothing). Deterministic (numpy MT19937)."""
+    rng = np.random.RandomState(case['seed'])
+    na = p.num_attrib
+    C = na - 5
+    n_obj = case.get('objects', 12)
+    out = []
+    B = p.batch
+    img_w = p.width[0] * p.stride_w[0]
+    img_h = p.height[0] * p.stride_h[0]
+    objs = [(rng.uniform(0.1, 0.9, n_obj) * img_w, rng.uniform(0.1, 0.9, n_obj) * img_h,
+             rng.uniform(*case.get('extent', (0.04, 0.25)), n_obj) * img_w, rng.randint(0, max(C, 1), n_obj),
+             rng.uniform(*case.get('amp', (4.0, 9.0)), n_obj))
+            for _ in range(B)]
+    for l in range(p.num_levels):
+        _, _, H, W = p.level_shape(l)
+        ys, xs = np.meshgrid((np.arange(H) + 0.5) * p.stride_h[l], (np.arange(W) + 0.5) * p.stride_w[l], indexing='ij')
+        x = np.empty((B, p.num_anchors, na, H, W), np.float32)
+        x[:, :, :4] = rng.standard_normal((B, p.num_anchors, 4, H, W)).astype(np.float32) * 0.2
+        x[:, :, 4] = rng.standard_normal((B, p.num_anchors, H, W)).astype(np.float32) * 1.0 - 7.0
+        x[:, :, 5:] = rng.standard_normal((B, p.num_anchors, C, H, W)).astype(np.float32) * 1.0 - 5.0
+        for b in range(B):
+            cx, cy, ext, cls, amp = objs[b]
+            for o in range(n_obj):
+                g = np.exp(-((xs - cx[o]) ** 2 + (ys - cy[o]) ** 2) / (2.0 * ext[o] ** 2)).astype(np.float32)
+                x[b, :, 4] += (amp[o] * g)[None]
+                if C > 0:
+                    x[b, :, 5 + cls[o]] += (1.2 * amp[o] * g)[None]
+        out.append(np.ascontiguousarray(x.reshape(p.level_shape(l)), np.float32))
     return out
 
 
