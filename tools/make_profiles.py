@@ -24,6 +24,14 @@ cp(f'bench_depth1_{tag}.json', f'{pre}_bench_sparse_depth1.json')
 cp(f'bench_yolov5_640_b128_sparse_{tag}.json', f'{pre}_bench_640_b128_csp.json')
 cp(f'bench_yolov3_640_b128_sparse_{tag}.json', f'{pre}_bench_640_b128_v3.json')
 cp(f'bench_yolov4_1280_b128_sparse_{tag}.json', f'{pre}_bench_1280_b128.json')
+cp(f'bench_driver_{tag}.json', f'{pre}_bench_sparse_driver_cmdline.json')
+cp(f'bench_nhwc_{tag}.json', f'{pre}_bench_sparse_nhwc.json')
+cp(f'bench_1280_b1024_n1_{tag}.json', f'{pre}_bench_1280_b1024_n1.json')
+cp(f'mish_{tag}.json', f'{pre}_mish.json')
+cp(f'host_submit_{tag}.txt', f'{pre}_host_submit.txt')
+cp(f'timeline_640v3_{tag}.txt', f'{pre}_timeline_640_b128_v3.txt')
+cp(f'phases_608_{tag}.txt', f'{pre}_phases_608_b64.txt')
+cp(f'smoke_{tag}.log', f'{pre}_smoke.log')
 cp(f'launches_{tag}.csv', f'{pre}_launches.csv')
 cp(f'pipe_traffic_{tag}.csv', f'{pre}_traffic_in_pipeline.csv')
 cp(f'timeline_608_{tag}.txt', f'{pre}_timeline_608_b64.txt')

@@ -22,7 +22,8 @@ for ln in dis.splitlines():
         lines_of[cur_fn].append(cur_line)
 fn = [f for f in lines_of if kname in f]
 assert fn, f'no function matching {kname}: {list(lines_of)[:20]}'
-fn = fn[0]
+# (template instances: the benchmark's head is the CSP convention, MODE 0)
+fn = ([f for f in fn if 'ILi0E' in f] or fn)[0]
 out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hdr = rows[1]

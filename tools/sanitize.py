@@ -9,7 +9,7 @@ names = sys.argv[1:] or ['csp_tiny', 'csp_odd', 'csp608_sparse', 'v3_tiny_nopre'
 for name in names:
     case = cases.CASES[name]
     p = cases.build_params(case)
-    levels = yolopp.synth.synth_levels(p, case['seed'], case['dist'])
+    levels = cases.device_levels(case, p)
     sf = cases.scale_factors(case)
     out = yolopp.get_bboxes_raw(p, levels, torch.from_numpy(sf).cuda() if sf is not None else None)
     torch.cuda.synchronize()
