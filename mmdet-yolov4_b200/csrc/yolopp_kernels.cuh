@@ -1148,7 +1148,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [DEC_STAGES]: the tile streamed into stage s has landed
     uint64_t* empty = full + DEC_STAGES;                      // [DEC_STAGES]: stage s may be refilled
     int* next_it = reinterpret_cast<int*>(empty + DEC_STAGES);  // next ring iteration a consumer may claim
-    volatile int* done = next_it + 1;                           // [DEC_PWARPS]: producer p has posted its STOP
+    int* done = next_it + 1;                                    // [DEC_PWARPS]: producer p has posted its STOP
     unsigned char* stages = smem_raw + 1024;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1282,6 +1282,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                         const int q_pl = plane * NA, q_m = P.lv[l].m_off + a * hwn + hw0, q_shift = q_m & 3;
                         const int tkz = kind == 3 ? (tk | (q_shift << 4) | ((q_pl & 3) << 8)) : tk;
                         *reinterpret_cast<int4*>(dst + g.desc_off + 16) = make_int4(hwn, rbase, tkz, t);
+                        __threadfence_block();  // release: the iteration word below is what the consumers poll (acquire)
                         *reinterpret_cast<int4*>(dst + g.desc_off) = make_int4(l | (a << 8) | (kind << 16), bb, hw0, it);
                         if (kind == 2) {
                             mbar_arrive(fb);  // gather tile: nothing to stream, the consumer reads global memory itself
@@ -1339,13 +1340,14 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         const int s = it % DEC_STAGES;
         const unsigned char* stage = stages + (size_t)s * g.stage_bytes;
         {
-            const volatile int* dit = reinterpret_cast<const volatile int*>(stage + g.desc_off) + 3;
+            // (acquire loads: what the producer wrote before the iteration word / the flag is visible afterwards, and the
+            // parity wait that follows cannot be served from an older view of the barrier)
+            const int* dit = reinterpret_cast<const int*>(stage + g.desc_off) + 3;
             bool gone = false;
-            while (*dit != it) {
-                if (done[it % DEC_PWARPS]) {
+            while (ld_acquire_cta_shared(dit) != it) {
+                if (ld_acquire_cta_shared(&done[it % DEC_PWARPS])) {
                     // the STOP was posted after every real fill of this producer was armed: look once more
-                    __threadfence_block();
-                    gone = *dit != it;
+                    gone = ld_acquire_cta_shared(dit) != it;
                     break;
                 }
                 __nanosleep(YPP_SLEEP);
@@ -1353,7 +1355,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             if (gone) {
                 bool all = true;
 #pragma unroll
-                for (int pw = 0; pw < DEC_PWARPS; ++pw) all = all && done[pw] != 0;
+                for (int pw = 0; pw < DEC_PWARPS; ++pw) all = all && ld_acquire_cta_shared(&done[pw]) != 0;
                 if (all) break;
                 continue;
             }
@@ -1364,12 +1366,12 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         if (kind == DEC_KIND_STOP) {
             if (lane == 0) {
                 __threadfence_block();
-                done[it % DEC_PWARPS] = 1;
+                *reinterpret_cast<volatile int*>(&done[it % DEC_PWARPS]) = 1;
             }
             __syncwarp();
             bool all = true;
 #pragma unroll
-            for (int pw = 0; pw < DEC_PWARPS; ++pw) all = all && done[pw] != 0;
+            for (int pw = 0; pw < DEC_PWARPS; ++pw) all = all && ld_acquire_cta_shared(&done[pw]) != 0;
             if (all) break;
             continue;
         }
@@ -2051,6 +2053,7 @@ __device__ __noinline__ int nms_resolve_classes(int m, int nlab, int nk, int cap
         __syncthreads();
         if (pb < 0) return -1;  // (-2: too many kept candidates share the pivot bin)
     }
+    __syncthreads();  // (every thread has read the count)
     if (tid == 0) Q.nkept = 0;
     __syncthreads();
 #pragma unroll 1
