@@ -216,6 +216,8 @@ typedef struct yolopp_plan_info {
     int64_t ldg_bytes_per_image; /* ... by the other decode kernels (dense admission, > 256 attributes; NHWC: the
                                     admitted rows, 4*(5+C)*R) */
     int64_t workspace_bytes;
+    int32_t decode_tile_positions; /* positions per tile of the TMA decode kernel (64 or 32; 0: kernel not launched) */
+    int32_t reserved_;
 } yolopp_plan_info;
 int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info);
 

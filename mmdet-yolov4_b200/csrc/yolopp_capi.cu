@@ -213,10 +213,29 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
             if (sg.has_topk && (long long)sg.k * 4 <= sg.N && d.lv[l].HW % 4 != 0) d.dec_quad = 1;
         }
 #endif
-        StageGeom geom = stage_geom(NA, d.dec_quad);
-        plan->dec_smem = 1024 /*alignment slack*/ + 1024 /*barriers*/ + (size_t)DEC_STAGES * geom.stage_bytes;
+        // tile size of the persistent kernel: 32 positions x 8 stages where a 64-position tile would hold 2 or more
+        // admitted anchors on average (the in-order ring then stalls on the tiles with many), 64 x 4 where tiles are
+        // mostly empty and the per-tile costs dominate (see dec_stages_of). Quad-row tiles exist for 64 only.
+        {
+            double adm = 0.0, pos = 0.0;
+            for (int l = 0; l < d.L; ++l) {
+                const SegDev& sg = d.seg[d.lv[l].seg];
+                if (!(sg.has_topk && (long long)sg.k * 4 <= sg.N)) continue;
+                adm += (double)sg.k * d.lv[l].HW * d.A / sg.N;  // the level's share of its segment's top-k (expected)
+                pos += (double)d.lv[l].HW * d.A;
+            }
+            d.tile_t = (!d.dec_quad && pos > 0.0 && 64.0 * adm / pos >= 2.0) ? 32 : 64;
+#ifdef YPP_TILE64
+            d.tile_t = 64;
+#endif
+#ifdef YPP_TILE32
+            if (!d.dec_quad) d.tile_t = 32;
+#endif
+        }
+        StageGeom geom = stage_geom(NA, d.dec_quad, d.tile_t);
+        plan->dec_smem = 1024 /*alignment slack*/ + 1024 /*barriers*/ + (size_t)dec_stages_of(d.tile_t) * geom.stage_bytes;
         tma_fits = tma_fits && plan->dec_smem <= 200 * 1024;
-        plan->dec_ctas_per_sm = plan->dec_smem <= 110 * 1024 ? 2 : 1;
+        plan->dec_ctas_per_sm = 2 * (plan->dec_smem + 1024) <= 233472 ? 2 : 1;  // (228 KB per SM, 1 KB reserved per CTA)
         // persistent decode kernel: sparse-admission levels — TMA tiles where the plane stride is 16-byte aligned,
         // gather tiles where it is not (quad-row TMA tiles in the -DYPP_QUAD build: measured slower)
         for (int l = 0; l < d.L; ++l) {
@@ -242,7 +261,7 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
                 const bool mine = pi == 0 ? (lv.use_tma == 2 || lv.use_tma == 3) : lv.use_tma == 1;
 #endif
                 if (!mine) continue;
-                lv.tpp = (lv.HW + TILE_T - 1) / TILE_T;
+                lv.tpp = (lv.HW + d.tile_t - 1) / d.tile_t;
                 lv.tile0 = tma_tiles;
                 long long t = (long long)lv.tpp * d.B * d.A;
                 CHECK_ARG(tma_tiles + t < (1ll << 30));
@@ -362,8 +381,10 @@ DeviceInfo device_info() {
         return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
     };
     cudaError_t e = opt_in((const void*)select_kernel);
-    if (e == cudaSuccess) e = opt_in((const void*)decode_tma_kernel<0>);
-    if (e == cudaSuccess) e = opt_in((const void*)decode_tma_kernel<1>);
+    if (e == cudaSuccess) e = opt_in((const void*)decode_tma_kernel<0, 64>);
+    if (e == cudaSuccess) e = opt_in((const void*)decode_tma_kernel<1, 64>);
+    if (e == cudaSuccess) e = opt_in((const void*)decode_tma_kernel<0, 32>);
+    if (e == cudaSuccess) e = opt_in((const void*)decode_tma_kernel<1, 32>);
     if (e == cudaSuccess) e = opt_in((const void*)nms_image_kernel);
     if (e != cudaSuccess) {
         di.rc = cuda_rc(e);
@@ -464,7 +485,7 @@ int prepare(const yolopp_params* p, const float* const* level_ptrs, const float*
         EncodeTiledFn enc = get_encode_fn();
         if (!enc) return YOLOPP_E_NO_DEVICE;
         memset(&pl->maps, 0, sizeof(pl->maps));
-        const StageGeom geom = stage_geom(d.NA, d.dec_quad);
+        const StageGeom geom = stage_geom(d.NA, d.dec_quad, d.tile_t);
         for (int l = 0; l < d.L; ++l) {
             const LevelDev& lv = d.lv[l];
             CUresult r = CUDA_SUCCESS;
@@ -536,10 +557,13 @@ int launch(const yolopp_plan* pl, cudaStream_t stream, void* const* events, int 
     }
     YPP_MARK();  // 1: start of decode (persistent TMA kernel / NHWC rows kernel)
     if (d.tma_tiles > 0) {
-        if (d.mode == YOLOPP_MODE_CSP)
-            decode_tma_kernel<0><<<pl->dec_grid, DEC_THREADS, plan.dec_smem, stream>>>(d, pl->maps);
-        else
-            decode_tma_kernel<1><<<pl->dec_grid, DEC_THREADS, plan.dec_smem, stream>>>(d, pl->maps);
+        if (d.mode == YOLOPP_MODE_CSP) {
+            if (d.tile_t == 64) decode_tma_kernel<0, 64><<<pl->dec_grid, DEC_THREADS, plan.dec_smem, stream>>>(d, pl->maps);
+            else decode_tma_kernel<0, 32><<<pl->dec_grid, DEC_THREADS, plan.dec_smem, stream>>>(d, pl->maps);
+        } else {
+            if (d.tile_t == 64) decode_tma_kernel<1, 64><<<pl->dec_grid, DEC_THREADS, plan.dec_smem, stream>>>(d, pl->maps);
+            else decode_tma_kernel<1, 32><<<pl->dec_grid, DEC_THREADS, plan.dec_smem, stream>>>(d, pl->maps);
+        }
         if ((e = cudaGetLastError()) != cudaSuccess) return cuda_rc(e);
     }
     if (d.nhwc) {
@@ -712,6 +736,7 @@ int yolopp_describe(const yolopp_params* p, yolopp_plan_info* info) {
     info->dense_tiles = d.dense_tiles;
     info->decode_smem_bytes = (int32_t)plan.dec_smem;
     info->decode_ctas_per_sm = plan.dec_ctas_per_sm;
+    info->decode_tile_positions = d.tma_tiles > 0 ? d.tile_t : 0;
     info->workspace_bytes = (int64_t)plan.total;
     for (int l = 0; l < d.L; ++l) {
         int64_t bytes = (int64_t)4 * d.A * d.NA * d.lv[l].HW;

@@ -16,9 +16,14 @@ constexpr int MAXL = 8;
 constexpr int MAXA = 8;
 constexpr uint32_t RANK_INVALID = 0xFFFFFFFFu;
 
-constexpr int TILE_T = 64;       // positions per TMA tile = two 32-wide boxes with 128-byte rows (SWIZZLE_128B)
+// Positions per TMA tile: 64 (two 32-wide boxes with 128-byte rows, SWIZZLE_128B; 4 stages) or 32 (one box; 8 stages),
+// chosen per plan (template parameter of the decode kernel). The ring is in-order: a tile with many admitted anchors
+// holds its stage through several register batches and everything behind it waits; half-size tiles in twice the
+// stages keep the same bytes in flight but halve what a slow tile blocks (608^2 b64: decode 100.2 -> 94.7 us; YOLOv3
+// 640^2: 284 -> 237 us). Where hardly any tile holds an admitted anchor (1280^2: 1 % of the positions) the per-tile
+// costs dominate instead and 64-position tiles stay ahead (663 vs 712 us).
+__host__ __device__ constexpr int dec_stages_of(int tile_t) { return tile_t == 64 ? 4 : 8; }
 constexpr int TILE_SUB = 32;     // positions per box
-constexpr int DEC_STAGES = 4;    // TMA pipeline depth
 constexpr int DEC_PWARPS = 2;    // producer warps per CTA: warp p issues the tiles of iterations it == p (mod 2)
 #ifndef YPP_CWARPS
 #define YPP_CWARPS 8
@@ -102,6 +107,7 @@ struct DevParams {
     int nms_stage_off, nms_stage_rows;  // staging ring of the candidate scan: NMS_STAGES x nms_stage_rows matrix rows
     int tma_tiles, ldg_blocks, dense_tiles;
     int dec_quad;            // some level is streamed as quad-row tiles (stage geometry)
+    int tile_t;              // positions per tile of the persistent decode kernel (64 or 32)
     unsigned* tile_ctr;      // workspace: next unclaimed position of the decode kernel's tile sequence (set by select_kernel)
     unsigned dec_first;      // positions [0, dec_first) of the tile sequence are dealt round-robin, the rest is claimed
     LevelDev lv[MAXL];
@@ -1034,23 +1040,33 @@ struct StageGeom {
     uint32_t desc_off;     // tile descriptor written by the producer
     uint32_t stage_bytes;
 };
-constexpr uint32_t RANK_ROW_BYTES = (TILE_T + 4) * 4u;  // quad-row tiles fetch the 16-byte aligned superset
+constexpr uint32_t RANK_ROW_BYTES = (64 + 4) * 4u;  // (64-position tiles; quad-row tiles fetch the 16-byte aligned superset)
 // A TMA box must START on a 16-byte boundary of the innermost dimension (an unaligned start coordinate raises an
 // illegal-instruction fault on sm_100), so a quad-row box fetches the aligned superset of its 64 positions: 68
 // floats per row, not swizzled (the 128-byte swizzle would cap the row at 32 floats).
-constexpr int QUAD_W = TILE_T + 4;
+constexpr int QUAD_W = 64 + 4;  // (quad-row tiles exist with 64-position tiles only)
 constexpr uint32_t QUAD_ROW_BYTES = QUAD_W * 4u;
-__host__ __device__ inline StageGeom stage_geom(int NA, int quad) {
+__host__ __device__ inline StageGeom stage_geom(int NA, int quad, int tile_t) {
     StageGeom g;
     g.sub_bytes = ((uint32_t)NA * 128u + 1023u) & ~1023u;
     // NA consecutive planes starting at plane p0 live in rows p0/4 .. (p0 + NA - 1)/4 of the four-plane view
     g.quad_rows = (((uint32_t)NA + 2u) >> 2) + 1u;
     g.quad_box = (g.quad_rows * QUAD_ROW_BYTES + 1023u) & ~1023u;
-    uint32_t data = 2u * g.sub_bytes;
+    uint32_t data = (uint32_t)(tile_t / TILE_SUB) * g.sub_bytes;
     if (quad && 4u * g.quad_box > data) data = 4u * g.quad_box;
     g.rank_off = data;
     g.desc_off = g.rank_off + ((RANK_ROW_BYTES + 31u) & ~31u);
     g.stage_bytes = (g.desc_off + 32u + 1023u) & ~1023u;
+#ifndef YPP_NO_PACK
+    // the rank row and the descriptor fit into the padding behind the last box (NA * 128 bytes are written, the box
+    // area is rounded up to 1024): no extra kilobyte per stage
+    const uint32_t used = data - g.sub_bytes + (((uint32_t)NA * 128u + 31u) & ~31u);
+    if (!quad && used + ((RANK_ROW_BYTES + 31u) & ~31u) + 32u <= data) {
+        g.rank_off = used;
+        g.desc_off = g.rank_off + ((RANK_ROW_BYTES + 31u) & ~31u);
+        g.stage_bytes = data;
+    }
+#endif
     return g;
 }
 // logit of attribute k at position p of the tile (SWIZZLE_128B: 16-byte chunk index XOR (row mod 8))
@@ -1136,14 +1152,15 @@ __device__ __forceinline__ void stage_release_fence() { fence_proxy_async(); }
 
 constexpr int DEC_KIND_STOP = 7;  // stage header: the producer has run out of tiles (tile kinds are 1, 2, 3)
 
-template <int MODE>
+template <int MODE, int TILE_T>
 __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid_constant__ DevParams P,
                                                                   const __grid_constant__ TmapPack maps) {
+    constexpr int DEC_STAGES = dec_stages_of(TILE_T);
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned base (swizzle) — the launch reserves 1 KB of slack
     unsigned char* smem_raw = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     const int NA = P.NA;
-    const StageGeom g = stage_geom(NA, P.dec_quad);
+    const StageGeom g = stage_geom(NA, P.dec_quad, TILE_T);
     const uint32_t box_bytes = (uint32_t)NA * 128u;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);  // [DEC_STAGES]: the tile streamed into stage s has landed
     uint64_t* empty = full + DEC_STAGES;                      // [DEC_STAGES]: stage s may be refilled
@@ -1300,7 +1317,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
 #endif
                         } else {
                             const bool topk = tk != 0;
-                            const bool two = hw0 + TILE_SUB < hwn;  // the second box is not entirely out of bounds
+                            const bool two = TILE_T > TILE_SUB && hw0 + TILE_SUB < hwn;  // the second box is not entirely out of bounds
                             mbar_arrive_expect_tx(fb, box_bytes * (two ? 2u : 1u) + (topk ? TILE_T * 4u : 0u));
                             // No L2 eviction hint on purpose: plane rows are in general not 128-byte aligned, so
                             // neighbouring tiles share the lines at their common edge; with evict_first the second
@@ -1392,7 +1409,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             const float* slab = lv.ptr + (size_t)(b * P.A + a) * NA * lv.HW;
             const size_t HW = (size_t)lv.HW;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < TILE_T / 32; ++h) {
                 const int hw = hw0 + h * 32 + lane;
                 uint32_t r = RANK_INVALID;
                 if (hw < lv.HW) r = row_of(P, lv, b, a, hw);
@@ -1438,7 +1455,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
         {
             const int p0 = lane, p1 = lane + 32;
             if (hw0 + p0 < HWn) r_lo = topk ? rk[p0] : (uint32_t)(rbase + (hw0 + p0) * P.A);
-            if (hw0 + p1 < HWn) r_hi = topk ? rk[p1] : (uint32_t)(rbase + (hw0 + p1) * P.A);
+            if (TILE_T > 32 && hw0 + p1 < HWn) r_hi = topk ? rk[p1] : (uint32_t)(rbase + (hw0 + p1) * P.A);
         }
         uint32_t m_lo = __ballot_sync(0xffffffffu, r_lo != RANK_INVALID);
         uint32_t m_hi = __ballot_sync(0xffffffffu, r_hi != RANK_INVALID);

@@ -117,6 +117,8 @@ class YoloppPlanInfo(ctypes.Structure):
         ('tma_bytes_per_image', c_int64),
         ('ldg_bytes_per_image', c_int64),
         ('workspace_bytes', c_int64),
+        ('decode_tile_positions', c_int32),
+        ('reserved_', c_int32),
     ]
 
 

@@ -38,7 +38,7 @@ cp(f'timeline_608_{tag}.txt', f'{pre}_timeline_608_b64.txt')
 cp(f'timeline_640_{tag}.txt', f'{pre}_timeline_640_b128.txt')
 cp(f'stock_gpu_{tag}.txt', f'{pre}_stock_gpu.txt')
 cp(f'pytest_gpu_{tag}.log', f'{pre}_pytest_gpu.log')
-for tool in ('memcheck', 'synccheck'):
+for tool in ('memcheck', 'synccheck', 'racecheck'):
     cp(f'sanitizer_{tool}_{tag}.txt', f'{pre}_sanitizer_{tool}.txt')
 
 # per-kernel ncu summaries + hot lines

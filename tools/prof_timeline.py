@@ -42,7 +42,7 @@ def ns(col):
 iss, land, rel, done = ns(1), ns(2), ns(3), ns(4)
 print('first issue %.2f us, first landed %.2f us, last issue %.2f, last landed %.2f us, last done %.2f us' % (iss.min() / 1e3, land.min() / 1e3, iss.max() / 1e3, land.max() / 1e3, done.max() / 1e3))
 NA = p.num_attrib
-tile_bytes = NA * 64 * 4
+tile_bytes = NA * (s.info.decode_tile_positions or 64) * 4
 end = done.max()
 edges = np.arange(0, end + 4000, 4000)
 h, _ = np.histogram(land, edges)

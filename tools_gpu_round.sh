@@ -33,6 +33,7 @@ timeout 100 python tools/prof_phases.py csp608_sparse 64 > gpurun_out/phases_608
 for tool in memcheck synccheck; do
   timeout 400 compute-sanitizer --tool $tool python tools/sanitize.py csp_tiny csp_odd csp608_sparse v3_tiny_nopre csp608_crowd v3_crowd csp_blobs_heavy 2>&1 | grep -E "ERROR SUMMARY|count|Error" | sort | uniq -c | head -20 > gpurun_out/sanitizer_${tool}_$TAG.txt
 done
+timeout 500 compute-sanitizer --tool racecheck --racecheck-report analysis python tools/sanitize.py csp608_sparse csp608_crowd v3_crowd csp_blobs_heavy csp_tiny v3_tiny_nopre csp_force_global 2>&1 | grep -E "RACECHECK SUMMARY|Race reported|and (Read|Write)|count ok|MISMATCH|kept" | sed -E "s/\(int, int.*\)\+/(...)+/" | sort | uniq -c | sort -rn | head -40 > gpurun_out/sanitizer_racecheck_$TAG.txt
 # launch list of the bench command (per-launch durations, serialised)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 3 --warmup 3 $Q --no-verify > /dev/null 2>> gpurun_out/bench_$TAG.err
 # DRAM traffic of the three kernels in their natural cache state (single pass, no replay)
