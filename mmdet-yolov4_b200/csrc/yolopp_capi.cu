@@ -261,7 +261,8 @@ bool make_plan(const yolopp_params* p, Plan* plan) {
                 const bool mine = pi == 0 ? (lv.use_tma == 2 || lv.use_tma == 3) : lv.use_tma == 1;
 #endif
                 if (!mine) continue;
-                lv.tpp = (lv.HW + d.tile_t - 1) / d.tile_t;
+                lv.tile_pos = lv.use_tma == 2 ? GATHER_T : d.tile_t;  // (a level that turns into a gather level later —
+                lv.tpp = (lv.HW + lv.tile_pos - 1) / lv.tile_pos;     //  unaligned pointer — keeps the kernel's tile size)
                 lv.tile0 = tma_tiles;
                 long long t = (long long)lv.tpp * d.B * d.A;
                 CHECK_ARG(tma_tiles + t < (1ll << 30));

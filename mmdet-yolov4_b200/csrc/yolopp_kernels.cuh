@@ -24,6 +24,14 @@ constexpr uint32_t RANK_INVALID = 0xFFFFFFFFu;
 // costs dominate instead and 64-position tiles stay ahead (663 vs 712 us).
 __host__ __device__ constexpr int dec_stages_of(int tile_t) { return tile_t == 64 ? 4 : 8; }
 constexpr int TILE_SUB = 32;     // positions per box
+// positions per GATHER tile (levels without a tensor map): nothing is streamed for them, a tile is just the unit of work
+// one consumer warp takes — and keeps for several DRAM round trips per admitted anchor. They sit at the head of the tile
+// sequence, so their number per CTA decides how many consumer warps are tied up while the ring fills: 8 per CTA
+// (32 positions) tie up every warp for ~9 us; measured decode 95.7 / 94.9 / 96.4 / 117 us at 32 / 64 / 128 / 256.
+#ifndef YPP_GATHER_T
+#define YPP_GATHER_T 64
+#endif
+constexpr int GATHER_T = YPP_GATHER_T;
 constexpr int DEC_PWARPS = 2;    // producer warps per CTA: warp p issues the tiles of iterations it == p (mod 2)
 #ifndef YPP_CWARPS
 #define YPP_CWARPS 8
@@ -59,6 +67,7 @@ struct LevelDev {
     int qrows;    // use_tma == 3: rows of the quad-row view = floor(B * A * NA / 4)
     int tile0;    // first tile id of this level in its kernel's tile enumeration
     int tpp;      // tiles per plane
+    int tile_pos; // positions per tile on this level: the kernel's tile size, or GATHER_T on a gathered level
     float sx, sy; // anchor-generator strides
     float cstride;// coder stride
     float inv_w;  // 1 / W (position -> (x, y) without an integer division)
@@ -1260,7 +1269,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
                 const int loc = t - lv.tile0;
                 d_t = t;
                 d_plane = loc / lv.tpp;  // b*A + a
-                d_hw0 = (loc - d_plane * lv.tpp) * TILE_T;
+                d_hw0 = (loc - d_plane * lv.tpp) * lv.tile_pos;
                 d_b = d_plane / P.A;
                 d_a = d_plane - d_b * P.A;
                 d_hw = lv.HW;
@@ -1408,8 +1417,8 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_tma_kernel(const __grid
             const SegDev& sg = P.seg[lv.seg];
             const float* slab = lv.ptr + (size_t)(b * P.A + a) * NA * lv.HW;
             const size_t HW = (size_t)lv.HW;
-#pragma unroll
-            for (int h = 0; h < TILE_T / 32; ++h) {
+#pragma unroll 1
+            for (int h = 0; h < lv.tile_pos / 32; ++h) {
                 const int hw = hw0 + h * 32 + lane;
                 uint32_t r = RANK_INVALID;
                 if (hw < lv.HW) r = row_of(P, lv, b, a, hw);
