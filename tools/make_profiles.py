@@ -62,7 +62,7 @@ for k, short in (('decode_tma', 'decode'), ('nms_image', 'nms'), ('select_kernel
                 vals[parts[0]] = int(v * {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}.get(unit, 1))
         if len(vals) == 2:
             rd, wr = vals['dram__bytes_read.sum'], vals['dram__bytes_write.sum']
-            json.dump(dict(kernel='decode_tma_kernel<0>',
+            json.dump(dict(kernel='decode_tma_kernel<0, 32>',
                            source=f'profiles/{pre}_decode_summary.txt (ncu --set full --clock-control none, one launch, 608^2 batch 64 sparse)',
                            dram_bytes_read=rd, dram_bytes_write=wr, dram_bytes_per_launch=rd + wr,
                            algorithmic_bytes_per_launch=494887680,
