@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define YOLOPP_ABI_VERSION 2
+#define YOLOPP_ABI_VERSION 3
 
 #define YOLOPP_MAX_LEVELS 8
 #define YOLOPP_MAX_ANCHORS 8      /* base anchors per level (mmdet asserts the same count on every level) */

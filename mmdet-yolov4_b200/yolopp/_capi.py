@@ -9,7 +9,7 @@ from ctypes import c_float, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 import numpy as np
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LEVELS = 8
 MAX_ANCHORS = 8
 MAX_CLASSES = 4096
