@@ -189,6 +189,22 @@ def test_plans_for_layouts_and_large_nms_pre():
     assert capi.describe(p1280).tma_level_mask == 0b111
 
 
+def test_decode_tile_size_follows_the_admitted_density():
+    """The persistent decode kernel streams 32-position tiles in 8 stages where a 64-position tile would hold two or more
+    admitted anchors on average (608^2: 2.8, YOLOv3 640^2: 5.3), 64-position tiles in 4 stages where tiles are mostly empty
+    (1280^2: 0.6); either way two CTAs fit an SM, and the tile count follows (the gathered 19^2 level keeps 64)."""
+    i608 = capi.describe(cases.build_params(dict(cases.CASES['csp608_sparse'], batch=64)))
+    assert i608.decode_tile_positions == 32 and i608.decode_ctas_per_sm == 2
+    assert i608.tma_tiles == 64 * 3 * (-(-76 * 76 // 32) + -(-38 * 38 // 32) + -(-19 * 19 // 64))
+    i1280 = capi.describe(cases.build_params(dict(cases.CASES['csp1280_sparse'], batch=8)))
+    assert i1280.decode_tile_positions == 64 and i1280.decode_ctas_per_sm == 2
+    iv3 = capi.describe(cases.build_params(dict(cases.CASES['v3_640_sparse'], batch=8)))
+    assert iv3.decode_tile_positions == 32 and iv3.dense_tiles > 0
+    nh = cases.build_params(dict(cases.CASES['csp608_sparse'], batch=2))
+    nh.layout = capi.LAYOUT_NHWC
+    assert capi.describe(nh).decode_tile_positions == 0  # kernel not launched
+
+
 def test_plan_and_stage_entries_reject_bad_calls_without_a_device():
     lib = capi.load_library()
     p = cases.build_params(cases.CASES['csp_tiny'])
