@@ -2492,7 +2492,7 @@ __device__ __forceinline__ void nms_image_body(const DevParams& P, const int b, 
                 staged = nms_bulk_scan(P, mat, rowkeys, nrows, lo, hi, keys, NMS_KCAP, nms_smem + P.nms_stage_off, &s_stash,
                                        stage_bar, stage_phase);
             YPP_SUB(2);
-            if (cls_parallel && staged > 0 && staged <= NMS_CH) {
+            if (cls_parallel && staged > 0 && staged <= NMS_CH && cap - s_nk <= NMS_THREADS) {
                 // the stash IS the complete set of candidates inside the window [lo, hi] — a prefix of the global order
                 // that reaches rank wc: resolve its classes in parallel, unsorted
                 stage_boxes(staged, true);

@@ -92,6 +92,9 @@ CASES = {
     # anchors of a class collide, so the class-parallel NMS pass has masks to resolve, boxes kept by earlier chunks to
     # honour (heavy: the first chunk yields far fewer than max_per_img) and classes of very different sizes
     'csp_overlap_split': _csp(256, 2, OVERLAP, 51, C=24, nms_pre=600, nms=dict(type='nms', iou_threshold=0.45, split_thr=100)),
+    # the same regime with max_per_img beyond what the class-parallel pass sorts (512 kept per chunk): group-wise pass
+    'csp_split_cap600': _csp(256, 2, OVERLAP, 58, C=24, nms_pre=1000, max_per_img=600,
+                             nms=dict(type='nms', iou_threshold=0.45, split_thr=100)),
     # detector-like inputs ('blobs': a few objects per image -> clusters of overlapping boxes of one class)
     'csp_blobs': _csp(416, 2, 'blobs', 52, C=20, nms_pre=1000, max_per_img=100, objects=14,
                       nms=dict(type='nms', iou_threshold=0.65, split_thr=1000)),
@@ -119,7 +122,7 @@ GOLDEN_CASES = ['csp608_sparse', 'csp608_dense', 'csp608_dense_thr07', 'csp608_s
                 'csp_saturated', 'tencent_agnostic', 'csp_nms_agnostic', 'csp_nms_offset1', 'csp_nms_maxnum',
                 'csp_force_global', 'v3_416_sparse', 'v3_416_dense', 'v3_320_mid', 'v3_rescale', 'csp640_sparse',
                 'csp_empty', 'v3_640_sparse', 'csp1280_sparse', 'csp_nms_score_thr', 'csp_nms_score_thr_split', 'csp608_gauss', 'v3_416_gauss',
-                'csp_overlap_split', 'csp_blobs', 'csp_blobs_heavy', 'csp608_blobs', 'v3_blobs', 'csp608_crowd', 'v3_crowd']
+                'csp_overlap_split', 'csp_split_cap600', 'csp_blobs', 'csp_blobs_heavy', 'csp608_blobs', 'v3_blobs', 'csp608_crowd', 'v3_crowd']
 
 
 def asis_rel_err(ref_dets, got_dets):
