@@ -1,12 +1,16 @@
 // yolopp_kernels.cuh — the kernels of the post-processing path (sm_100a). Included by yolopp_capi.cu.
 //
-//   K0 select_kernel      objectness top-k per (image, segment): adaptive 2-pass select + smem sort -> rank map
-//   K1 decode_tma_kernel  TMA-streamed fused decode + score + threshold -> dense (row, class) score matrix
-//      decode_ldg_kernel  same semantics with plain coalesced loads (HW % 4 != 0 levels, dense admission)
-//   K2 nms_image_kernel   per image: candidates visited in global (score desc, flat index asc) order, fetched in
-//                         sorted chunks by the adaptive select; greedy NMS against a kept list with the
-//                         reference's regime rule (n < split_thr: one problem over class-offset boxes;
-//                         else: classes independent); stops at max_per_img kept and writes the outputs.
+//   K0 select_kernel      objectness top-k per (image, segment) on the raw logits: staged in shared memory, sampled
+//                         histogram cut, sort of the survivors -> rank map (exact fallback over 64-bit keys)
+//   K1 decode_tma_kernel  persistent, TMA-streamed fused decode + score + threshold -> dense (row, class) score matrix
+//      decode_dense / decode_rows / decode_ldg_kernel   the same semantics for densely admitted levels, channels-last
+//                         tensors, and levels with more than 256 attributes
+//   K2 nms_image_kernel   per image: the candidates that can reach the first max_per_img are fetched as a prefix of the
+//                         global (score desc, flat index asc) order (row-maximum bound + bulk-copied matrix rows);
+//                         greedy NMS with the reference's regime rule — n >= split_thr: classes independent, resolved
+//                         in parallel (pair masks per class), only the kept boxes sorted; n < split_thr: one problem
+//                         over class-offset boxes, walked in sorted groups of 64; stops at max_per_img kept, writes
+//                         the outputs and their grouping by label.
 #pragma once
 #include "yolopp_device.cuh"
 
@@ -113,7 +117,7 @@ struct DevParams {
     int sel_stride;// 1: whole segments are staged; 2^j: every 2^j-th logit is staged (sample), the rest is streamed
     int nhwc;      // level tensors are channels-last memory (B, H, W, A*NA): row-driven decode, no rank map
     int nms_rowkeys_off;  // byte offset of the sorted row-best keys inside the NMS kernel's dynamic smem
-    int nms_stage_off, nms_stage_rows;  // staging ring of the candidate scan: NMS_STAGES x nms_stage_rows matrix rows
+    int nms_stage_off, nms_stage_rows;  // staging buffer of the candidate scan: nms_stage_rows score-matrix rows
     int tma_tiles, ldg_blocks, dense_tiles;
     int dec_quad;            // some level is streamed as quad-row tiles (stage geometry)
     int tile_t;              // positions per tile of the persistent decode kernel (64 or 32)
@@ -1128,13 +1132,13 @@ __device__ __noinline__ void consume_quad_tile(const DevParams& P, const unsigne
 }
 #endif
 
-// Persistent, warp-specialised. Warp 0 is the producer: its 32 lanes work out the coordinates of the CTA's next
-// 32 tiles in parallel (the level lookup and the integer divisions are the long latency chain of a tile), then
-// lane 0 streams each (NA x 64) tile of the raw head tensor into a 4-stage shared-memory ring as two
-// 128B-swizzled TMA boxes (L2 evict-first: the tensor is read exactly once) plus the tile's rank-map row (1-D
-// bulk copy) and a 16-byte tile descriptor. 8 consumer warps take whole tiles round-robin: a consumer pulls the
-// logits of the tile's admitted anchors into registers, hands the stage straight back to the producer, and
-// only then does the math (lanes over classes), so a stage is held for a few hundred cycles.
+// Persistent, warp-specialised. Two producer warps: a warp's 32 lanes work out the coordinates of its next 32 tiles
+// in parallel (the level lookup and the integer divisions are the long latency chain of a tile), then lane 0 streams
+// each (NA x TILE_T) tile of the raw head tensor into the shared-memory ring — 8 stages of one 128B-swizzled TMA box
+// (TILE_T = 32) or 4 stages of two (TILE_T = 64), no L2 eviction hint — plus the tile's rank-map row (1-D bulk copy)
+// and a 32-byte tile descriptor. 8 consumer warps claim whole tiles in order: a consumer pulls the logits of up to
+// four admitted anchors into registers, hands the stage back to the producer before the last batch's math, and only
+// then does the math (lanes over classes), so a stage is held for a few hundred cycles unless the tile is heavy.
 #ifdef YPP_PROFILE
 // per-tile timestamps (profiling build only): [tile][0..5] = issue start, issued, landed, released, done, smid
 __device__ long long g_prof[(1 << 16) * 8];
