@@ -11,7 +11,7 @@ from yolopp.ops import Session
 lib = _capi.load_library()
 case = dict(cases.CASES[sys.argv[1] if len(sys.argv) > 1 else 'csp608_sparse'], batch=int(sys.argv[2]) if len(sys.argv) > 2 else 64)
 p = cases.build_params(case)
-levels = yolopp.synth.synth_levels(p, 11, 'sparse')
+levels = cases.device_levels(case, p) if case['dist'] in cases.HOST_DISTS else yolopp.synth.synth_levels(p, 11, case['dist'] if isinstance(case['dist'], (str, tuple)) else 'sparse')
 s = Session(p)
 for _ in range(4): s.run(levels)
 torch.cuda.synchronize()
