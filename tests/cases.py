@@ -106,6 +106,12 @@ CASES = {
     'csp608_crowd': _csp(608, 2, 'blobs', 56, objects=160, amp=(6.0, 7.0), extent=(0.02, 0.06),
                          nms=dict(type='nms', iou_threshold=0.45)),
     'v3_crowd': _v3(416, 2, 'blobs', 57, C=80, objects=120, amp=(6.0, 7.0), extent=(0.02, 0.06)),
+    # small classes (<= 64 candidates per chunk) with heavy suppression: the class-parallel pass end to end, the second
+    # one over two chunks (538 candidates visited for 300 kept)
+    'csp416_crowd': _csp(416, 2, 'blobs', 61, objects=260, amp=(6.0, 7.0), extent=(0.015, 0.04),
+                         nms=dict(type='nms', iou_threshold=0.45)),
+    'csp608_crowd_iou03': _csp(608, 2, 'blobs', 62, objects=400, amp=(6.2, 6.8), extent=(0.012, 0.03),
+                               nms=dict(type='nms', iou_threshold=0.3)),
     'v3_blobs': _v3(416, 2, 'blobs', 54, C=20, objects=20, nms=dict(type='nms', iou_threshold=0.45, split_thr=1000)),
 }
 
@@ -122,7 +128,7 @@ GOLDEN_CASES = ['csp608_sparse', 'csp608_dense', 'csp608_dense_thr07', 'csp608_s
                 'csp_saturated', 'tencent_agnostic', 'csp_nms_agnostic', 'csp_nms_offset1', 'csp_nms_maxnum',
                 'csp_force_global', 'v3_416_sparse', 'v3_416_dense', 'v3_320_mid', 'v3_rescale', 'csp640_sparse',
                 'csp_empty', 'v3_640_sparse', 'csp1280_sparse', 'csp_nms_score_thr', 'csp_nms_score_thr_split', 'csp608_gauss', 'v3_416_gauss',
-                'csp_overlap_split', 'csp_split_cap600', 'csp_blobs', 'csp_blobs_heavy', 'csp608_blobs', 'v3_blobs', 'csp608_crowd', 'v3_crowd']
+                'csp_overlap_split', 'csp_split_cap600', 'csp_blobs', 'csp_blobs_heavy', 'csp608_blobs', 'v3_blobs', 'csp608_crowd', 'v3_crowd', 'csp416_crowd', 'csp608_crowd_iou03']
 
 
 def asis_rel_err(ref_dets, got_dets):
