@@ -30,6 +30,26 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(capi.YoloppParams) == 4 * (7 + 5 * 8 + 8 * 8 * 4 + 11 + 7)
 
 
+def test_header_struct_layouts_match_the_ctypes_mirrors(tmp_path):
+    """include/yolopp.h compiled as plain C (the header is the boundary a cgo / JNI / ctypes binding reads): sizes and
+    a few member offsets of the three structs must equal the Python mirrors the tests and the shim go through."""
+    import subprocess
+    src = tmp_path / 'layout.c'
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "yolopp.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(yolopp_params), sizeof(yolopp_outputs), sizeof(yolopp_plan_info),\n'
+                   '         offsetof(yolopp_params, base_anchors), offsetof(yolopp_outputs, cls_offsets),\n'
+                   '         offsetof(yolopp_plan_info, workspace_bytes), offsetof(yolopp_plan_info, decode_tile_positions));\n'
+                   '  return YOLOPP_ABI_VERSION == ' + str(capi.ABI_VERSION) + ' ? 0 : 1;\n}\n')
+    exe = tmp_path / 'layout'
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-I', os.path.join(ROOT, 'include'), str(src), '-o', str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    got = [int(x) for x in out]
+    want = [ctypes.sizeof(capi.YoloppParams), ctypes.sizeof(capi.YoloppOutputs), ctypes.sizeof(capi.YoloppPlanInfo),
+            capi.YoloppParams.base_anchors.offset, capi.YoloppOutputs.cls_offsets.offset,
+            capi.YoloppPlanInfo.workspace_bytes.offset, capi.YoloppPlanInfo.decode_tile_positions.offset]
+    assert got == want, (got, want)
+
+
 def test_planning_calls_need_no_device():
     lib = capi.load_library()
     p = cases.build_params(dict(cases.CASES['csp608_sparse'], batch=64))
