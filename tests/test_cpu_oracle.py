@@ -135,6 +135,19 @@ def test_oracle_batched_nms_regimes():
     d2, k2 = oracle.batched_nms(boxes, scores, idxs, 0.5, split_thr=10)
     np.testing.assert_array_equal(k1, k2)  # boxes are >= 0 so class offset ranges never overlap
     np.testing.assert_array_equal(d1, d2)
+    # independent implementation of the classes-independent regime (the >= split_thr branch, written by another hand):
+    # torchvision.ops.batched_nms, both of its strategies (coordinate trick below 4000 boxes, per-class loop above)
+    torch = pytest.importorskip('torch')
+    tv = pytest.importorskip('torchvision')
+    for nn, ncls, thr in ((600, 7, 0.5), (600, 7, 0.2), (5000, 40, 0.45)):
+        xy2 = rng.rand(nn, 2).astype(np.float32) * 100
+        wh2 = rng.rand(nn, 2).astype(np.float32) * 40 + 1
+        b2 = np.concatenate([xy2, xy2 + wh2], 1)
+        s2 = rng.permutation(nn).astype(np.float32) / nn  # no ties
+        i2 = rng.randint(0, ncls, nn)
+        _, kk = oracle.batched_nms(b2, s2, i2, thr, split_thr=10)
+        ref = tv.ops.batched_nms(torch.from_numpy(b2), torch.from_numpy(s2), torch.from_numpy(i2), thr).numpy()
+        np.testing.assert_array_equal(kk, ref)
     d0, k0 = oracle.batched_nms(np.zeros((0, 4), np.float32), np.zeros(0, np.float32), np.zeros(0, np.int64), 0.5)
     assert d0.shape == (0, 5) and k0.shape == (0, )
     d3, k3 = oracle.batched_nms(boxes[:1], scores[:1], idxs[:1], 0.5)
